@@ -1,0 +1,16 @@
+"""gpemsr_b200: B200-native (sm_100a) kernels for GPEMSR's inference hot path.
+
+Host-side mirrors of the reference's operators for this path (same names, argument
+meaning and error behaviour) over the C ABI in ``include/gpemsr_b200.h``:
+
+  * ``flow_warp``                       -- BasicSR ``flow_warp`` (SpyNet's warping operator)
+  * ``Codebook`` (``forward`` / ``inference_lr``)   -- model/codebook.py
+  * ``Decoder`` (``forward`` / ``multi_scale_feat_calculate``) -- model/decoder.py
+  * ``SRTail``                          -- model/GPEMSR.py:441-455
+
+The CUDA library is mandatory: nothing here falls back to PyTorch or the CPU.
+"""
+from ._lib import GpemsrError, LIB_PATH, kernel_launches, lib  # noqa: F401
+from .flow_warp import flow_warp  # noqa: F401
+
+__all__ = ['flow_warp', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']

@@ -1,0 +1,79 @@
+"""ctypes binding of libgpemsr_b200.so (the C ABI declared in include/gpemsr_b200.h).
+
+There is no fallback: if the shared library is missing, or the device is not
+sm_100-class, calls raise.  PyTorch is used above this layer only for device
+memory and streams (``tensor.data_ptr()``, ``torch.cuda.current_stream()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libgpemsr_b200.so')
+
+ERRORS = {0: 'OK', -1: 'BAD_SHAPE', -2: 'BAD_ALIGN', -3: 'UNSUPPORTED_ARCH', -4: 'CUDA', -5: 'WORKSPACE',
+          -6: 'UNSUPPORTED'}
+
+
+class GpemsrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'gpemsr_b200: {ERRORS.get(code, code)}: {msg}')
+        self.code = code
+
+
+_p, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+_f = C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/gpemsr_b200.h declares
+SIGNATURES = {
+    'gpemsr_version': (_i, []),
+    'gpemsr_last_error_string': (C.c_char_p, []),
+    'gpemsr_device_check': (_i, [_i]),
+    'gpemsr_kernel_launches': (_i64, []),
+    'gpemsr_flow_warp': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    'gpemsr_vq_workspace_bytes': (_sz, [_i64, _i, _i]),
+    'gpemsr_vq_lookup_nchw': (_i, [_p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
+    'gpemsr_logits_argmax_gather': (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    'gpemsr_argmax_gather': (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
+    'gpemsr_selftest_gemm_workspace_bytes': (_sz, [_i64, _i, _i]),
+    'gpemsr_selftest_gemm': (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    'gpemsr_selftest_gemm_status': (_i, [_p, _i64, _i, _i, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpemsrError(-6, f'{LIB_PATH} is missing: build it with `python -m gpemsr_b200.build` '
+                                  '(there is no CPU or PyTorch fallback)')
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name, None)
+            if fn is None:      # stale build: calling the symbol raises AttributeError; tests/test_capi.py checks the full list
+                continue
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GpemsrError(rc, lib().gpemsr_last_error_string().decode())
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def kernel_launches():
+    return int(lib().gpemsr_kernel_launches())

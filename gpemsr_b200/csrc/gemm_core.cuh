@@ -1,0 +1,199 @@
+// Warp-specialised tcgen05 GEMM core shared by the VQ lookup, the implicit-GEMM convolutions and the
+// non-local attention:   D[m, n] = sum_t sum_k  A[m + a_row_off[t], k] * B_t[n, k]      (fp32 accumulate in TMEM)
+//
+// Operand format ("K8-blocked", bf16): a matrix X[rows, K] is stored as  [K/8][rows_alloc][8]  i.e. for every group
+// of 8 consecutive k a column of 16-byte row cells.  A [rows x 8k] slab is therefore ONE contiguous run in HBM
+// (fetched by one cp.async.bulk, no tensor map needed) and lands in shared memory exactly in the tcgen05
+// K-major SWIZZLE_NONE canonical layout (core matrix = 8 rows x 16 B, SBO = 128 B, LBO = rows*16 B).
+// Because rows are 16-byte cells at a uniform stride, a row SHIFT of the A operand is just a different start
+// address -- that is what turns a 3x3 convolution over a zero-padded, flattened image into 9 shifted GEMMs
+// with no im2col buffer (conv_igemm.cu).
+//
+// Precision: SPLIT == 1 -> one bf16 pass.  SPLIT == 3 -> operands carry (hi, lo) bf16 planes with
+// hi = bf16(x), lo = bf16(x - hi) and three MMAs hi*hi + lo*hi + hi*lo are accumulated (error ~2^-16 relative):
+// fp32-faithful convolutions on the bf16 tensor pipe at 1/3 of its rate (still ~5x the fp32 CUDA-core rate).
+//
+// Roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
+// (each owns the TMEM lane quarter (warp % 4)).  Pipelines: NSTAGE smem stages (full/empty mbarriers) and two
+// TMEM accumulator buffers (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Persistent: CTA b processes tiles b, b+grid, ...
+#pragma once
+#include "sm100.cuh"
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_TAPS = 49;
+
+struct Operands {
+  const __nv_bfloat16* a_hi;   // [K/8][a_rows][8]
+  const __nv_bfloat16* a_lo;   // same shape, only read when SPLIT == 3
+  const __nv_bfloat16* b_hi;   // [taps][K/8][b_rows][8]
+  const __nv_bfloat16* b_lo;
+  long long a_rows;            // allocated rows of A (k-chunk stride = a_rows * 16 B)
+  int b_rows;                  // allocated rows of B per tap (>= n_tiles * BLOCK_N)
+  int k;                       // reduction length per tap, multiple of BLOCK_K
+  int taps;                    // number of shifted GEMMs accumulated into one tile
+  int a_row_off[MAX_TAPS];     // row shift of A for every tap
+  long long m_tiles;           // number of 128-row tiles
+  int n_tiles;                 // number of BLOCK_N column tiles
+  long long a_row0;            // row of A that tile 0 / row 0 maps to (so shifts may be negative)
+  int* err_flag;               // device int, set non-zero on a pipeline time-out
+};
+
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE>
+struct Config {
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N");
+  static_assert(BLOCK_K % 16 == 0, "UMMA K = 16 for bf16");
+  static_assert(SPLIT == 1 || SPLIT == 3, "SPLIT");
+  static constexpr int PLANES = SPLIT == 3 ? 2 : 1;
+  static constexpr int KCH = BLOCK_K / 8;                           // 16-byte k-cells per stage
+  static constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_PLANE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* barriers, tmem ptr, epilogue scratch */;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+struct Barriers {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// Epilogue concept:
+//   struct Epi { __device__ void tile(uint32_t tmem_acc /*lane-adjusted*/, long long m_tile, int n_tile,
+//                                     int row_in_tile /*0..127 = this thread's row*/, int warp_q); };
+// The epilogue reads its accumulator with sm100::tmem_ld_32x32(tmem_acc + col, regs) and must finish with the
+// loads retired (tmem_ld_wait) before returning.
+
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
+  using Cfg = Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stages = smem;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + NSTAGE * Cfg::STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_tiles = op.m_tiles * op.n_tiles;
+  const int kiters_per_tap = op.k / BLOCK_K;
+  const int kiters = op.taps * kiters_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], 4); }
+    sm100::fence_mbar_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<Cfg::TMEM_COLS>(&bars->tmem_base);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer: bulk copies HBM/L2 -> smem =====================
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (long long t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      const long long m_tile = t / op.n_tiles;
+      const int n_tile = (int)(t % op.n_tiles);
+      for (int it = 0; it < kiters && ok; ++it) {
+        const int tap = it / kiters_per_tap, kc0 = (it % kiters_per_tap) * Cfg::KCH;
+        ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+        if (!ok) break;
+        uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+        __syncwarp();
+        const long long a_row = op.a_row0 + m_tile * BLOCK_M + op.a_row_off[tap];
+        // one 16-byte-cell column per copy: A cell column = BLOCK_M*16 B, B cell column = BLOCK_N*16 B
+        for (int c = lane; c < Cfg::PLANES * Cfg::KCH * 2; c += 32) {
+          const int is_b = c / (Cfg::PLANES * Cfg::KCH);
+          const int r = c % (Cfg::PLANES * Cfg::KCH);
+          const int plane = r / Cfg::KCH, kc = r % Cfg::KCH;
+          if (!is_b) {
+            const __nv_bfloat16* src = (plane ? op.a_lo : op.a_hi) + ((long long)(kc0 + kc) * op.a_rows + a_row) * 8;
+            sm100::bulk_g2s(sa + plane * Cfg::A_PLANE_BYTES + kc * (BLOCK_M * 16), src, BLOCK_M * 16, &bars->full[stage]);
+          } else {
+            const long long brow = ((long long)tap * (op.k / 8) + (kc0 + kc)) * op.b_rows + (long long)n_tile * BLOCK_N;
+            const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + brow * 8;
+            sm100::bulk_g2s(sb + plane * Cfg::B_PLANE_BYTES + kc * (BLOCK_N * 16), src, BLOCK_N * 16, &bars->full[stage]);
+          }
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    for (long long t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+      if (!ok) break;
+      sm100::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+      for (int it = 0; it < kiters && ok; ++it) {
+        ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        if (sm100::elect_one()) {
+          const uint32_t sa = sm100::smem_u32(stages + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < BLOCK_K / 16; ++k16) {
+            // one UMMA consumes two 16-byte k-cells: advance the start address by 2 cell columns per step
+            const uint64_t a_hi = sm100::smem_desc_kmajor_noswz(sa + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
+            const uint64_t b_hi = sm100::smem_desc_kmajor_noswz(sb + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+            sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | k16) != 0);
+            if constexpr (SPLIT == 3) {
+              const uint64_t a_lo = sm100::smem_desc_kmajor_noswz(sa + Cfg::A_PLANE_BYTES + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
+              const uint64_t b_lo = sm100::smem_desc_kmajor_noswz(sb + Cfg::B_PLANE_BYTES + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+              sm100::umma_bf16(tmem_acc, a_lo, b_hi, idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
+            }
+          }
+          sm100::umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
+          if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    for (long long t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      const long long m_tile = t / op.n_tiles;
+      const int n_tile = (int)(t % op.n_tiles);
+      ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+      if (!ok) break;
+      sm100::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epi.tile(tmem_acc, m_tile, n_tile, row, q);
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+    }
+  }
+
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace gemm

@@ -1,0 +1,51 @@
+"""Quick single-GPU microbenchmarks (CUDA events, L2-flushed) used while developing; bench.py is the contract."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+import gpemsr_b200
+
+
+def timeit(fn, iters=10, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def flow_warp_bench():
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    out = []
+    for c, s in ((64, 156), (64, 312), (64, 624), (64, 1250), (3, 128), (3, 640)):
+        x = torch.randn(1, c, s, s, device='cuda')
+        fl = 2.0 * torch.randn(1, s, s, 2, device='cuda')
+        fl = torch.nn.functional.avg_pool2d(fl.permute(0, 3, 1, 2), 5, 1, 2).permute(0, 2, 3, 1).contiguous()
+        med, best = timeit(lambda: gpemsr_b200.flow_warp(x, fl, 'bilinear', 'border'), flush=flush)
+        byt = 8 * c * s * s + 8 * s * s
+        from oracle.flow_warp import flow_warp_torch
+        med_t, _ = timeit(lambda: flow_warp_torch(x, fl, 'bilinear', 'border'), flush=flush)
+        white = 4.0 * torch.randn(1, s, s, 2, device='cuda')
+        med_w, _ = timeit(lambda: gpemsr_b200.flow_warp(x, white, 'bilinear', 'border'), flush=flush)
+        out.append(dict(op='flow_warp', c=c, s=s, ms=med, ms_best=best, gbs=byt / med / 1e6, frac=byt / med / 1e6 / 6550.1,
+                        ms_white=med_w, gbs_white=byt / med_w / 1e6, torch_grid_sample_ms=med_t))
+    return out
+
+
+if __name__ == '__main__':
+    torch.cuda.init()
+    res = []
+    if 'flow' in sys.argv[1:] or len(sys.argv) == 1:
+        res += flow_warp_bench()
+    for r in res:
+        print(json.dumps(r))
