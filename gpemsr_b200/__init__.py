@@ -12,5 +12,8 @@ The CUDA library is mandatory: nothing here falls back to PyTorch or the CPU.
 """
 from ._lib import GpemsrError, LIB_PATH, kernel_launches, lib  # noqa: F401
 from .flow_warp import flow_warp  # noqa: F401
+from .codebook import Codebook, argmax_gather, logits_argmax_gather, vq_lookup  # noqa: F401
+from .decoder import Decoder  # noqa: F401
+from .sr_tail import SRTail  # noqa: F401
 
-__all__ = ['flow_warp', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']
+__all__ = ['flow_warp', 'Decoder', 'SRTail', 'Codebook', 'vq_lookup', 'logits_argmax_gather', 'argmax_gather', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']

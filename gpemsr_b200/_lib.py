@@ -36,6 +36,15 @@ SIGNATURES = {
     'gpemsr_vq_lookup_nchw': (_i, [_p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     'gpemsr_logits_argmax_gather': (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
     'gpemsr_argmax_gather': (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
+    'gpemsr_igemm': (_i, [_p, _p]),
+    'gpemsr_act_pack_nchw': (_i, [_p, _i, _p, _i, _p, _p, _p, _p]),
+    'gpemsr_act_unpack_nchw': (_i, [_p, _i, _p, _i, _p, _p]),
+    'gpemsr_pack_weights': (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _p, _p, _p]),
+    'gpemsr_gn_stats': (_i, [_p, _i, _p, _p, _p]),
+    'gpemsr_gn_scale_shift': (_i, [_p, _p, _p, _i, _i, _i, C.c_double, _f, _p, _p]),
+    'gpemsr_affine_act': (_i, [_p, _i, _p, _p, _i, _f, _p, _p, _p, _p, _p, _p]),
+    'gpemsr_softmax_rows_blocked': (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    'gpemsr_add_bilinear_base': (_i, [_p, _i, _i, _i, _i, _p, _p]),
     'gpemsr_selftest_gemm_workspace_bytes': (_sz, [_i64, _i, _i]),
     'gpemsr_selftest_gemm': (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _sz, _p]),
     'gpemsr_selftest_gemm_status': (_i, [_p, _i64, _i, _i, _p]),
@@ -67,7 +76,11 @@ def check(rc):
 
 
 def ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
 
 
 def stream_ptr():

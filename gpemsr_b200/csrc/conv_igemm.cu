@@ -1,0 +1,595 @@
+// a-3 / a-4: implicit-GEMM convolution family on the tcgen05 GEMM core.
+//
+// Replaces the cuDNN / cuBLAS calls of Decoder / ResidualBlock / UpBlock / NonLocalBlock (model/decoder.py:37-57,
+// model/blocks.py:8-83) and of the SR tail (model/GPEMSR.py:441-455).  One entry point, gpemsr_igemm(), covers
+//   * Conv2d 3x3 / 1x1, stride 1 (9 or 1 row-shifted GEMMs over the zero-ringed, flattened activation),
+//   * ConvTranspose2d(k3, s2, p1, op1) as four output-parity phases with 1/2/2/4 taps (no zero-stuffed MACs),
+//   * the attention products q^T k and P v^T and the Linear head (plain GEMMs on compact rows),
+// with the epilogue fused: scale, bias (per column or per row), ReLU / LeakyReLU, residual add, PixelShuffle(2),
+// parity-phase scatter, and stores as fp32 master, (hi, lo) bf16 operand planes for the next layer, NCHW or row-major.
+#include "capi_common.h"
+#include "gemm_core.cuh"
+#include <algorithm>
+
+namespace {
+
+struct Geom {
+  int n, h, w, padded;
+  long long r_img, m0, rows_alloc;
+  __host__ __device__ int wp() const { return padded ? w + 2 : w; }
+};
+Geom to_geom(const gpemsr_geom_t& g) { return Geom{g.n, g.h, g.w, g.padded, g.r_img, g.m0, g.rows_alloc}; }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == GPEMSR_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == GPEMSR_ACT_LRELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// decode a row of geometry g (relative to g.m0) into (image, y, x); false for ring / tail rows
+__device__ __forceinline__ bool decode_row(const Geom& g, long long rel, int& img, int& y, int& x) {
+  img = (int)(rel / g.r_img);
+  const long long q = rel - (long long)img * g.r_img;
+  if (g.padded) {
+    const int wp = g.w + 2;
+    const int yp = (int)(q / wp), xp = (int)(q - (long long)yp * wp);
+    y = yp - 1; x = xp - 1;
+    return img < g.n && yp >= 1 && yp <= g.h && xp >= 1 && xp <= g.w;
+  }
+  y = (int)(q / g.w); x = (int)(q - (long long)y * g.w);
+  return img < g.n && q < (long long)g.h * g.w;
+}
+__device__ __forceinline__ long long place_row(const Geom& g, int img, int y, int x) {
+  return g.m0 + (long long)img * g.r_img + (g.padded ? (long long)(y + 1) * (g.w + 2) + (x + 1) : (long long)y * g.w + x);
+}
+
+template <int BLOCK_N>
+struct EpiConv {
+  Geom ag, og;
+  int n_cols;
+  float scale;
+  const float* bias;
+  int bias_per_row, act;
+  float slope;
+  const float* residual;
+  int up, py, px, pixel_shuffle, c_off;
+  float* out_f32;
+  __nv_bfloat16 *out_hi, *out_lo;
+  float* out_nchw;
+  int nchw_c;
+  float* out_rowmajor;
+  long long ld;
+
+  struct State {
+    bool init = false, valid = false;
+    int img = 0, y = 0, x = 0;
+    float row_bias = 0.f;
+  };
+
+  // one cell = 8 consecutive output channels of one output pixel
+  __device__ __forceinline__ void store_cell(const State& st, float (&v)[8], int col0, int dy, int dx) const {
+    const int Y = up * st.y + py + dy, X = up * st.x + px + dx;
+    const int ch0 = c_off + col0;
+    if (out_f32 || out_hi || residual) {
+      const long long orow = place_row(og, st.img, Y, X);
+      const size_t cell = ((size_t)(ch0 >> 3) * og.rows_alloc + orow) * 8;
+      if (residual) {
+        const float4 r0 = *reinterpret_cast<const float4*>(residual + cell), r1 = *reinterpret_cast<const float4*>(residual + cell + 4);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+      }
+      if (out_f32) {
+        *reinterpret_cast<float4*>(out_f32 + cell) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(out_f32 + cell + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (out_hi) {
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(out_hi + cell) = hi;
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + cell) = lo;
+      }
+    }
+    if (out_nchw) {
+      const long long Ho = (long long)up * ag.h, Wo = (long long)up * ag.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (ch0 + j < nchw_c) out_nchw[(((long long)st.img * nchw_c + ch0 + j) * Ho + Y) * Wo + X] = v[j];
+    }
+  }
+
+  template <int CHUNK>
+  __device__ __forceinline__ void chunk(const State& st, const uint32_t (&r)[CHUNK], int col0, long long rel) const {
+    float f[CHUNK];
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      const int col = col0 + j;
+      float v = scale * __uint_as_float(r[j]);
+      v += bias_per_row ? st.row_bias : ((bias && col < n_cols) ? __ldg(bias + col) : 0.f);
+      f[j] = col < n_cols ? apply_act(v, act, slope) : 0.f;
+    }
+    if (out_rowmajor) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; j += 4)
+        *reinterpret_cast<float4*>(out_rowmajor + rel * ld + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+    if (!(out_f32 || out_hi || out_nchw)) return;
+    if (pixel_shuffle) {
+      if constexpr (CHUNK == 32) {     // 32 columns = 8 channels x (dy, dx)
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = f[4 * j + sub];
+          store_cell(st, v, col0 >> 2, sub >> 1, sub & 1);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < CHUNK / 8; ++g) {
+        if (col0 + 8 * g >= n_cols) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = f[8 * g + j];
+        store_cell(st, v, col0 + 8 * g, 0, 0);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int, int row, int) const {
+    const long long rel = m_tile * gemm::BLOCK_M + row;
+    if (!st.init) {
+      st.init = true;
+      st.valid = decode_row(ag, rel, st.img, st.y, st.x);
+      if (bias_per_row && st.valid) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
+    }
+    constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+      uint32_t r[CHUNK];
+      if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + c0, r);
+      else sm100::tmem_ld_32x16(tmem_acc + c0, r);
+      sm100::tmem_ld_wait();
+      const int col0 = n_tile * BLOCK_N + c0;
+      if (st.valid && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
+    }
+  }
+};
+
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE>
+int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t s) {
+  using Cfg = gemm::Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
+  using Epi = EpiConv<BLOCK_N>;
+  Epi e;
+  e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
+  e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
+  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.c_off = d.c_off;
+  e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
+  e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
+  auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, Epi>;
+  GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int sms = gpemsr::num_sms();
+  const long long gx = std::min<long long>(op.m_tiles, sms);
+  long long gy = 1;
+  if (op.m_tiles < sms) gy = std::min<long long>(op.n_tiles, (sms + op.m_tiles - 1) / op.m_tiles);
+  kern<<<dim3((unsigned)gx, (unsigned)gy), gemm::NUM_THREADS, Cfg::SMEM_BYTES, s>>>(op, e);
+  GPEMSR_LAUNCH_OK("gemm_kernel<EpiConv>");
+  return GPEMSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pack / unpack
+__global__ void act_pack_nchw_kernel(const float* __restrict__ x, int c, Geom g, int c_off, float* __restrict__ f32,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long hw = (long long)g.h * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (img, cell, pixel), pixel fastest
+  const int cells = (c + 7) / 8;
+  if (t >= (long long)g.n * cells * hw) return;
+  const long long p = t % hw;
+  const int cc = (int)((t / hw) % cells), img = (int)(t / (hw * cells));
+  const int y = (int)(p / g.w), xx = (int)(p % g.w);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cc * 8 + j;
+    v[j] = ch < c ? __ldg(x + ((long long)img * c + ch) * hw + p) : 0.f;
+  }
+  const size_t cell = ((size_t)((c_off >> 3) + cc) * g.rows_alloc + place_row(g, img, y, xx)) * 8;
+  if (f32) {
+    *reinterpret_cast<float4*>(f32 + cell) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(f32 + cell + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (hi) {
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(hi + cell) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + cell) = l;
+  }
+}
+
+__global__ void act_unpack_nchw_kernel(const float* __restrict__ f32, int c, Geom g, int c_off, float* __restrict__ x) {
+  const long long hw = (long long)g.h * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cells = (c + 7) / 8;
+  if (t >= (long long)g.n * cells * hw) return;
+  const long long p = t % hw;
+  const int cc = (int)((t / hw) % cells), img = (int)(t / (hw * cells));
+  const int y = (int)(p / g.w), xx = (int)(p % g.w);
+  const size_t cell = ((size_t)((c_off >> 3) + cc) * g.rows_alloc + place_row(g, img, y, xx)) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(f32 + cell), b = *reinterpret_cast<const float4*>(f32 + cell + 4);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cc * 8 + j;
+    if (ch < c) x[((long long)img * c + ch) * hw + p] = v[j];
+  }
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int n, int k, long long n_stride, long long k_stride, int taps,
+                                    const int* __restrict__ tap_src, int b_rows, int k_pad, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (tap, kc, row)
+  const int kcs = k_pad / 8;
+  if (t >= (long long)taps * kcs * b_rows) return;
+  const int row = (int)(t % b_rows), kc = (int)((t / b_rows) % kcs), tap = (int)(t / ((long long)b_rows * kcs));
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kk = kc * 8 + j;
+    v[j] = (row < n && kk < k) ? __ldg(w + row * n_stride + kk * k_stride + tap_src[tap]) : 0.f;
+  }
+  uint4 h, l;
+  split8(v, h, l);
+  *reinterpret_cast<uint4*>(hi + (size_t)t * 8) = h;
+  if (lo) *reinterpret_cast<uint4*>(lo + (size_t)t * 8) = l;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// per-channel sum / sum of squares over an image's rows (ring and tail rows are zero by construction)
+__global__ void gn_stats_kernel(const float* __restrict__ x, int c, Geom g, double* __restrict__ sums) {
+  const int cc = blockIdx.x, img = blockIdx.y;
+  const long long r0 = g.m0 + (long long)img * g.r_img;
+  const float* base = x + ((size_t)cc * g.rows_alloc + r0) * 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = (long long)blockIdx.z * blockDim.x + threadIdx.x; r < g.r_img; r += (long long)gridDim.z * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(base + r * 8), b = *reinterpret_cast<const float4*>(base + r * 8 + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+  }
+  __shared__ double red[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double ds = s[j], dq = q[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dq += __shfl_xor_sync(0xffffffffu, dq, o); }
+    if (lane == 0) { red[warp][2 * j] = ds; red[warp][2 * j + 1] = dq; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0;
+    for (int wv = 0; wv < (blockDim.x >> 5); ++wv) t += red[wv][threadIdx.x];
+    const int ch = cc * 8 + (threadIdx.x >> 1);
+    if (ch < c) atomicAdd(sums + ((size_t)img * c + ch) * 2 + (threadIdx.x & 1), t);
+  }
+}
+
+__global__ void gn_scale_shift_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      int n, int c, int groups, double count, float eps, float* __restrict__ ss) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * c) return;
+  const int img = t / c, ch = t % c, cpg = c / groups, g0 = (ch / cpg) * cpg;
+  double s = 0, q = 0;
+  for (int j = 0; j < cpg; ++j) { s += sums[((size_t)img * c + g0 + j) * 2]; q += sums[((size_t)img * c + g0 + j) * 2 + 1]; }
+  const double cnt = count * cpg, mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[ch] * rstd;
+  ss[(size_t)t * 2] = sc;
+  ss[(size_t)t * 2 + 1] = beta[ch] - (float)mean * sc;
+}
+
+// y = act(x * scale + shift) (+ residual); re-rowed into `og` when it differs from `g`
+__global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, const float* __restrict__ ss, int act, float slope,
+                                  const float* __restrict__ residual, Geom og, float* __restrict__ out_f32,
+                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const long long hw = (long long)g.h * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (img, cell, pixel)
+  const int cells = (c + 7) / 8;
+  if (t >= (long long)g.n * cells * hw) return;
+  const long long p = t % hw;
+  const int cc = (int)((t / hw) % cells), img = (int)(t / (hw * cells));
+  const int y = (int)(p / g.w), xx = (int)(p % g.w);
+  const size_t cell = ((size_t)cc * g.rows_alloc + place_row(g, img, y, xx)) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(x + cell), b = *reinterpret_cast<const float4*>(x + cell + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cc * 8 + j;
+    if (ss && ch < c) {
+      const float2 s2 = __ldg(reinterpret_cast<const float2*>(ss) + (size_t)img * c + ch);
+      v[j] = fmaf(v[j], s2.x, s2.y);
+    }
+    v[j] = ch < c ? apply_act(v[j], act, slope) : 0.f;
+  }
+  const size_t ocell = ((size_t)cc * og.rows_alloc + place_row(og, img, y, xx)) * 8;
+  if (residual) {
+    const float4 r0 = *reinterpret_cast<const float4*>(residual + ocell), r1 = *reinterpret_cast<const float4*>(residual + ocell + 4);
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+  }
+  if (out_f32) {
+    *reinterpret_cast<float4*>(out_f32 + ocell) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(out_f32 + ocell + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (out_hi) {
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(out_hi + ocell) = h;
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + ocell) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ softmax
+__global__ void softmax_stats_kernel(const float* __restrict__ s, long long t, long long ld, float* __restrict__ stats) {
+  const long long row = blockIdx.x;
+  const float* p = s + row * ld;
+  float mx = -INFINITY;
+  for (long long j = threadIdx.x; j < t; j += blockDim.x) mx = fmaxf(mx, p[j]);
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (long long j = threadIdx.x; j < t; j += blockDim.x) sum += expf(p[j] - mx);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+    stats[row * 2] = mx;
+    stats[row * 2 + 1] = tot;
+  }
+}
+
+// p = exp(s - max) / sum -> (hi, lo) cells, transposed at 16-byte-cell granularity through shared memory:
+// reads are coalesced along j (a warp reads 32 consecutive 32-byte score groups of one row), writes along i.
+__global__ void softmax_write_kernel(const float* __restrict__ s, long long t, long long ld, long long t_pad,
+                                     const float* __restrict__ stats, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+  __shared__ uint4 th[32][33], tl[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 32 threads
+  const long long i = (long long)blockIdx.y * 32 + ty, jc = (long long)blockIdx.x * 32 + tx;
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (i < t && jc * 8 < t) {
+    const float mx = stats[i * 2], inv_den = stats[i * 2 + 1];
+    const float4 a = *reinterpret_cast<const float4*>(s + i * ld + jc * 8), b = *reinterpret_cast<const float4*>(s + i * ld + jc * 8 + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (jc * 8 + j < t) ? expf(x[j] - mx) / inv_den : 0.f;
+  }
+  uint4 h, l;
+  split8(v, h, l);
+  th[ty][tx] = h; tl[ty][tx] = l;
+  __syncthreads();
+  const long long oi = (long long)blockIdx.y * 32 + tx, ojc = (long long)blockIdx.x * 32 + ty;   // lanes along i
+  if (oi < t_pad && ojc < t_pad / 8) {
+    *reinterpret_cast<uint4*>(p_hi + ((size_t)ojc * t_pad + oi) * 8) = th[tx][ty];
+    if (p_lo) *reinterpret_cast<uint4*>(p_lo + ((size_t)ojc * t_pad + oi) * 8) = tl[tx][ty];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear base
+// ATen upsample_bilinear2d, align_corners=False, scale_factor given: src = (dst + 0.5) / scale - 0.5, clamped at 0
+__global__ void add_bilinear_base_kernel(const float* __restrict__ xc, int n, int h, int w, int scale, float* __restrict__ out) {
+  const long long Ho = (long long)h * scale, Wo = (long long)w * scale;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * Ho * Wo) return;
+  const int ox = (int)(t % Wo), oy = (int)((t / Wo) % Ho), img = (int)(t / (Wo * Ho));
+  const float rs = 1.0f / (float)scale;
+  float sy = rs * ((float)oy + 0.5f) - 0.5f, sx = rs * ((float)ox + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* p = xc + (long long)img * h * w;
+  const float v = hy * (hx * p[(long long)y0 * w + x0] + lx * p[(long long)y0 * w + x1]) +
+                  ly * (hx * p[(long long)y1 * w + x0] + lx * p[(long long)y1 * w + x1]);
+  out[t] += v;
+}
+
+int check_geom(const gpemsr_geom_t& g, const char* what) {
+  using namespace gpemsr;
+  if (g.n <= 0 || g.h <= 0 || g.w <= 0 || g.r_img <= 0 || (g.r_img % gemm::BLOCK_M) != 0)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: bad geometry n=%d h=%d w=%d r_img=%lld", what, g.n, g.h, g.w, (long long)g.r_img);
+  const long long need = g.padded ? (long long)(g.h + 2) * (g.w + 2) : (long long)g.h * g.w;
+  const long long margin = g.padded ? g.w + 3 : 0;
+  if (g.r_img < need || g.m0 < margin || g.rows_alloc < g.m0 + (long long)g.n * g.r_img + margin)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: geometry does not leave room for the zero ring / tap shifts", what);
+  return GPEMSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  if (!dp) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null descriptor");
+  const gpemsr_igemm_desc_t& d = *dp;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if ((rc = check_geom(d.a_geom, "igemm(a)")) != GPEMSR_OK) return rc;
+  if ((d.out_f32 || d.out_hi || d.residual) && (rc = check_geom(d.o_geom, "igemm(out)")) != GPEMSR_OK) return rc;
+  if (d.taps < 1 || d.taps > gemm::MAX_TAPS || d.k_pad <= 0 || d.k_pad % 64 || d.n_cols <= 0)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: taps=%d k_pad=%d n_cols=%d", d.taps, d.k_pad, d.n_cols);
+  if (d.split != 1 && d.split != 3) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: split must be 1 or 3");
+  if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || !d.b_lo))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
+  if (d.up != 1 && d.up != 2) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: up must be 1 or 2");
+  if (d.pixel_shuffle && (d.up != 2 || d.n_cols % 32)) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: pixel_shuffle needs up=2 and n_cols %% 32 == 0");
+  if (d.c_off % 8) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: c_off must be a multiple of 8");
+  if (d.out_rowmajor && (d.ld % 4)) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: ld must be a multiple of 4");
+  if (!d.err_flag) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: err_flag is required");
+
+  const int block_n = d.n_cols <= 16 && !d.pixel_shuffle ? 16 : d.n_cols <= 64 ? 64 : d.n_cols <= 128 ? 128 : 256;
+  gemm::Operands op{};
+  op.a_hi = (const __nv_bfloat16*)d.a_hi; op.a_lo = (const __nv_bfloat16*)d.a_lo;
+  op.b_hi = (const __nv_bfloat16*)d.b_hi; op.b_lo = (const __nv_bfloat16*)d.b_lo;
+  op.a_rows = d.a_geom.rows_alloc; op.b_rows = d.b_rows; op.k = d.k_pad; op.taps = d.taps;
+  const int wp = d.a_geom.padded ? d.a_geom.w + 2 : d.a_geom.w;
+  for (int t = 0; t < d.taps; ++t) {
+    if (!d.a_geom.padded && (d.tap_dy[t] || d.tap_dx[t])) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: shifted taps need a padded geometry");
+    if (abs(d.tap_dy[t]) > 1 || abs(d.tap_dx[t]) > 1) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: taps beyond +-1 need a wider ring");
+    op.a_row_off[t] = d.tap_dy[t] * wp + d.tap_dx[t];
+  }
+  op.m_tiles = (long long)d.a_geom.n * d.a_geom.r_img / gemm::BLOCK_M;
+  op.n_tiles = (d.n_cols + block_n - 1) / block_n;
+  if (d.b_rows < op.n_tiles * block_n) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: b_rows=%d < %d", d.b_rows, op.n_tiles * block_n);
+  op.a_row0 = d.a_geom.m0; op.err_flag = d.err_flag;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d.split == 3) {
+    switch (block_n) {
+      case 16: return launch<16, 32, 3, 6>(op, d, s);
+      case 64: return launch<64, 32, 3, 6>(op, d, s);
+      case 128: return launch<128, 32, 3, 5>(op, d, s);
+      default: return launch<256, 32, 3, 4>(op, d, s);
+    }
+  }
+  switch (block_n) {
+    case 16: return launch<16, 64, 1, 6>(op, d, s);
+    case 64: return launch<64, 64, 1, 6>(op, d, s);
+    case 128: return launch<128, 64, 1, 5>(op, d, s);
+    default: return launch<256, 64, 1, 4>(op, d, s);
+  }
+}
+
+int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* g, int c_off, float* f32, void* hi, void* lo,
+                         gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!g || !x || c <= 0 || c_off % 8) return set_error(GPEMSR_ERR_BAD_SHAPE, "act_pack_nchw: bad arguments");
+  if ((rc = check_geom(*g, "act_pack_nchw")) != GPEMSR_OK) return rc;
+  const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
+  act_pack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c, to_geom(*g), c_off, f32,
+                                                                                        (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  GPEMSR_LAUNCH_OK("act_pack_nchw_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int c_off, float* x, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!g || !x || !f32 || c <= 0 || c_off % 8) return set_error(GPEMSR_ERR_BAD_SHAPE, "act_unpack_nchw: bad arguments");
+  if ((rc = check_geom(*g, "act_unpack_nchw")) != GPEMSR_OK) return rc;
+  const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
+  act_unpack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f32, c, to_geom(*g), c_off, x);
+  GPEMSR_LAUNCH_OK("act_unpack_nchw_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_pack_weights(const float* w, int n, int k, int64_t n_stride, int64_t k_stride, int taps, const int32_t* tap_src,
+                        int b_rows, int k_pad, void* hi, void* lo, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!w || !hi || !tap_src || n <= 0 || k <= 0 || taps <= 0 || b_rows < n || k_pad < k || k_pad % 8)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "pack_weights: bad arguments");
+  const long long total = (long long)taps * (k_pad / 8) * b_rows;
+  pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, n, k, n_stride, k_stride, taps, tap_src, b_rows, k_pad, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  GPEMSR_LAUNCH_OK("pack_weights_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_gn_stats(const float* x_f32, int c, const gpemsr_geom_t* g, double* chan_sums, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x_f32 || !g || !chan_sums || c <= 0) return set_error(GPEMSR_ERR_BAD_SHAPE, "gn_stats: bad arguments");
+  if ((rc = check_geom(*g, "gn_stats")) != GPEMSR_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  GPEMSR_CUDA_OK(cudaMemsetAsync(chan_sums, 0, (size_t)g->n * c * 2 * sizeof(double), s));
+  const int cells = (c + 7) / 8;
+  long long splits = std::max<long long>(1, std::min<long long>((g->r_img + 256 * 8 - 1) / (256 * 8),
+                                                                (4LL * num_sms() + (long long)cells * g->n - 1) / ((long long)cells * g->n)));
+  gn_stats_kernel<<<dim3(cells, g->n, (unsigned)splits), 256, 0, s>>>(x_f32, c, to_geom(*g), chan_sums);
+  GPEMSR_LAUNCH_OK("gn_stats_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_gn_scale_shift(const double* chan_sums, const float* gamma, const float* beta, int n, int c, int groups,
+                          double count_per_channel, float eps, float* scale_shift, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!chan_sums || !gamma || !beta || !scale_shift || n <= 0 || c <= 0 || groups <= 0 || c % groups)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "gn_scale_shift: bad arguments (c=%d groups=%d)", c, groups);
+  gn_scale_shift_kernel<<<(n * c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chan_sums, gamma, beta, n, c, groups,
+                                                                            count_per_channel, eps, scale_shift);
+  GPEMSR_LAUNCH_OK("gn_scale_shift_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const float* scale_shift, int act, float slope,
+                      const float* residual, const gpemsr_geom_t* og, float* out_f32, void* out_hi, void* out_lo,
+                      gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x_f32 || !g || !og || c <= 0) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: bad arguments");
+  if ((rc = check_geom(*g, "affine_act(in)")) != GPEMSR_OK || (rc = check_geom(*og, "affine_act(out)")) != GPEMSR_OK) return rc;
+  if (g->n != og->n || g->h != og->h || g->w != og->w) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: geometries differ in shape");
+  const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
+  affine_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x_f32, c, to_geom(*g), scale_shift, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  GPEMSR_LAUNCH_OK("affine_act_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t_pad, float* row_stats, void* p_hi, void* p_lo,
+                                gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!s || !row_stats || !p_hi || t <= 0 || ld < t || ld % 8 || t_pad < t || t_pad % 8)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "softmax_rows_blocked: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  softmax_stats_kernel<<<(unsigned)t, 256, 0, st>>>(s, t, ld, row_stats);
+  GPEMSR_LAUNCH_OK("softmax_stats_kernel");
+  dim3 grid((unsigned)((t_pad / 8 + 31) / 32), (unsigned)((t_pad + 31) / 32));
+  softmax_write_kernel<<<grid, 1024, 0, st>>>(s, t, ld, t_pad, row_stats, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo);
+  GPEMSR_LAUNCH_OK("softmax_write_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_add_bilinear_base(const float* x_center, int n, int h, int w, int scale, float* out, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x_center || !out || n <= 0 || h <= 0 || w <= 0 || scale <= 0) return set_error(GPEMSR_ERR_BAD_SHAPE, "add_bilinear_base: bad arguments");
+  const long long total = (long long)n * h * scale * w * scale;
+  add_bilinear_base_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_center, n, h, w, scale, out);
+  GPEMSR_LAUNCH_OK("add_bilinear_base_kernel");
+  return GPEMSR_OK;
+}
+
+}  // extern "C"

@@ -16,7 +16,9 @@
 // Roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
 // (each owns the TMEM lane quarter (warp % 4)).  Pipelines: NSTAGE smem stages (full/empty mbarriers) and two
 // TMEM accumulator buffers (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Persistent: CTA b processes tiles b, b+grid, ...
+// Persistent: CTA b owns the 128-row tiles b, b+grid, ... and sweeps ALL column tiles of each before moving on, so an
+// epilogue can carry per-row state across the column tiles of a row (the VQ arg-min) and the A slab stays L2-hot.
+// gridDim.y > 1 splits the column tiles across CTAs instead (stateless epilogues on problems with few row tiles).
 #pragma once
 #include "sm100.cuh"
 
@@ -67,8 +69,11 @@ struct Barriers {
 };
 
 // Epilogue concept:
-//   struct Epi { __device__ void tile(uint32_t tmem_acc /*lane-adjusted*/, long long m_tile, int n_tile,
-//                                     int row_in_tile /*0..127 = this thread's row*/, int warp_q); };
+//   struct Epi {
+//     struct State { ... };     // per-thread (= per-row) state, default-constructed at the start of every 128-row tile
+//     __device__ void tile(State&, uint32_t tmem_acc /*lane-adjusted*/, long long m_tile, int n_tile, int n_tiles,
+//                          int row_in_tile /*0..127 = this thread's row*/, int warp_q) const;
+//   };
 // The epilogue reads its accumulator with sm100::tmem_ld_32x32(tmem_acc + col, regs) and must finish with the
 // loads retired (tmem_ld_wait) before returning.
 
@@ -81,7 +86,6 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
   Barriers* bars = reinterpret_cast<Barriers*>(smem + NSTAGE * Cfg::STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total_tiles = op.m_tiles * op.n_tiles;
   const int kiters_per_tap = op.k / BLOCK_K;
   const int kiters = op.taps * kiters_per_tap;
 
@@ -100,33 +104,33 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     // ===================== producer: bulk copies HBM/L2 -> smem =====================
     uint32_t stage = 0, phase = 0;
     bool ok = true;
-    for (long long t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-      const long long m_tile = t / op.n_tiles;
-      const int n_tile = (int)(t % op.n_tiles);
-      for (int it = 0; it < kiters && ok; ++it) {
-        const int tap = it / kiters_per_tap, kc0 = (it % kiters_per_tap) * Cfg::KCH;
-        ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
-        if (!ok) break;
-        uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
-        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
-        __syncwarp();
-        const long long a_row = op.a_row0 + m_tile * BLOCK_M + op.a_row_off[tap];
-        // one 16-byte-cell column per copy: A cell column = BLOCK_M*16 B, B cell column = BLOCK_N*16 B
-        for (int c = lane; c < Cfg::PLANES * Cfg::KCH * 2; c += 32) {
-          const int is_b = c / (Cfg::PLANES * Cfg::KCH);
-          const int r = c % (Cfg::PLANES * Cfg::KCH);
-          const int plane = r / Cfg::KCH, kc = r % Cfg::KCH;
-          if (!is_b) {
-            const __nv_bfloat16* src = (plane ? op.a_lo : op.a_hi) + ((long long)(kc0 + kc) * op.a_rows + a_row) * 8;
-            sm100::bulk_g2s(sa + plane * Cfg::A_PLANE_BYTES + kc * (BLOCK_M * 16), src, BLOCK_M * 16, &bars->full[stage]);
-          } else {
-            const long long brow = ((long long)tap * (op.k / 8) + (kc0 + kc)) * op.b_rows + (long long)n_tile * BLOCK_N;
-            const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + brow * 8;
-            sm100::bulk_g2s(sb + plane * Cfg::B_PLANE_BYTES + kc * (BLOCK_N * 16), src, BLOCK_N * 16, &bars->full[stage]);
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        for (int it = 0; it < kiters && ok; ++it) {
+          const int tap = it / kiters_per_tap, kc0 = (it % kiters_per_tap) * Cfg::KCH;
+          ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+          if (!ok) break;
+          uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+          __syncwarp();
+          const long long a_row = op.a_row0 + m_tile * BLOCK_M + op.a_row_off[tap];
+          // one 16-byte-cell column per copy: A cell column = BLOCK_M*16 B, B cell column = BLOCK_N*16 B
+          for (int c = lane; c < Cfg::PLANES * Cfg::KCH * 2; c += 32) {
+            const int is_b = c / (Cfg::PLANES * Cfg::KCH);
+            const int r = c % (Cfg::PLANES * Cfg::KCH);
+            const int plane = r / Cfg::KCH, kc = r % Cfg::KCH;
+            if (!is_b) {
+              const __nv_bfloat16* src = (plane ? op.a_lo : op.a_hi) + ((long long)(kc0 + kc) * op.a_rows + a_row) * 8;
+              sm100::bulk_g2s(sa + plane * Cfg::A_PLANE_BYTES + kc * (BLOCK_M * 16), src, BLOCK_M * 16, &bars->full[stage]);
+            } else {
+              const long long brow = ((long long)tap * (op.k / 8) + (kc0 + kc)) * op.b_rows + (long long)n_tile * BLOCK_N;
+              const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + brow * 8;
+              sm100::bulk_g2s(sb + plane * Cfg::B_PLANE_BYTES + kc * (BLOCK_N * 16), src, BLOCK_N * 16, &bars->full[stage]);
+            }
           }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -134,38 +138,40 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
     uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
     bool ok = true;
-    for (long long t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-      ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
-      if (!ok) break;
-      sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
-      for (int it = 0; it < kiters && ok; ++it) {
-        ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
         if (!ok) break;
         sm100::tc_fence_after();
-        if (sm100::elect_one()) {
-          const uint32_t sa = sm100::smem_u32(stages + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+        for (int it = 0; it < kiters && ok; ++it) {
+          ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+          if (!ok) break;
+          sm100::tc_fence_after();
+          if (sm100::elect_one()) {
+            const uint32_t sa = sm100::smem_u32(stages + stage * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
 #pragma unroll
-          for (int k16 = 0; k16 < BLOCK_K / 16; ++k16) {
-            // one UMMA consumes two 16-byte k-cells: advance the start address by 2 cell columns per step
-            const uint64_t a_hi = sm100::smem_desc_kmajor_noswz(sa + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
-            const uint64_t b_hi = sm100::smem_desc_kmajor_noswz(sb + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
-            sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | k16) != 0);
-            if constexpr (SPLIT == 3) {
-              const uint64_t a_lo = sm100::smem_desc_kmajor_noswz(sa + Cfg::A_PLANE_BYTES + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
-              const uint64_t b_lo = sm100::smem_desc_kmajor_noswz(sb + Cfg::B_PLANE_BYTES + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
-              sm100::umma_bf16(tmem_acc, a_lo, b_hi, idesc, true);
-              sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
+            for (int k16 = 0; k16 < BLOCK_K / 16; ++k16) {
+              // one UMMA consumes two 16-byte k-cells: advance the start address by 2 cell columns per step
+              const uint64_t a_hi = sm100::smem_desc_kmajor_noswz(sa + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
+              const uint64_t b_hi = sm100::smem_desc_kmajor_noswz(sb + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+              sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | k16) != 0);
+              if constexpr (SPLIT == 3) {
+                const uint64_t a_lo = sm100::smem_desc_kmajor_noswz(sa + Cfg::A_PLANE_BYTES + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
+                const uint64_t b_lo = sm100::smem_desc_kmajor_noswz(sb + Cfg::B_PLANE_BYTES + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+                sm100::umma_bf16(tmem_acc, a_lo, b_hi, idesc, true);
+                sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
+              }
             }
+            sm100::umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
+            if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);   // accumulator complete
           }
-          sm100::umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
-          if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);   // accumulator complete
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
       }
-      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
@@ -173,18 +179,19 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     const int row = q * 32 + lane;
     uint32_t acc_buf = 0, acc_phase = 0;
     bool ok = true;
-    for (long long t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-      const long long m_tile = t / op.n_tiles;
-      const int n_tile = (int)(t % op.n_tiles);
-      ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
-      if (!ok) break;
-      sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epi.tile(tmem_acc, m_tile, n_tile, row, q);
-      sm100::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
-      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      typename Epi::State st{};
+      for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+        epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, q);
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+        if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+      }
     }
   }
 

@@ -12,7 +12,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 
 // Row-major fp32 X[rows, k] (row stride ld) -> blocked [k_pad/8][rows_alloc][8] hi (and lo if non-null).
 // Rows >= rows and k >= k are written as zero up to rows_fill / k_pad.
-__global__ void pack_rowmajor_kernel(const float* __restrict__ x, long long rows, int k, long long ld,
+static __global__ void pack_rowmajor_kernel(const float* __restrict__ x, long long rows, int k, long long ld,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                      long long rows_alloc, long long rows_fill, int k_pad, long long row_dst0) {
   const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte cell per thread

@@ -31,7 +31,8 @@ struct EpiRowMajor {
 };
 template <int BLOCK_N>
 struct EpiRowMajorN : EpiRowMajor {
-  __device__ __forceinline__ void tile(uint32_t tmem_acc, long long m_tile, int n_tile, int row, int) const {
+  struct State {};
+  __device__ __forceinline__ void tile(State&, uint32_t tmem_acc, long long m_tile, int n_tile, int, int row, int) const {
     this->template run<BLOCK_N>(tmem_acc, m_tile, n_tile, row);
   }
 };
@@ -43,8 +44,7 @@ int launch(const gemm::Operands& op, const EpiRowMajor& e, cudaStream_t s) {
   static_cast<EpiRowMajor&>(epi) = e;
   auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, EpiRowMajorN<BLOCK_N>>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const long long tiles = op.m_tiles * op.n_tiles;
-  const int grid = (int)std::min<long long>(tiles, gpemsr::num_sms());
+  const int grid = (int)std::min<long long>(op.m_tiles, gpemsr::num_sms());
   kern<<<grid, gemm::NUM_THREADS, Cfg::SMEM_BYTES, s>>>(op, epi);
   GPEMSR_LAUNCH_OK("gemm_kernel(selftest)");
   return GPEMSR_OK;

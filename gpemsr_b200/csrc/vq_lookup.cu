@@ -1,0 +1,452 @@
+// a-1 / a-2: codebook lookup = GEMM [rows x D] . [D x K] + per-row arg-extremum + code-vector gather.
+//
+// Replaces Codebook.forward (model/codebook.py:15-32: NHWC copy, d = |z|^2 + |e|^2 - 2 z.e^T, argmin, embedding
+// gather, NCHW copy) and Indexer.embedding + Codebook.inference_lr (model/indexer.py:47,53 / 96,100 and
+// model/codebook.py:34-43: Linear(512->1024) + softmax + top-1 + gather).  The [rows x K] distance / logit matrix
+// never reaches HBM: it lives in TMEM and is reduced by the GEMM epilogue.
+//
+// Exactness.  tcgen05 has no fp32-input MMA, so the GEMM runs ONE bf16 pass and the epilogue keeps,
+// per row, every code whose approximate score is within a rigorous error margin of the best one:
+//     |z.e - bf16(z).bf16(e)| <= (2^-8 + 2^-18) |z|_2 |e|_2                 (two roundings of 2^-9 each, Cauchy-Schwarz)
+// Rows with a single survivor are decided in the epilogue; the others (their candidate lists are tiny) are re-scored on
+// CUDA cores with fp32 FMA accumulation in the reference's association (|z|^2 + |e_k|^2) - 2 z.e_k (codebook.py:19-21),
+// lowest index on ties (codebook.py:23).  The result is therefore the arg-min of fp32-accumulated distances.
+//
+// Pipeline of one call (all on the caller's stream, no host sync):
+//   vq_prep_codes   e fp32 [K,D]   -> K8-blocked bf16 B operand, c_k (= |e_k|^2 or -bias_k), max |e_k|
+//   vq_prep_rows    z fp32 NCHW    -> K8-blocked bf16 A operand (the NCHW->NHWC permute of :16 fused with the bf16
+//                                     conversion), |z|^2 and the candidate margin per row; ONE pass over z
+//   gemm_kernel<EpiArgExtremum>    -> a CTA owns 128 rows and sweeps all code tiles; the epilogue thread of a row carries
+//                                     the running minimum and a <= 8 entry candidate list across the tiles
+//   vq_finalize     32-row blocks: z tile staged (transposed) in smem, warp-per-row fp32 re-score of ambiguous rows,
+//                   code-vector gather transposed through smem so that both e reads and NCHW z_q writes are coalesced
+#include "capi_common.h"
+#include "gemm_core.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+constexpr int CMAX = 8;              // candidates a row may carry; more -> exact scan of every code for that row
+constexpr int VQ_BLOCK_N = 256;
+constexpr uint32_t OVERFLOW = 0xFFFFFFFFu;
+constexpr int FIN_ROWS = 32;         // rows per finalize block
+constexpr int FIN_THREADS = 512;
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+struct Workspace {
+  __nv_bfloat16* a;       // [d_pad/8][rows_pad][8]
+  __nv_bfloat16* b;       // [d_pad/8][k_pad][8]
+  float* c;               // [k_pad]   |e_k|^2 (or -bias_k); +inf for padding codes
+  float* zz;              // [rows_pad]
+  float* margin;          // [rows_pad]
+  uint32_t* cand_cnt;     // [rows_pad]  0 = decided in the epilogue, n = ambiguous with n candidates, OVERFLOW
+  uint32_t* cand;         // [rows_pad][CMAX] code indices (ascending)
+  float* emax;            // [1] max_k |e_k|_2   (as float bits, written with atomicMax)
+  int* err;               // [1] GEMM pipeline error flag
+  size_t bytes;
+};
+
+Workspace carve(void* base, long long rows, int d, int k) {
+  const long long rows_pad = round_up(std::max<long long>(rows, 1), gemm::BLOCK_M);
+  const long long d_pad = round_up(d, 64), k_pad = round_up(k, VQ_BLOCK_N);
+  uintptr_t p = (uintptr_t)base;
+  auto take = [&](size_t n) { uintptr_t r = p; p += (uintptr_t)round_up((long long)n, 256); return (void*)r; };
+  Workspace w;
+  w.a = (__nv_bfloat16*)take((size_t)rows_pad * d_pad * 2);
+  w.b = (__nv_bfloat16*)take((size_t)k_pad * d_pad * 2);
+  w.c = (float*)take((size_t)k_pad * 4);
+  w.zz = (float*)take((size_t)rows_pad * 4);
+  w.margin = (float*)take((size_t)rows_pad * 4);
+  w.cand_cnt = (uint32_t*)take((size_t)rows_pad * 4);
+  w.cand = (uint32_t*)take((size_t)rows_pad * CMAX * 4);
+  w.emax = (float*)take(4);
+  w.err = (int*)take(4);
+  w.bytes = (size_t)(p - (uintptr_t)base);
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// codes: one warp per code k.  c_k = |e_k|^2 (mode 0) or -bias_k (mode 1); B operand cells; max norm.
+__global__ void vq_prep_codes(const float* __restrict__ e, const float* __restrict__ bias, int k, int d, int k_pad, int d_pad,
+                              int mode, __nv_bfloat16* __restrict__ b, float* __restrict__ c, float* __restrict__ emax) {
+  const int code = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (code >= k_pad) return;
+  float ss = 0.f;
+  for (int kc = lane; kc < d_pad / 8; kc += 32) {
+    uint32_t h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d0 = kc * 8 + 2 * j;
+      const float v0 = (code < k && d0 < d) ? e[(size_t)code * d + d0] : 0.f;
+      const float v1 = (code < k && d0 + 1 < d) ? e[(size_t)code * d + d0 + 1] : 0.f;
+      ss = fmaf(v0, v0, ss);
+      ss = fmaf(v1, v1, ss);
+      h[j] = sm100::pack_bf16x2(v0, v1);
+    }
+    *reinterpret_cast<uint4*>(b + ((size_t)kc * k_pad + code) * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) {
+    c[code] = (code >= k) ? INFINITY : (mode == 0 ? ss : -bias[code]);
+    if (code < k) atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(ss)));   // non-negative floats order like ints
+  }
+}
+
+// rows: one thread per row; consecutive threads <-> consecutive hw, so the NCHW reads (stride hw between the 8 values of
+// a cell) and the blocked 16-byte cell writes are both coalesced.  One pass over z produces the bf16 operand, |z|^2 and
+//   margin = |alpha| * 2 * 1.25 * (2^-8 + 2^-18) * |z| * max|e|     (two scores, each off by at most the bound; x1.25 for
+//            the tensor core's own accumulation rounding)  +  2^-20 * (|z|^2 + max|e|^2 + 1)  (fp32 quantisation of the
+//            reference's own (|z|^2 + |e|^2) - 2 z.e and summation-order noise)
+__global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long long hw, int d, int d_pad, long long rows_pad,
+                             float alpha_abs, const float* __restrict__ emax, __nv_bfloat16* __restrict__ a,
+                             float* __restrict__ zz, float* __restrict__ margin) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows_pad) return;
+  const bool live = r < rows;
+  const long long bi = live ? r / hw : 0, p = live ? r % hw : 0;
+  const float* src = z + bi * d * hw + p;
+  float s = 0.f;
+  for (int kc = 0; kc < d_pad / 8; ++kc) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dd = kc * 8 + j;
+      v[j] = (live && dd < d) ? __ldg(src + (long long)dd * hw) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s = fmaf(v[j], v[j], s);
+    *reinterpret_cast<uint4*>(a + ((size_t)kc * rows_pad + r) * 8) =
+        make_uint4(sm100::pack_bf16x2(v[0], v[1]), sm100::pack_bf16x2(v[2], v[3]), sm100::pack_bf16x2(v[4], v[5]),
+                   sm100::pack_bf16x2(v[6], v[7]));
+  }
+  if (live) {
+    zz[r] = s;
+    const float em = *emax;
+    margin[r] = alpha_abs * 2.0f * 1.25f * (0x1p-8f + 0x1p-18f) * sqrtf(s) * em + 0x1p-20f * (s + em * em + 1.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GEMM epilogue: score_k = c_k + alpha * acc_k (minimised).  Per code tile: pass 1 lowers the row's running minimum,
+// pass 2 appends every code within `margin` of it (a superset of the codes within `margin` of the final minimum, since
+// the running minimum only decreases).  After the last tile the list is filtered against the final minimum.
+struct EpiArgExtremum {
+  const float* c;
+  const float* margin;
+  uint32_t* cand_cnt;
+  uint32_t* cand;
+  long long* idx_out;
+  long long rows;
+  float alpha;
+
+  struct State {
+    float runmin = INFINITY;
+    uint32_t cnt = 0;
+    bool overflow = false;
+    uint32_t idx[CMAX];
+    float val[CMAX];
+  };
+
+  __device__ __forceinline__ void push(State& st, uint32_t code, float v, float thr) const {
+    if (st.cnt == CMAX) {               // drop entries the lowered minimum has left behind
+      uint32_t n = 0;
+      for (uint32_t i = 0; i < CMAX; ++i)
+        if (st.val[i] <= thr) { st.idx[n] = st.idx[i]; st.val[n] = st.val[i]; ++n; }
+      st.cnt = n;
+    }
+    if (st.cnt == CMAX) { st.overflow = true; return; }
+    st.idx[st.cnt] = code; st.val[st.cnt] = v; ++st.cnt;
+  }
+
+  // one pass: a code is appended when it is within `margin` of the running minimum seen so far (records lower the
+  // minimum as they arrive); stale entries are dropped by push()'s compaction and by the final filter.
+  __device__ __forceinline__ void scan32(State& st, const uint32_t (&r)[32], const float* __restrict__ cc, uint32_t code0,
+                                         float mg, float& thr) const {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 ck = __ldg(reinterpret_cast<const float4*>(cc + j));
+      const float v0 = fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), v1 = fmaf(alpha, __uint_as_float(r[j + 1]), ck.y);
+      const float v2 = fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), v3 = fmaf(alpha, __uint_as_float(r[j + 3]), ck.w);
+      if (fminf(fminf(v0, v1), fminf(v2, v3)) <= thr) {
+        const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (v[u] <= thr) {
+            if (v[u] < st.runmin) { st.runmin = v[u]; thr = v[u] + mg; }
+            push(st, code0 + j + u, v[u], thr);
+          }
+        }
+      }
+    }
+  }
+
+  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int) const {
+    const long long gr = m_tile * gemm::BLOCK_M + row;
+    const float* cc = c + (size_t)n_tile * VQ_BLOCK_N;
+    const float mg = gr < rows ? __ldg(margin + gr) : 0.f;
+    float thr = st.runmin + mg;           // +inf on the first tile
+    uint32_t ra[32], rb[32];
+    sm100::tmem_ld_32x32(tmem_acc, ra);
+#pragma unroll 1
+    for (int c0 = 0; c0 < VQ_BLOCK_N; c0 += 64) {
+      sm100::tmem_ld_wait();
+      sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);                    // prefetch the next 32 columns
+      scan32(st, ra, cc + c0, (uint32_t)(n_tile * VQ_BLOCK_N + c0), mg, thr);
+      sm100::tmem_ld_wait();
+      if (c0 + 64 < VQ_BLOCK_N) sm100::tmem_ld_32x32(tmem_acc + c0 + 64, ra);
+      scan32(st, rb, cc + c0 + 32, (uint32_t)(n_tile * VQ_BLOCK_N + c0 + 32), mg, thr);
+    }
+    if (n_tile == n_tiles - 1 && gr < rows) {
+      if (st.overflow) { cand_cnt[gr] = OVERFLOW; return; }
+      uint32_t n = 0, only = 0;
+      for (uint32_t i = 0; i < st.cnt; ++i)
+        if (st.val[i] <= thr) { only = st.idx[i]; ++n; }
+      if (n <= 1) {                       // decided (n == 0 only for NaN rows: index 0)
+        idx_out[gr] = only;
+        cand_cnt[gr] = 0;
+      } else {
+        uint32_t* out = cand + (size_t)gr * CMAX;
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < st.cnt; ++i)
+          if (st.val[i] <= thr) out[m++] = st.idx[i];
+        cand_cnt[gr] = m;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// finalize: a block owns FIN_ROWS consecutive rows of one image (consecutive hw).
+//   mode 0 (Codebook.forward):  d_k = (|z|^2 + |e_k|^2) - 2 * dot_k, minimise, lowest index on ties
+//   mode 1 (inference_lr):      l_k = dot_k + bias_k, maximise, lowest index on ties
+__device__ __forceinline__ float warp_dot(const float* __restrict__ zt, int r, const float* __restrict__ wk, int d, int lane) {
+  float acc = 0.f;
+  for (int i = lane; i < d; i += 32) acc = fmaf(zt[i * (FIN_ROWS + 1) + r], __ldg(wk + i), acc);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+__device__ __forceinline__ float score_of(float dot, int mode, float zz, float ck) {
+  if (mode == 0) return __fsub_rn(__fadd_rn(zz, ck), __fmul_rn(2.0f, dot));
+  return -__fadd_rn(dot, -ck);          // ck = -bias_k ; negated logit so that "smaller is better"
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ table, long long hw,
+            int blocks_per_image, int d, int k, int dq, int mode, const float* __restrict__ c, const float* __restrict__ zz,
+            const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand, float* __restrict__ zq,
+            long long* __restrict__ idx_out, float* __restrict__ sq_err) {
+  extern __shared__ float zt[];                  // [max(d, dq)][FIN_ROWS + 1]
+  __shared__ int s_idx[FIN_ROWS];
+  __shared__ uint32_t s_cnt[FIN_ROWS];
+  __shared__ int s_any;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bi = blockIdx.x / blocks_per_image;
+  const long long p0 = (long long)(blockIdx.x % blocks_per_image) * FIN_ROWS;
+  const int nrows = (int)min((long long)FIN_ROWS, hw - p0);
+  const long long row0 = bi * hw + p0;
+  constexpr int LD = FIN_ROWS + 1;
+
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  if (threadIdx.x < FIN_ROWS) {
+    const uint32_t n = threadIdx.x < nrows ? cand_cnt[row0 + threadIdx.x] : 0;
+    s_cnt[threadIdx.x] = n;
+    if (threadIdx.x < nrows && n == 0) s_idx[threadIdx.x] = (int)idx_out[row0 + threadIdx.x];
+    if (n != 0) s_any = 1;
+  }
+  __syncthreads();
+  const bool need_z = s_any != 0 || sq_err != nullptr;
+
+  // phase A: stage the fp32 z tile transposed ([d][row]) -- coalesced global reads, conflict-free smem writes
+  if (need_z) {
+    const float* zb = z + bi * d * hw + p0 + (lane < nrows ? lane : 0);
+    constexpr int NW = FIN_THREADS / 32;
+    int i = warp;
+    for (; i + 7 * NW < d; i += 8 * NW) {            // 8 independent 128-byte loads in flight per warp
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(zb + (long long)(i + u * NW) * hw);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) zt[(i + u * NW) * LD + lane] = v[u];
+    }
+    for (; i < d; i += NW) zt[i * LD + lane] = __ldg(zb + (long long)i * hw);
+    __syncthreads();
+    // phase B: warp-per-row fp32 re-score of the ambiguous rows
+    for (int r = warp; r < nrows; r += FIN_THREADS / 32) {
+      const uint32_t n = s_cnt[r];
+      if (n == 0) continue;
+      const float zzr = zz[row0 + r];
+      float bs = INFINITY;
+      int best = 0;
+      if (n == OVERFLOW) {               // more near-ties than the list holds (e.g. many duplicated codes): scan every code
+        for (int kk = 0; kk < k; ++kk) {
+          const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zzr, c[kk]);
+          if (sc < bs) { bs = sc; best = kk; }
+        }
+      } else {
+        for (uint32_t i = 0; i < n; ++i) {           // ascending code order; strict '<' keeps the lowest index on ties
+          const int kk = (int)cand[(size_t)(row0 + r) * CMAX + i];
+          const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zzr, c[kk]);
+          if (sc < bs) { bs = sc; best = kk; }
+        }
+      }
+      if (lane == 0) { s_idx[r] = best; idx_out[row0 + r] = best; }
+    }
+    __syncthreads();
+  }
+
+  // phase C: gather e[idx] (coalesced along d) into the transposed tile, optionally accumulating (e - z)^2
+  float err = 0.f;
+  for (int r = warp; r < nrows; r += FIN_THREADS / 32) {
+    const float* src = table + (size_t)s_idx[r] * dq;
+    int i = lane;
+    for (; i + 96 < dq; i += 128) {
+      float ev[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ev[u] = __ldg(src + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (sq_err) { const float dl = ev[u] - zt[(i + 32 * u) * LD + r]; err = fmaf(dl, dl, err); }
+        zt[(i + 32 * u) * LD + r] = ev[u];
+      }
+    }
+    for (; i < dq; i += 32) {
+      const float ev = __ldg(src + i);
+      if (sq_err) { const float dl = ev - zt[i * LD + r]; err = fmaf(dl, dl, err); }
+      zt[i * LD + r] = ev;
+    }
+  }
+  __syncthreads();
+  // phase D: NCHW store, lane <-> consecutive hw
+  float* qb = zq + bi * dq * hw + p0;
+  if (lane < nrows)
+    for (int i = warp; i < dq; i += FIN_THREADS / 32) __stcs(qb + (long long)i * hw + lane, zt[i * LD + lane]);
+  if (sq_err) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+    if (lane == 0 && err != 0.f) atomicAdd(sq_err, err);
+  }
+}
+
+// argmax over materialised logits + gather (Codebook.inference_lr on its own): one warp per row
+__global__ void argmax_gather_kernel(const float* __restrict__ p, const float* __restrict__ table, long long rows, long long hw,
+                                     int k, int dq, float* __restrict__ zq, long long* __restrict__ idx_out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* row = p + r * k;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < k; i += 32) {
+    const float v = __ldg(row + i);
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;
+  if (lane == 0) idx_out[r] = bi;
+  const long long b = r / hw, q = r % hw;
+  for (int i = lane; i < dq; i += 32) zq[(b * dq + i) * hw + q] = __ldg(table + (size_t)bi * dq + i);
+}
+
+int run_lookup(const float* z, const float* w, const float* bias, const float* table, int b, int d, long long hw, int k, int dq,
+               int mode, float* zq, long long* idx, float* sq_err_sum, void* ws, size_t ws_bytes, cudaStream_t s) {
+  using namespace gpemsr;
+  if (b < 0 || d <= 0 || hw < 0 || k <= 0 || dq <= 0)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: bad shape b=%d d=%d hw=%lld k=%d dq=%d", b, d, hw, k, dq);
+  if (std::max(d, dq) > 1536)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: latent_dim %d > 1536 does not fit the finalize tile", std::max(d, dq));
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  const long long rows = (long long)b * hw;
+  if (rows == 0) return GPEMSR_OK;
+  if (!z || !w || !table || !zq || !idx) return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: null pointer");
+  if (mode == 1 && !bias) return set_error(GPEMSR_ERR_BAD_SHAPE, "logits_argmax_gather: bias is required");
+  const size_t need = gpemsr_vq_workspace_bytes(rows, d, k);
+  if (!ws || ws_bytes < need) return set_error(GPEMSR_ERR_WORKSPACE, "vq lookup: workspace %zu B < required %zu B", ws_bytes, need);
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return set_error(GPEMSR_ERR_BAD_ALIGN, "vq lookup: workspace must be 256-byte aligned");
+
+  Workspace W = carve(ws, rows, d, k);
+  const long long rows_pad = round_up(rows, gemm::BLOCK_M);
+  const int d_pad = (int)round_up(d, 64), k_pad = (int)round_up(k, VQ_BLOCK_N), n_tiles = k_pad / VQ_BLOCK_N;
+  const float alpha = mode == 0 ? -2.0f : -1.0f;
+
+  GPEMSR_CUDA_OK(cudaMemsetAsync(W.emax, 0, 512, s));       // emax and err (adjacent 256-byte slots)
+  vq_prep_codes<<<(k_pad + 7) / 8, 256, 0, s>>>(w, bias, k, d, k_pad, d_pad, mode, W.b, W.c, W.emax);
+  GPEMSR_LAUNCH_OK("vq_prep_codes");
+  vq_prep_rows<<<(unsigned)((rows_pad + 127) / 128), 128, 0, s>>>(z, rows, hw, d, d_pad, rows_pad, fabsf(alpha), W.emax, W.a,
+                                                                W.zz, W.margin);
+  GPEMSR_LAUNCH_OK("vq_prep_rows");
+  {
+    gemm::Operands op{};
+    op.a_hi = W.a; op.a_lo = nullptr; op.b_hi = W.b; op.b_lo = nullptr;
+    op.a_rows = rows_pad; op.b_rows = k_pad; op.k = d_pad; op.taps = 1; op.a_row_off[0] = 0;
+    op.m_tiles = rows_pad / gemm::BLOCK_M; op.n_tiles = n_tiles; op.a_row0 = 0; op.err_flag = W.err;
+    EpiArgExtremum epi{W.c, W.margin, W.cand_cnt, W.cand, idx, rows, alpha};
+    using Cfg = gemm::Config<VQ_BLOCK_N, 64, 1, 4>;
+    auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum>;
+    GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    const int grid = (int)std::min<long long>(op.m_tiles, num_sms());
+    kern<<<grid, gemm::NUM_THREADS, Cfg::SMEM_BYTES, s>>>(op, epi);
+    GPEMSR_LAUNCH_OK("gemm_kernel<EpiArgExtremum>");
+  }
+  {
+    if (sq_err_sum) GPEMSR_CUDA_OK(cudaMemsetAsync(sq_err_sum, 0, sizeof(float), s));
+    const int blocks_per_image = (int)((hw + FIN_ROWS - 1) / FIN_ROWS);
+    const size_t smem = (size_t)std::max(d, dq) * (FIN_ROWS + 1) * sizeof(float);
+    GPEMSR_CUDA_OK(cudaFuncSetAttribute(vq_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vq_finalize<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, smem, s>>>(
+        z, w, table, hw, blocks_per_image, d, k, dq, mode, W.c, W.zz, W.cand_cnt, W.cand, zq, idx,
+        (mode == 0) ? sq_err_sum : nullptr);
+    GPEMSR_LAUNCH_OK("vq_finalize");
+  }
+  return GPEMSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gpemsr_vq_workspace_bytes(int64_t n_rows, int d, int k) {
+  if (n_rows < 0 || d <= 0 || k <= 0) return 0;
+  return carve(nullptr, n_rows, d, k).bytes;
+}
+
+int gpemsr_vq_lookup_nchw(const float* z, const float* emb, int b, int d, int64_t hw, int k, float* zq, int64_t* idx,
+                          float* sq_err_sum, void* ws, size_t ws_bytes, gpemsr_stream_t stream) {
+  return run_lookup(z, emb, nullptr, emb, b, d, hw, k, d, 0, zq, (long long*)idx, sq_err_sum, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int gpemsr_logits_argmax_gather(const float* feat, const float* w, const float* bias, const float* emb, int b, int d, int64_t hw,
+                                int k, int dq, float* zq, int64_t* idx, float* logits, void* ws, size_t ws_bytes,
+                                gpemsr_stream_t stream) {
+  if (logits)
+    return gpemsr::set_error(GPEMSR_ERR_UNSUPPORTED, "logits_argmax_gather: materialising the logits is not built yet; pass "
+                             "logits = NULL (the fused path never writes them)");
+  return run_lookup(feat, w, bias, emb, b, d, hw, k, dq, 1, zq, (long long*)idx, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int gpemsr_argmax_gather(const float* p, const float* emb, int b, int64_t hw, int k, int dq, float* zq, int64_t* idx,
+                         gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  if (b < 0 || hw < 0 || k <= 0 || dq <= 0) return set_error(GPEMSR_ERR_BAD_SHAPE, "argmax_gather: bad shape");
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  const long long rows = (long long)b * hw;
+  if (rows == 0) return GPEMSR_OK;
+  if (!p || !emb || !zq || !idx) return set_error(GPEMSR_ERR_BAD_SHAPE, "argmax_gather: null pointer");
+  argmax_gather_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p, emb, rows, hw, k, dq, zq, (long long*)idx);
+  GPEMSR_LAUNCH_OK("argmax_gather_kernel");
+  return GPEMSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference VQ-GAN ``Decoder`` (model/decoder.py) and its blocks (model/blocks.py)
+on the sm_100a implicit-GEMM kernels.
+
+The module tree, constructor arguments and parameter names are those of the reference
+(``input_layer.{0..}``, ``feat_extract.{i}.block.{0,1,3,4}``, ``feat_extract.{i}.upblock``, ``output_layer`` ...),
+so reference checkpoints load with ``strict=True``; the nn.Modules below only HOLD parameters -- ``forward`` and
+``multi_scale_feat_calculate`` (same signatures and return values as model/decoder.py:37-57) run the CUDA path.
+Inference only.  ``precision='fp32'`` (default) runs every GEMM as a 3-term bf16 split (fp32-faithful);
+``precision='bf16'`` runs single bf16 passes.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import igemm as G
+
+
+def Normalize(in_channels):                                   # model/blocks.py:5-6
+    return nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class ResidualBlock(nn.Module):                               # parameter holder for model/blocks.py:8-23
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.block = nn.Sequential(nn.Conv2d(in_channels, out_channels, 3, 1, 1), Normalize(out_channels), nn.ReLU(inplace=True),
+                                   nn.Conv2d(out_channels, out_channels, 3, 1, 1), Normalize(out_channels), nn.ReLU(inplace=True))
+        if in_channels != out_channels:
+            self.channel_up = nn.Conv2d(in_channels, out_channels, 1, 1, 0)
+
+
+class UpBlock(nn.Module):                                     # model/blocks.py:32-38
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.upblock = nn.ConvTranspose2d(in_channels, out_channels, 3, 2, 1, 1)
+
+
+class NonLocalBlock(nn.Module):                               # model/blocks.py:50-59
+    def __init__(self, channels):
+        super().__init__()
+        self.in_channels = channels
+        self.gn = Normalize(channels)
+        self.q = nn.Conv2d(channels, channels, 1, 1, 0)
+        self.k = nn.Conv2d(channels, channels, 1, 1, 0)
+        self.v = nn.Conv2d(channels, channels, 1, 1, 0)
+        self.proj_out = nn.Conv2d(channels, channels, 1, 1, 0)
+
+
+class _Plan:
+    """Packed weights + activation buffers for one input shape (built lazily, reused across calls)."""
+
+    def __init__(self, dec, n, h, w, device):
+        self.split = 3 if dec.precision == 'fp32' else 1
+        self.device = device
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.n, self.h, self.w = n, h, w
+        self.bufs = {}
+        self.wts = {}
+        self.gn = {}
+
+    def act(self, name, geom, c, f32, planes=True):
+        key = name
+        a = self.bufs.get(key)
+        if a is None:
+            a = G.Act(geom, c, self.device, f32=f32, planes=planes, split=self.split)
+            self.bufs[key] = a
+        return a
+
+    def weights(self, name, param, kind, taps=None):
+        wt = self.wts.get(name)
+        if wt is None:
+            wt = G.Weights(param, kind, taps=taps, split=self.split)
+            self.wts[name] = wt
+        return wt
+
+    def scratch(self, n, c):
+        key = (n, c)
+        s = self.gn.get(key)
+        if s is None:
+            s = G.GroupNormScratch(n, c, self.device)
+            self.gn[key] = s
+        return s
+
+
+class Decoder(nn.Module):
+    """Drop-in for ``model.decoder.Decoder`` (same ``args`` dict)."""
+
+    def __init__(self, args, precision='fp32'):
+        super().__init__()
+        self.args = args
+        self.channel_list = args['channel_list']
+        self.num_res_blocks = args['num_resblock_per_scale']
+        self.num_input_resblck = args['num_input_resblck']
+        self.latent_dim = args['latent_dim']
+        self.use_non_local = args['use_non_local']
+        assert precision in ('fp32', 'bf16')
+        self.precision = precision
+
+        layers = [nn.Conv2d(self.latent_dim, self.channel_list[0], 1)]
+        for _ in range(self.num_input_resblck):
+            layers.append(ResidualBlock(self.channel_list[0], self.channel_list[0]))
+        self.input_layer = nn.Sequential(*layers)
+        layers = []
+        if self.use_non_local:
+            layers.append(NonLocalBlock(self.channel_list[0]))
+        for i in range(len(self.channel_list) - 1):
+            cin, cout = self.channel_list[i], self.channel_list[i + 1]
+            for _ in range(self.num_res_blocks):
+                layers.append(ResidualBlock(cin, cin))
+            layers.append(UpBlock(cin, cout))
+        self.feat_extract = nn.Sequential(*layers)
+        self.output_layer = nn.Conv2d(self.channel_list[-1], args['im_channel'], 3, 1, 1)
+        self._plans = {}
+
+    # ------------------------------------------------------------------ building blocks
+    def _conv(self, P, name, mod, x, out, **kw):
+        wt = P.weights(name, mod.weight, 'conv')
+        G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), out=out, **kw)
+
+    def _res_block(self, P, name, rb, x):
+        """x + ReLU(GN(conv(ReLU(GN(conv(x))))))  (model/blocks.py:25-29); x carries fp32 master + planes."""
+        g, c = x.geom, rb.out_channels
+        raw = P.act(f'raw{g.key()}_{c}', g, c, f32=True, planes=False)
+        h = P.act(f'h{g.key()}_{c}', g, c, f32=False)
+        y = P.act(name + '.out', g, c, f32=True)
+        sc = P.scratch(g.n, c)
+        self._conv(P, name + '.block.0', rb.block[0], x, raw, out_planes=False)
+        G.group_norm_act(raw, rb.block[1].weight.detach(), rb.block[1].bias.detach(), sc, h, act=G.ACT_RELU, out_f32=False)
+        self._conv(P, name + '.block.3', rb.block[3], h, raw, out_planes=False)
+        if rb.in_channels != rb.out_channels:
+            short = P.act(name + '.short', g, c, f32=True, planes=False)
+            self._conv(P, name + '.channel_up', rb.channel_up, x, short, out_planes=False)
+            res = short.f32
+        else:
+            res = x.f32
+        G.group_norm_act(raw, rb.block[4].weight.detach(), rb.block[4].bias.detach(), sc, y, act=G.ACT_RELU, residual=res)
+        return y
+
+    def _up_block(self, P, name, ub, x, need_f32):
+        """ConvTranspose2d(k3, s2, p1, op1) as four parity-phase GEMMs (model/blocks.py:32-38)."""
+        g = x.geom
+        og = G.Geom(g.n, 2 * g.h, 2 * g.w, True)
+        cout = ub.upblock.weight.shape[1]
+        y = P.act(name + '.out', og, cout, f32=need_f32)
+        for py in (0, 1):
+            for px in (0, 1):
+                wt = P.weights(f'{name}.p{py}{px}', ub.upblock.weight, 'convT', taps=G.convT_phase_taps(py, px))
+                G.igemm(x, wt, P.err, split=P.split, bias=ub.upblock.bias.detach(), out=y, up=2, py=py, px=px,
+                        out_f32=need_f32)
+        return y
+
+    def _non_local(self, P, name, nl, x):
+        """x + proj_out(softmax(q^T k / sqrt(c)) applied to v)  (model/blocks.py:61-83)."""
+        g, c = x.geom, nl.in_channels
+        t = g.h * g.w
+        t_pad = G._round_up(t, 128)
+        cg = G.Geom(g.n, g.h, g.w, padded=False, r_img=t_pad)          # compact token rows
+        hn = P.act(name + '.h', cg, c, f32=False)
+        sc = P.scratch(g.n, c)
+        G.group_norm_act(x, nl.gn.weight.detach(), nl.gn.bias.detach(), sc, hn, act=G.ACT_NONE, out_f32=False)
+        q = P.act(name + '.q', cg, c, f32=False)
+        k = P.act(name + '.k', cg, c, f32=False)
+        o = P.act(name + '.o', cg, c, f32=False)
+        G.igemm(hn, P.weights(name + '.q', nl.q.weight, 'conv'), P.err, split=P.split, bias=nl.q.bias.detach(), out=q, out_f32=False)
+        G.igemm(hn, P.weights(name + '.k', nl.k.weight, 'conv'), P.err, split=P.split, bias=nl.k.bias.detach(), out=k, out_f32=False)
+        # v^T [tokens/8][channels][8]: weights as the A operand, tokens as columns, bias per row
+        wv = P.weights(name + '.v', nl.v.weight, 'conv')
+        c_rows = wv.b_rows
+        wgeom = G.Geom(1, 1, c, padded=False, r_img=G._round_up(c_rows, 128), m0=0, rows_alloc=c_rows)
+        assert c_rows % 128 == 0, 'attention width must be a multiple of 128'
+        wa = _View(wv.hi[0], wv.lo[0] if wv.lo is not None else None, wgeom)
+        vt = P.bufs.get(name + '.vt')
+        if vt is None:
+            shape = (g.n, t_pad // 8, c_rows, 8)
+            vt = (torch.zeros(shape, dtype=torch.bfloat16, device=P.device),
+                  torch.zeros(shape, dtype=torch.bfloat16, device=P.device) if P.split == 3 else None)
+            P.bufs[name + '.vt'] = vt
+            P.bufs[name + '.s'] = torch.zeros(t_pad, t_pad, dtype=torch.float32, device=P.device)
+            P.bufs[name + '.stats'] = torch.zeros(t_pad, 2, dtype=torch.float32, device=P.device)
+            pshape = (t_pad // 8, t_pad, 8)
+            P.bufs[name + '.p'] = (torch.zeros(pshape, dtype=torch.bfloat16, device=P.device),
+                                   torch.zeros(pshape, dtype=torch.bfloat16, device=P.device) if P.split == 3 else None)
+        s_buf, stats = P.bufs[name + '.s'], P.bufs[name + '.stats']
+        p_hi, p_lo = P.bufs[name + '.p']
+        row_bytes = 16                                                # one 8 x bf16 cell
+        for i in range(g.n):
+            vt_geom = G.Geom(1, 1, c, padded=False, r_img=wgeom.r_img, m0=0, rows_alloc=c_rows)
+            vt_i = _View(vt[0][i], vt[1][i] if vt[1] is not None else None, vt_geom)
+            G.igemm(wa, None, P.err, split=P.split, bias=nl.v.bias.detach(), bias_per_row=True, out=vt_i, out_f32=False,
+                    n_cols=t, b_hi=hn.hi.data_ptr() + i * t_pad * row_bytes,
+                    b_lo=(hn.lo.data_ptr() + i * t_pad * row_bytes) if hn.lo is not None else None,
+                    b_rows=cg.rows_alloc, k_pad=hn.c_pad)
+            # scores = q_i^T k_i / sqrt(c)  -> fp32 [t_pad, t_pad]
+            G.igemm(q, None, P.err, split=P.split, scale=float(int(c) ** (-0.5)), a_geom=cg.sample(i), n_cols=t,
+                    b_hi=k.hi.data_ptr() + i * t_pad * row_bytes,
+                    b_lo=(k.lo.data_ptr() + i * t_pad * row_bytes) if k.lo is not None else None,
+                    b_rows=cg.rows_alloc, k_pad=k.c_pad, out_rowmajor=s_buf, ld=t_pad)
+            G.softmax_rows_blocked(s_buf, t, t_pad, t_pad, stats, p_hi, p_lo)
+            # o_i = P v_i^T
+            pg = G.Geom(1, g.h, g.w, padded=False, r_img=t_pad, m0=0, rows_alloc=t_pad)
+            pa = _View(p_hi, p_lo, pg)
+            G.igemm(pa, None, P.err, split=P.split, n_cols=c, b_hi=vt_i.hi.data_ptr(),
+                    b_lo=vt_i.lo.data_ptr() if vt_i.lo is not None else None, b_rows=c_rows, k_pad=t_pad,
+                    out=o, o_geom=cg.sample(i), out_f32=False)
+        y = P.act(name + '.out', g, c, f32=True)
+        G.igemm(o, P.weights(name + '.proj_out', nl.proj_out.weight, 'conv'), P.err, split=P.split,
+                bias=nl.proj_out.bias.detach(), residual=x.f32, out=y)
+        return y
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def multi_scale_feat_calculate(self, x):                  # model/decoder.py:40-57
+        feats, img = self._run(x, want_feats=True)
+        return feats + [img]
+
+    @torch.no_grad()
+    def forward(self, x):                                     # model/decoder.py:37-38
+        return self._run(x, want_feats=False)[1]
+
+    def _run(self, x, want_feats):
+        if not x.is_cuda:
+            from ._lib import GpemsrError
+            raise GpemsrError(-3, 'Decoder needs CUDA tensors: there is no CPU fallback')
+        n, c, h, w = x.shape
+        key = (n, h, w, x.device.index)
+        P = self._plans.get(key)
+        if P is None:
+            P = _Plan(self, n, h, w, x.device)
+            self._plans[key] = P
+        g = G.Geom(n, h, w, True)
+        xin = P.act('in', g, c, f32=False)
+        G.pack_nchw(x.float(), xin)
+        cur = P.act('input_layer.0.out', g, self.channel_list[0], f32=True)
+        self._conv(P, 'input_layer.0', self.input_layer[0], xin, cur)
+        for i in range(self.num_input_resblck):
+            cur = self._res_block(P, f'input_layer.{i + 1}', self.input_layer[i + 1], cur)
+        feats = []
+        nlayers = len(self.feat_extract)
+        for li, mod in enumerate(self.feat_extract):
+            name = f'feat_extract.{li}'
+            if isinstance(mod, NonLocalBlock):
+                cur = self._non_local(P, name, mod, cur)
+            elif isinstance(mod, ResidualBlock):
+                cur = self._res_block(P, name, mod, cur)
+                nxt = self.feat_extract[li + 1] if li + 1 < nlayers else None
+                if want_feats and isinstance(nxt, UpBlock):    # the tensors model/decoder.py:46/51 collects
+                    feats.append(G.unpack_nchw(cur))
+            else:
+                last = li == nlayers - 1
+                cur = self._up_block(P, name, mod, cur, need_f32=not last)
+        img = torch.empty(n, self.output_layer.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
+        wt = P.weights('output_layer', self.output_layer.weight, 'conv')
+        G.igemm(cur, wt, P.err, split=P.split, bias=self.output_layer.bias.detach(), out_nchw=img,
+                nchw_c=self.output_layer.out_channels)
+        self._last_plan = P
+        return feats, img
+
+    def check(self):
+        """Synchronise and raise if a GEMM pipeline timed out (tests / smoke)."""
+        G.check_pipeline(self._last_plan.err)
+
+
+class _View:
+    """Operand planes that are not a whole Act (weights used as the A operand, per-sample slices)."""
+
+    def __init__(self, hi, lo, geom):
+        self.hi, self.lo, self.geom, self.f32 = hi, lo, geom, None

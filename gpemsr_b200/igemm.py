@@ -1,0 +1,217 @@
+"""Host-side plumbing for the implicit-GEMM kernels: geometry, activation buffers, packed weights, launches.
+
+Everything here is bookkeeping around the C ABI (``gpemsr_igemm`` and friends in include/gpemsr_b200.h):
+PyTorch only provides device memory and the stream.  The activation format is described in the header
+("padded K8-blocked"); ``Geom`` mirrors ``gpemsr_geom_t`` and ``IgemmDesc`` mirrors ``gpemsr_igemm_desc_t``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+
+class GeomC(C.Structure):
+    _fields_ = [('n', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('padded', C.c_int32),
+                ('r_img', C.c_int64), ('m0', C.c_int64), ('rows_alloc', C.c_int64)]
+
+
+class IgemmDesc(C.Structure):
+    _fields_ = [('a_hi', C.c_void_p), ('a_lo', C.c_void_p), ('b_hi', C.c_void_p), ('b_lo', C.c_void_p),
+                ('a_geom', GeomC),
+                ('k_pad', C.c_int32), ('taps', C.c_int32), ('tap_dy', C.c_int32 * 49), ('tap_dx', C.c_int32 * 49),
+                ('b_rows', C.c_int32), ('n_cols', C.c_int32), ('split', C.c_int32),
+                ('scale', C.c_float), ('bias', C.c_void_p), ('bias_per_row', C.c_int32), ('act', C.c_int32),
+                ('slope', C.c_float), ('residual', C.c_void_p),
+                ('o_geom', GeomC),
+                ('up', C.c_int32), ('py', C.c_int32), ('px', C.c_int32), ('pixel_shuffle', C.c_int32), ('c_off', C.c_int32),
+                ('out_f32', C.c_void_p), ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
+                ('out_nchw', C.c_void_p), ('nchw_c', C.c_int32),
+                ('out_rowmajor', C.c_void_p), ('ld', C.c_int64),
+                ('err_flag', C.c_void_p)]
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Geom:
+    """Row geometry of a flattened image batch (mirrors gpemsr_geom_t)."""
+
+    def __init__(self, n, h, w, padded=True, m0=None, rows_alloc=None, r_img=None):
+        self.n, self.h, self.w, self.padded = int(n), int(h), int(w), bool(padded)
+        per = (h + 2) * (w + 2) if padded else h * w
+        self.r_img = _round_up(per, 128) if r_img is None else int(r_img)
+        margin = _round_up(w + 3, 128) if padded else 0
+        self.m0 = margin if m0 is None else int(m0)
+        # tail: room for the +1-row tap shifts (padded) / for a last column tile read as B operand (compact)
+        tail = margin if padded else 256
+        self.rows_alloc = (self.m0 + self.n * self.r_img + tail) if rows_alloc is None else int(rows_alloc)
+
+    @property
+    def c(self):
+        return GeomC(self.n, self.h, self.w, int(self.padded), self.r_img, self.m0, self.rows_alloc)
+
+    def sample(self, i):
+        """The same storage seen as the single image i (used to run per-sample GEMMs on a batch buffer)."""
+        return Geom(1, self.h, self.w, self.padded, m0=self.m0 + i * self.r_img, rows_alloc=self.rows_alloc, r_img=self.r_img)
+
+    def key(self):
+        return (self.n, self.h, self.w, self.padded)
+
+
+class Act:
+    """An activation tensor in the internal format: optional fp32 master + optional (hi, lo) bf16 operand planes."""
+
+    def __init__(self, geom, c, device, f32=False, planes=True, split=3):
+        self.geom, self.c = geom, int(c)
+        self.c_pad = _round_up(self.c, 64)
+        shape = (self.c_pad // 8, geom.rows_alloc, 8)
+        self.f32 = torch.zeros(shape, dtype=torch.float32, device=device) if f32 else None
+        self.hi = torch.zeros(shape, dtype=torch.bfloat16, device=device) if planes else None
+        self.lo = torch.zeros(shape, dtype=torch.bfloat16, device=device) if (planes and split == 3) else None
+
+
+class Weights:
+    """B-operand planes [taps][k_pad/8][b_rows][8] packed once from a reference-layout parameter."""
+
+    def __init__(self, w, kind, taps=None, split=3, block_rows=256):
+        """kind: 'conv' [co, ci, kh, kw] | 'convT' [ci, co, kh, kw] | 'linear' [n, k].
+        taps: list of (src_index, dy, dx); default = all kh*kw taps of a 'same' convolution."""
+        w = w.detach().contiguous().float()
+        dev = w.device
+        if kind == 'conv':
+            co, ci, kh, kw = w.shape
+            n, k, n_stride, k_stride = co, ci, ci * kh * kw, kh * kw
+            if taps is None:
+                taps = [(ky * kw + kx, ky - kh // 2, kx - kw // 2) for ky in range(kh) for kx in range(kw)]
+        elif kind == 'convT':
+            ci, co, kh, kw = w.shape
+            n, k, n_stride, k_stride = co, ci, kh * kw, co * kh * kw
+            assert taps is not None
+        elif kind == 'linear':
+            n, k = w.shape
+            n_stride, k_stride = k, 1
+            taps = [(0, 0, 0)]
+        else:
+            raise ValueError(kind)
+        self.n, self.k = n, k
+        self.k_pad = _round_up(k, 64)
+        self.b_rows = _round_up(n, 16) if n <= 16 else _round_up(n, 64) if n <= 64 else _round_up(n, 128) if n <= 128 \
+            else _round_up(n, block_rows)
+        self.taps = [(dy, dx) for _, dy, dx in taps]
+        src = torch.tensor([t[0] for t in taps], dtype=torch.int32, device=dev)
+        shape = (len(taps), self.k_pad // 8, self.b_rows, 8)
+        self.hi = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+        self.lo = torch.empty(shape, dtype=torch.bfloat16, device=dev) if split == 3 else None
+        _lib.check(_lib.lib().gpemsr_pack_weights(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src),
+                                                  self.b_rows, self.k_pad, _lib.ptr(self.hi), _lib.ptr(self.lo),
+                                                  _lib.stream_ptr()))
+        self._keep = (w, src)
+
+
+def convT_phase_taps(py, px):
+    """ConvTranspose2d(k3, s2, p1, op1): output (2a+py, 2b+px) = sum over the listed (ky, kx) of
+    in(a + dy, b + dx) * W[:, :, ky, kx]  with  oy = 2*iy - 1 + ky  (model/blocks.py:35)."""
+    ks = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}          # parity -> [(k index, input offset)]
+    return [(ky * 3 + kx, dy, dx) for ky, dy in ks[py] for kx, dx in ks[px]]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row=False, act=ACT_NONE, slope=0.0,
+          residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, c_off=0,
+          out_f32=True, out_planes=True, out_nchw=None, nchw_c=0, out_rowmajor=None, ld=0,
+          b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None):
+    """One fused implicit-GEMM launch.  `a`: Act (A operand); `w`: Weights or None when b_* are given explicitly;
+    `out`: Act receiving fp32 master / planes (whichever it owns and the flags allow)."""
+    d = IgemmDesc()
+    d.a_hi, d.a_lo = _p(a.hi), _p(a.lo)
+    d.a_geom = (a_geom or a.geom).c
+    if w is not None:
+        d.b_hi, d.b_lo, d.b_rows, d.k_pad = _p(w.hi), _p(w.lo), w.b_rows, w.k_pad
+        tp = w.taps
+        d.n_cols = w.n if n_cols is None else n_cols
+    else:
+        d.b_hi, d.b_lo, d.b_rows, d.k_pad = b_hi, b_lo, b_rows, k_pad
+        tp = taps or [(0, 0)]
+        d.n_cols = n_cols
+    d.taps = len(tp)
+    for i, (dy, dx) in enumerate(tp):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.split = split
+    d.scale = scale
+    d.bias, d.bias_per_row, d.act, d.slope = _p(bias), int(bias_per_row), act, slope
+    d.residual = _p(residual)
+    og = o_geom or (out.geom if out is not None else (a_geom or a.geom))
+    d.o_geom = og.c
+    d.up, d.py, d.px, d.pixel_shuffle, d.c_off = up, py, px, int(pixel_shuffle), c_off
+    if out is not None:
+        d.out_f32 = _p(out.f32) if out_f32 else None
+        d.out_hi = _p(out.hi) if out_planes else None
+        d.out_lo = _p(out.lo) if out_planes else None
+    d.out_nchw, d.nchw_c = _p(out_nchw), nchw_c
+    d.out_rowmajor, d.ld = _p(out_rowmajor), ld
+    d.err_flag = _p(err)
+    _lib.check(_lib.lib().gpemsr_igemm(C.byref(d), _lib.stream_ptr()))
+
+
+def pack_nchw(x, act, c_off=0):
+    x = x.contiguous()
+    g = act.geom.c
+    _lib.check(_lib.lib().gpemsr_act_pack_nchw(_lib.ptr(x), x.shape[1], C.byref(g), c_off, _lib.ptr(act.f32),
+                                               _lib.ptr(act.hi), _lib.ptr(act.lo), _lib.stream_ptr()))
+
+
+def unpack_nchw(act, c=None, c_off=0):
+    g = act.geom
+    c = act.c if c is None else c
+    out = torch.empty(g.n, c, g.h, g.w, dtype=torch.float32, device=act.f32.device)
+    gc = g.c
+    _lib.check(_lib.lib().gpemsr_act_unpack_nchw(_lib.ptr(act.f32), c, C.byref(gc), c_off, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+class GroupNormScratch:
+    def __init__(self, n, c, device):
+        self.sums = torch.zeros(n, c, 2, dtype=torch.float64, device=device)
+        self.ss = torch.empty(n, c, 2, dtype=torch.float32, device=device)
+
+
+def group_norm_act(x, gamma, beta, scratch, out, act=ACT_NONE, slope=0.0, residual=None, groups=32, eps=1e-6,
+                   out_f32=True, out_planes=True):
+    """GroupNorm(32, eps=1e-6) of the fp32 master of `x` (model/blocks.py:5-6), then act (+ residual) into `out`."""
+    L = _lib.lib()
+    g = x.geom.c
+    og = out.geom.c
+    st = _lib.stream_ptr()
+    _lib.check(L.gpemsr_gn_stats(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.sums), st))
+    _lib.check(L.gpemsr_gn_scale_shift(_lib.ptr(scratch.sums), _lib.ptr(gamma), _lib.ptr(beta), x.geom.n, x.c, groups,
+                                       float(x.geom.h * x.geom.w), eps, _lib.ptr(scratch.ss), st))
+    _lib.check(L.gpemsr_affine_act(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.ss), act, slope, _lib.ptr(residual),
+                                   C.byref(og), _lib.ptr(out.f32) if out_f32 else None,
+                                   _lib.ptr(out.hi) if out_planes else None, _lib.ptr(out.lo) if out_planes else None, st))
+
+
+def softmax_rows_blocked(s, t, ld, t_pad, stats, p_hi, p_lo):
+    _lib.check(_lib.lib().gpemsr_softmax_rows_blocked(_lib.ptr(s), t, ld, t_pad, _lib.ptr(stats), _lib.ptr(p_hi),
+                                                      _lib.ptr(p_lo), _lib.stream_ptr()))
+
+
+def add_bilinear_base(x_center, scale, out):
+    n, _, h, w = x_center.shape
+    _lib.check(_lib.lib().gpemsr_add_bilinear_base(_lib.ptr(x_center.contiguous()), n, h, w, scale, _lib.ptr(out),
+                                                   _lib.stream_ptr()))
+
+
+def check_pipeline(err):
+    """Synchronises and raises if any GEMM pipeline timed out (tests / smoke only; the hot path never syncs)."""
+    code = int(err.item())
+    if code:
+        raise _lib.GpemsrError(-4, f'GEMM pipeline timed out at wait site {code}')

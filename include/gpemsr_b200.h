@@ -92,6 +92,89 @@ GPEMSR_API int gpemsr_logits_argmax_gather(const float* feat, const float* w, co
 GPEMSR_API int gpemsr_argmax_gather(const float* p, const float* emb, int b, int64_t hw, int k, int dq,
                          float* zq, int64_t* idx, gpemsr_stream_t stream);
 
+/* ---- a-3 / a-4: implicit-GEMM convolutions, GroupNorm, non-local attention --------------------------
+ * Replaces the cuDNN / cuBLAS / ATen calls behind Decoder.forward / multi_scale_feat_calculate
+ * (model/decoder.py:37-57), ResidualBlock / UpBlock / NonLocalBlock (model/blocks.py:8-83) and the SR tail of
+ * GPEMSR.forward (model/GPEMSR.py:441-455).  gpemsr_b200/decoder.py and gpemsr_b200/sr_tail.py chain these.
+ *
+ * Internal activation format ("padded K8-blocked"): an image batch [n, c, h, w] is flattened to rows
+ *     row(i, y, x) = m0 + i * r_img + (y + 1) * (w + 2) + (x + 1)          (one zero ring around every image)
+ * and stored per group of 8 channels as [c_pad/8][rows_alloc][8]: an fp32 master and/or (hi, lo) bf16 planes with
+ * hi = bf16(v), lo = bf16(v - hi).  A 3x3 tap is then a ROW SHIFT of the A operand, so a convolution is 9 shifted
+ * GEMMs accumulated in TMEM -- no im2col buffer.  Ring / tail rows are never written and must stay zero (buffers
+ * are zeroed once by the caller).  "Compact" tensors (attention tokens) use row(i, y, x) = i * r_img + y * w + x. */
+typedef struct gpemsr_geom {
+  int32_t n, h, w;         /* images, height, width */
+  int32_t padded;          /* 1: zero ring (wp = w + 2), 0: compact */
+  int64_t r_img;           /* rows reserved per image (multiple of 128) */
+  int64_t m0;              /* first row of image 0 (>= w + 3 when padded) */
+  int64_t rows_alloc;      /* rows allocated per 8-channel plane */
+} gpemsr_geom_t;
+
+typedef struct gpemsr_igemm_desc {
+  /* A operand: activations (rows) ; B operand: weights / keys (columns), both K8-blocked bf16 */
+  const void* a_hi; const void* a_lo;       /* [k_pad/8][a_geom.rows_alloc][8] */
+  const void* b_hi; const void* b_lo;       /* [taps][k_pad/8][b_rows][8] */
+  gpemsr_geom_t a_geom;                     /* rows computed = n * r_img starting at m0 */
+  int32_t k_pad;                            /* reduction length per tap (multiple of 64) */
+  int32_t taps;                             /* 1..49 */
+  int32_t tap_dy[49], tap_dx[49];           /* A row shift of tap t = dy * (w + 2) + dx */
+  int32_t b_rows;                           /* allocated B rows per tap (multiple of block_n) */
+  int32_t n_cols;                           /* valid output columns (channels) */
+  int32_t split;                            /* 3: hi/lo planes, fp32-faithful ; 1: single bf16 pass (a_lo/b_lo unused) */
+  /* epilogue: v = act(scale * acc + bias) + residual */
+  float scale;
+  const float* bias;                        /* [n_cols] or, if bias_per_row, indexed by output row within the image */
+  int32_t bias_per_row;
+  int32_t act; float slope;                 /* GPEMSR_ACT_* */
+  const float* residual;                    /* fp32 master in the OUTPUT geometry / channel blocking, or NULL */
+  /* output placement */
+  gpemsr_geom_t o_geom;                     /* geometry of the blocked outputs */
+  int32_t up;                               /* 1: same resolution ; 2: output pixel (2y + py, 2x + px) */
+  int32_t py, px;
+  int32_t pixel_shuffle;                    /* 1: column c*4 + dy*2 + dx -> channel c at (2y + dy, 2x + dx) (up must be 2) */
+  int32_t c_off;                            /* first output channel (multiple of 8) inside the output tensors */
+  float* out_f32;                           /* fp32 master [co_pad/8][o_geom.rows_alloc][8] or NULL */
+  void* out_hi; void* out_lo;               /* bf16 planes or NULL */
+  float* out_nchw; int32_t nchw_c;          /* reference layout [n, nchw_c, up*h, up*w] or NULL */
+  float* out_rowmajor; int64_t ld;          /* [rows, ld] fp32 (attention scores), rows relative to m0, or NULL */
+  int32_t* err_flag;                        /* device int: set when the pipeline times out (never hangs) */
+} gpemsr_igemm_desc_t;
+
+GPEMSR_API int gpemsr_igemm(const gpemsr_igemm_desc_t* desc, gpemsr_stream_t stream);
+
+/* NCHW fp32 <-> internal format.  pack writes whichever of f32 / hi / lo are non-NULL (channels c_off..c_off+c-1). */
+GPEMSR_API int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* g, int c_off,
+                         float* f32, void* hi, void* lo, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int c_off, float* x,
+                           gpemsr_stream_t stream);
+/* weights -> B operand planes.  src element (col n, k, tap t) = w[n * n_stride + k * k_stride + tap_src[t]].
+ * Conv2d weight [co, ci, kh, kw]: n_stride = ci*kh*kw, k_stride = kh*kw ; ConvTranspose2d [ci, co, kh, kw]:
+ * n_stride = kh*kw, k_stride = co*kh*kw ; Linear [n, k]: n_stride = k, k_stride = 1, one tap. */
+GPEMSR_API int gpemsr_pack_weights(const float* w, int n, int k, int64_t n_stride, int64_t k_stride, int taps,
+                        const int32_t* tap_src, int b_rows, int k_pad, void* hi, void* lo, gpemsr_stream_t stream);
+
+/* GroupNorm(32 groups, eps) over an fp32 master (model/blocks.py:5-6): stats -> per-(image, channel) scale/shift,
+ * then y = act(x * scale + shift) (+ residual) written as fp32 master and/or hi/lo planes, optionally re-rowed
+ * into a compact geometry (attention tokens).  chan_sums: [n, c, 2] doubles (zeroed by gn_stats). */
+GPEMSR_API int gpemsr_gn_stats(const float* x_f32, int c, const gpemsr_geom_t* g, double* chan_sums,
+                    gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_gn_scale_shift(const double* chan_sums, const float* gamma, const float* beta, int n, int c,
+                          int groups, double count_per_channel, float eps, float* scale_shift /* [n, c, 2] */,
+                          gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const float* scale_shift,
+                      int act, float slope, const float* residual, const gpemsr_geom_t* og,
+                      float* out_f32, void* out_hi, void* out_lo, gpemsr_stream_t stream);
+
+/* softmax over the last dim of fp32 scores s [t, ld] (first t columns valid; model/blocks.py:76) ->
+ * probabilities as K8-blocked bf16 A operand planes [t_pad/8][t_pad][8] (hi, lo). */
+GPEMSR_API int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t_pad, float* row_stats /* [t,2] */,
+                                void* p_hi, void* p_lo, gpemsr_stream_t stream);
+
+/* out[i, 0, y, x] += bilinear_upsample(x_center, scale, align_corners=False)  (model/GPEMSR.py:452-455) */
+GPEMSR_API int gpemsr_add_bilinear_base(const float* x_center, int n, int h, int w, int scale, float* out,
+                             gpemsr_stream_t stream);
+
 /* ---- self-test of the tcgen05 GEMM core (used by tests/, not by the product path) ------
  * D[m,n] = A[m,k] * B[n,k]^T, fp32 row-major; split = 1 (single bf16 pass) or 3 (hi/lo bf16,
  * fp32-faithful); block_n in {64,128,256}.  _status() synchronises and reports pipeline time-outs. */

@@ -42,10 +42,29 @@ def flow_warp_bench():
     return out
 
 
+def vq_bench(sizes=((1 << 20, 512), (1 << 20, 256), (1 << 16, 512))):
+    from oracle import ref_ops as R
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    out = []
+    for n, d in sizes:
+        z = torch.randn(1, d, n, 1, device='cuda')
+        emb = torch.randn(1024, d, device='cuda')
+        med, best = timeit(lambda: gpemsr_b200.vq_lookup(z, emb), iters=5, flush=flush)
+        flops = 2.0 * n * 1024 * d
+        byt = 8.0 * n * d + 8 * n + 4096 * d
+        torch.backends.cuda.matmul.allow_tf32 = False
+        med_t, _ = timeit(lambda: R.codebook_forward(z, emb), iters=3, warm=1, flush=flush)
+        out.append(dict(op='vq_lookup', n=n, d=d, ms=med, ms_best=best, tflops=flops / med / 1e9, tc_frac=flops / med / 1e9 / 1649.2,
+                        gbs=byt / med / 1e6, hbm_frac=byt / med / 1e6 / 6550.1, torch_ref_ms=med_t))
+    return out
+
+
 if __name__ == '__main__':
     torch.cuda.init()
     res = []
     if 'flow' in sys.argv[1:] or len(sys.argv) == 1:
         res += flow_warp_bench()
+    if 'vq' in sys.argv[1:] or len(sys.argv) == 1:
+        res += vq_bench()
     for r in res:
         print(json.dumps(r))
