@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- GPEMSR inference hot path on B200: HR megapixels / s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--no-cpu-baseline]
+
+A "step" is one pass of the hot path over one slice window of BASELINE.json configs[1]
+(GPEMSR x16, N_frames = 5 per option/output_GPEMSR_x16.yml, 80x80 LR -> 1280x1280 HR; 78x78 cannot run through the
+reference):
+
+    a-2  Indexer head Linear(512->1024) + softmax/top-1 + codebook gather on the 5 x 512 x 80 x 80 latents
+    a-3  Decoder.multi_scale_feat_calculate on the 5 quantised latents  (-> 5 x 1 x 1280 x 1280 reference images)
+    a-5  the 60 flow_warp calls SpyNet makes per forward (5 frames x 2 calls x 6 pyramid levels, 3 x 10^2 .. 3 x 320^2)
+    a-4  the SR tail on the fused 64 x 80 x 80 feature (-> 1 x 1 x 1280 x 1280)
+
+`value` times the step with inputs resident in HBM; `e2e` re-times it through the same public API with every step
+input coming from pinned host memory and the HR slice read back.  N > 1: one process per GPU (torchrun), each rank
+processes its own slice windows (weak scaling, no collective on the hot path); the HR slices are all-gathered (NCCL)
+once per step.  `--impl reference` times the CPU restatement of the reference (oracle/, PyTorch fp32, all host cores)
+on a bounded LR crop of the same window.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCALE, NFRAMES, LR = 16, 5, 80
+DEC_CFG = dict(channel_list=[512, 256, 128, 64, 64], im_channel=1, num_resblock_per_scale=1, num_input_resblck=3,
+               latent_dim=512, use_non_local=True)
+METRIC, UNIT = 'hr_megapixels_per_s', 'MP/s'
+
+
+def warp_levels(lr):
+    """SpyNet pyramid sizes for frames upsampled x4 (model/GPEMSR.py:99) and resized to a multiple of 32."""
+    s = -(-(4 * lr) // 32) * 32
+    return [s >> k for k in range(5, -1, -1)]
+
+
+def make_inputs(lr, nframes, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    ins = {
+        'feat': torch.randn(nframes, 512, lr, lr, generator=g),            # Indexer output_layer result
+        'fea': torch.randn(1, 64, lr, lr, generator=g),                    # ThreeDA output
+        'x_center': torch.rand(1, 1, lr, lr, generator=g),
+    }
+    for i, s in enumerate(warp_levels(lr)):
+        ins[f'warp_x{i}'] = torch.randn(2 * nframes, 3, s, s, generator=g)       # one batch row per SpyNet call
+        ins[f'warp_f{i}'] = 1.5 * torch.randn(2 * nframes, s, s, 2, generator=g)
+    if pin:
+        ins = {k: v.pin_memory() for k, v in ins.items()}
+    return ins
+
+
+def make_weights(seed=1):
+    from oracle import weights as W      # deterministic random-init parameters (no checkpoints offline)
+    return dict(dec=W.fill(W.decoder_spec(), seed), emb=W.fill(W.codebook_spec(), seed + 1)['embedding.weight'],
+                head=W.fill(W.indexer_head_spec(), seed + 2), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
+
+
+# ----------------------------------------------------------------------------------------------- native arm
+class NativeHotPath:
+    def __init__(self, wts, device):
+        import gpemsr_b200
+        self.g = gpemsr_b200
+        self.cb = gpemsr_b200.Codebook({'num_codebook_vectors': 1024, 'latent_dim': 512, 'beta': 1}).to(device)
+        self.cb.load_state_dict({'embedding.weight': wts['emb']})
+        self.dec = gpemsr_b200.Decoder(DEC_CFG).to(device)
+        self.dec.load_state_dict(wts['dec'], strict=True)
+        self.tail = gpemsr_b200.SRTail(64, 10, SCALE).to(device)
+        self.tail.load_state_dict(wts['tail'], strict=True)
+        self.hw = wts['head']['embedding.weight'].to(device)
+        self.hb = wts['head']['embedding.bias'].to(device)
+
+    def step(self, d):
+        zq = self.cb.inference_from_feat(d['feat'], self.hw, self.hb)
+        feats = self.dec.multi_scale_feat_calculate(zq)
+        nlev = len([k for k in d if k.startswith('warp_x')])
+        for i in range(nlev):
+            x, f = d[f'warp_x{i}'], d[f'warp_f{i}']
+            for j in range(x.shape[0]):                 # the reference issues these one SpyNet level at a time
+                self.g.flow_warp(x[j:j + 1], f[j:j + 1], 'bilinear', 'border')
+        out = self.tail(d['fea'], d['x_center'])
+        return out, feats
+
+
+# ----------------------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_step(wts, ins):
+    from oracle import ref_ops as R
+    from oracle.flow_warp import flow_warp_torch
+    with torch.no_grad():
+        feats, _ = R.ref_extract_from_feat(ins['feat'], wts['head'], wts['emb'], wts['dec'])
+        i = 0
+        while f'warp_x{i}' in ins:
+            x, f = ins[f'warp_x{i}'], ins[f'warp_f{i}']
+            for j in range(x.shape[0]):
+                flow_warp_torch(x[j:j + 1], f[j:j + 1], 'bilinear', 'border')
+            i += 1
+        out = R.sr_tail(ins['fea'], ins['x_center'], wts['tail'], SCALE)
+    return out, feats
+
+
+def cpu_time(wts, lr, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    ins = make_inputs(lr, NFRAMES, seed=7)
+    for _ in range(warmup):
+        cpu_step(wts, ins)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(wts, ins)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, (SCALE * lr) ** 2 / 1e6 / dt
+
+
+def pick_cpu_crop(wts, budget_s):
+    """Largest LR crop (multiple of 4, <= 80) whose step fits `budget_s`, from a 16x16 probe (cost ~ pixels)."""
+    dt, _ = cpu_time(wts, 16, 1, 1)
+    per_px = dt / 256.0
+    lr = int((budget_s / per_px) ** 0.5) // 4 * 4
+    return max(8, min(LR, lr))
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        if not self.path or not os.path.exists(self.path):
+            return None
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(',')]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx = max(mx, float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf=d.get('bf16_tflops_sustained', d['bf16_tflops']), tf_burst=d['bf16_tflops'], src='measured')
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src='fallback')
+
+
+def instrumented_step(hp, dev_in):
+    """One extra step with CUDA events around every GEMM launch (on the launching stream): per-kernel-class time and
+    algorithmic FLOPs (2 * valid rows * cols * k * taps -- one pass, no padding, no split factor)."""
+    from gpemsr_b200 import igemm as G
+    rec = []
+    orig = G.igemm
+
+    def wrapped(a, w, err, **kw):
+        geom = kw.get('a_geom') or a.geom
+        rows = geom.n * geom.h * geom.w
+        if w is not None:
+            n, k, taps = (kw.get('n_cols') or w.n), w.k, len(w.taps)
+        else:
+            n, k, taps = kw['n_cols'], kw['k_pad'], 1
+        bn = 16 if (n <= 16 and not kw.get('pixel_shuffle')) else 64 if n <= 64 else 128 if n <= 128 else 256
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(a, w, err, **kw)
+        e.record()
+        rec.append((f'gemm_kernel<{bn},split{kw.get("split", 3)}>', 2.0 * rows * n * k * taps, s, e))
+
+    G.igemm = wrapped
+    import gpemsr_b200.decoder as D
+    import gpemsr_b200.sr_tail as S
+    try:
+        hp.step(dev_in)
+        torch.cuda.synchronize()
+    finally:
+        G.igemm = orig
+    agg = {}
+    for name, fl, s, e in rec:
+        a = agg.setdefault(name, [0.0, 0.0, 0])
+        a[0] += fl; a[1] += s.elapsed_time(e); a[2] += 1
+    return agg
+
+
+def micro_rooflines(peaks):
+    """The two kernel-level numbers BASELINE.json's metric also names: VQ lookup TC fraction and flow_warp HBM fraction."""
+    import gpemsr_b200
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def med(fn, iters=5, warm=3):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sorted(ts)[len(ts) // 2]
+
+    n, d = 1 << 20, 512
+    z = torch.randn(1, d, n, 1, device='cuda')
+    emb = torch.randn(1024, d, device='cuda')
+    ms = med(lambda: gpemsr_b200.vq_lookup(z, emb))
+    fl = 2.0 * n * 1024 * d
+    out['vq_lookup'] = {'bound': 'tensor', 'shape': f'N=2^20 x D={d} vs 1024 codes', 'ms': ms, 'achieved': fl / ms / 1e9,
+                        'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': fl / ms / 1e9 / peaks['tf_burst'],
+                        'note': 'whole lookup (prep + GEMM + re-score + gather), L2 flushed'}
+    del z
+    c, s = 64, 1250
+    x = torch.randn(1, c, s, s, device='cuda')
+    f = torch.nn.functional.avg_pool2d(2.0 * torch.randn(1, 2, s, s, device='cuda'), 5, 1, 2).permute(0, 2, 3, 1).contiguous()
+    ms = med(lambda: gpemsr_b200.flow_warp(x, f, 'bilinear', 'border'))
+    by = 8.0 * c * s * s + 8.0 * s * s
+    out['flow_warp'] = {'bound': 'hbm', 'shape': f'{c} x {s}^2', 'ms': ms, 'achieved': by / ms / 1e6, 'peak': peaks['hbm'],
+                        'unit': 'GB/s', 'frac': by / ms / 1e6 / peaks['hbm']}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- main
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wts = make_weights()
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    lr = pick_cpu_crop(wts, budget)
+    dt, mps = cpu_time(wts, lr, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    sample = f'{NFRAMES}x{lr}x{lr} LR crop of the {NFRAMES}x{LR}x{LR} window ({SCALE * lr}^2 HR px per step)'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': mps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config_block(1),
+            'cpu_baseline': {'value': mps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': mps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_block(world):
+    return {'workload': f'GPEMSR x16 hot path (Indexer head + codebook lookup, VQ decoder multi-scale, 60 SpyNet flow_warp '
+                        f'calls, SR tail), {NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
+            'lr': LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
+            'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '
+            'exceeds the 126 MB L2; no explicit flush', 'precision': 'bf16 x3 split (fp32-faithful) on tcgen05'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-micro', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    import gpemsr_b200
+    wts = make_weights()
+    hp = NativeHotPath(wts, dev)
+    host_in = make_inputs(LR, NFRAMES, seed=100 + rank, pin=True)
+    dev_in = {k: v.to(dev) for k, v in host_in.items()}
+    hr_px = (SCALE * LR) ** 2
+    gathered = torch.empty(world, 1, 1, SCALE * LR, SCALE * LR, device=dev) if world > 1 else None
+
+    def step(d):
+        out, feats = hp.step(d)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out.unsqueeze(0))
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step(dev_in)
+    hp.dec.check(); hp.tail.check()
+
+    # ---- value: inputs resident in HBM
+    barrier()
+    l0 = gpemsr_b200.kernel_launches()
+    with ClockSampler(local) as cs:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            step(dev_in)
+        e.record()
+        barrier()
+    launches = gpemsr_b200.kernel_launches() - l0
+    ms = s.elapsed_time(e)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps * hr_px / 1e6 / (ms_total / 1e3)
+
+    # ---- e2e: every step input from pinned host memory, HR slice read back
+    stage = {k: torch.empty_like(v) for k, v in dev_in.items()}
+    out_host = torch.empty(1, 1, SCALE * LR, SCALE * LR).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        for k in stage:
+            stage[k].copy_(host_in[k], non_blocking=True)
+        out_host.copy_(step(stage), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e2.record()
+    barrier()
+    t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.steps * hr_px / 1e6 / (float(t2.item()) / 1e3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        agg = instrumented_step(hp, dev_in)
+        name, (fl, tms, cnt) = max(agg.items(), key=lambda kv: kv[1][1])
+        step_ms = ms_total / args.steps
+        prof = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        traffic = json.load(open(prof)).get(name) if os.path.exists(prof) else None
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': fl / tms / 1e9, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
+                'frac': fl / tms / 1e9 / peaks['tf'], 'traffic': traffic, 'launches_per_step': cnt,
+                'ms_per_launch': tms / cnt, 'share_of_step': tms / step_ms, 'peak_source': peaks['src'] + ' (bf16 sustained)',
+                'note': 'algorithmic FLOPs = 2*rows*cols*k*taps (one pass); the kernel issues 3 bf16 MMAs per product '
+                        '(fp32-faithful split), so frac <= 1/3 by construction',
+                'by_kernel': {k: {'tflops': v[0] / v[1] / 1e9, 'ms': v[1], 'launches': v[2]} for k, v in agg.items()}}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': W,
+                'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16x3->f32',
+                'data': 'synthetic', 'config': config_block(world), 'roofline': roof,
+                'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+                'gpu_launches': int(launches), 'clocks': cs.summary(), 'impl': 'native'}
+        if world == 1 and not args.no_micro:
+            line['micro'] = micro_rooflines(peaks)
+        if world == 1 and not args.no_cpu_baseline:
+            lr = pick_cpu_crop(wts, 20.0)
+            dt, mps = cpu_time(wts, lr, 1, 0)
+            line['cpu_baseline'] = {'value': mps, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                    'sample': f'1 step on a {NFRAMES}x{lr}x{lr} LR crop of the window ({dt:.1f} s of CPU work), '
+                                              'oracle/ref_ops.py on all host cores'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

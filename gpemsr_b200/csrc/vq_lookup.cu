@@ -145,63 +145,91 @@ struct EpiArgExtremum {
 
   struct State {
     float runmin = INFINITY;
+    float evicted_min = INFINITY;        // smallest score ever dropped because the list was full
     uint32_t cnt = 0;
-    bool overflow = false;
     uint32_t idx[CMAX];
     float val[CMAX];
   };
 
-  __device__ __forceinline__ void push(State& st, uint32_t code, float v, float thr) const {
-    if (st.cnt == CMAX) {               // drop entries the lowered minimum has left behind
+  // Append (code, v).  When the list is full, first drop entries the lowered minimum has left behind; if it is still
+  // full, evict the largest score and remember it: the row only needs the exact fallback if the FINAL threshold
+  // reaches an evicted score.
+  __device__ __noinline__ void push(State& st, uint32_t code, float v, float thr) const {
+    if (st.cnt == CMAX) {
       uint32_t n = 0;
       for (uint32_t i = 0; i < CMAX; ++i)
         if (st.val[i] <= thr) { st.idx[n] = st.idx[i]; st.val[n] = st.val[i]; ++n; }
       st.cnt = n;
     }
-    if (st.cnt == CMAX) { st.overflow = true; return; }
+    if (st.cnt == CMAX) {
+      uint32_t worst = 0;
+      for (uint32_t i = 1; i < CMAX; ++i)
+        if (st.val[i] > st.val[worst]) worst = i;
+      if (v >= st.val[worst]) { st.evicted_min = fminf(st.evicted_min, v); return; }
+      st.evicted_min = fminf(st.evicted_min, st.val[worst]);
+      for (uint32_t i = worst; i + 1 < CMAX; ++i) { st.idx[i] = st.idx[i + 1]; st.val[i] = st.val[i + 1]; }   // keep code order
+      st.cnt = CMAX - 1;
+    }
     st.idx[st.cnt] = code; st.val[st.cnt] = v; ++st.cnt;
   }
 
-  // one pass: a code is appended when it is within `margin` of the running minimum seen so far (records lower the
-  // minimum as they arrive); stale entries are dropped by push()'s compaction and by the final filter.
+  __device__ __forceinline__ float min32(const uint32_t (&r)[32], const float* __restrict__ cc, float mn) const {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 ck = __ldg(reinterpret_cast<const float4*>(cc + j));
+      mn = fminf(mn, fminf(fminf(fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), fmaf(alpha, __uint_as_float(r[j + 1]), ck.y)),
+                           fminf(fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), fmaf(alpha, __uint_as_float(r[j + 3]), ck.w))));
+    }
+    return mn;
+  }
   __device__ __forceinline__ void scan32(State& st, const uint32_t (&r)[32], const float* __restrict__ cc, uint32_t code0,
-                                         float mg, float& thr) const {
+                                         float thr) const {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 ck = __ldg(reinterpret_cast<const float4*>(cc + j));
       const float v0 = fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), v1 = fmaf(alpha, __uint_as_float(r[j + 1]), ck.y);
       const float v2 = fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), v3 = fmaf(alpha, __uint_as_float(r[j + 3]), ck.w);
       if (fminf(fminf(v0, v1), fminf(v2, v3)) <= thr) {
-        const float v[4] = {v0, v1, v2, v3};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (v[u] <= thr) {
-            if (v[u] < st.runmin) { st.runmin = v[u]; thr = v[u] + mg; }
-            push(st, code0 + j + u, v[u], thr);
-          }
-        }
+        if (v0 <= thr) push(st, code0 + j + 0, v0, thr);
+        if (v1 <= thr) push(st, code0 + j + 1, v1, thr);
+        if (v2 <= thr) push(st, code0 + j + 2, v2, thr);
+        if (v3 <= thr) push(st, code0 + j + 3, v3, thr);
       }
     }
   }
 
+  // Two passes over the tile's 256 accumulator columns, TMEM loads software-pipelined one 32-column chunk ahead:
+  // pass 1 lowers the row's running minimum, pass 2 appends every code within `margin` of it (a superset of the codes
+  // within `margin` of the FINAL minimum, since the running minimum only decreases).
   __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int) const {
     const long long gr = m_tile * gemm::BLOCK_M + row;
     const float* cc = c + (size_t)n_tile * VQ_BLOCK_N;
     const float mg = gr < rows ? __ldg(margin + gr) : 0.f;
-    float thr = st.runmin + mg;           // +inf on the first tile
     uint32_t ra[32], rb[32];
+    float mn = st.runmin;
     sm100::tmem_ld_32x32(tmem_acc, ra);
 #pragma unroll 1
     for (int c0 = 0; c0 < VQ_BLOCK_N; c0 += 64) {
       sm100::tmem_ld_wait();
-      sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);                    // prefetch the next 32 columns
-      scan32(st, ra, cc + c0, (uint32_t)(n_tile * VQ_BLOCK_N + c0), mg, thr);
+      sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);
+      mn = min32(ra, cc + c0, mn);
+      sm100::tmem_ld_wait();
+      sm100::tmem_ld_32x32(tmem_acc + ((c0 + 64) & (VQ_BLOCK_N - 1)), ra);     // wraps to column 0 for pass 2
+      mn = min32(rb, cc + c0 + 32, mn);
+    }
+    st.runmin = mn;
+    const float thr = mn + mg;
+#pragma unroll 1
+    for (int c0 = 0; c0 < VQ_BLOCK_N; c0 += 64) {
+      sm100::tmem_ld_wait();
+      sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);
+      scan32(st, ra, cc + c0, (uint32_t)(n_tile * VQ_BLOCK_N + c0), thr);
       sm100::tmem_ld_wait();
       if (c0 + 64 < VQ_BLOCK_N) sm100::tmem_ld_32x32(tmem_acc + c0 + 64, ra);
-      scan32(st, rb, cc + c0 + 32, (uint32_t)(n_tile * VQ_BLOCK_N + c0 + 32), mg, thr);
+      scan32(st, rb, cc + c0 + 32, (uint32_t)(n_tile * VQ_BLOCK_N + c0 + 32), thr);
     }
     if (n_tile == n_tiles - 1 && gr < rows) {
-      if (st.overflow) { cand_cnt[gr] = OVERFLOW; return; }
+      if (st.evicted_min <= thr) { cand_cnt[gr] = OVERFLOW; return; }
       uint32_t n = 0, only = 0;
       for (uint32_t i = 0; i < st.cnt; ++i)
         if (st.val[i] <= thr) { only = st.idx[i]; ++n; }

@@ -67,10 +67,10 @@ class _Plan:
             self.bufs[key] = a
         return a
 
-    def weights(self, name, param, kind, taps=None):
+    def weights(self, name, param, kind, taps=None, min_rows=0):
         wt = self.wts.get(name)
         if wt is None:
-            wt = G.Weights(param, kind, taps=taps, split=self.split)
+            wt = G.Weights(param, kind, taps=taps, split=self.split, min_rows=min_rows)
             self.wts[name] = wt
         return wt
 
@@ -165,10 +165,10 @@ class Decoder(nn.Module):
         G.igemm(hn, P.weights(name + '.q', nl.q.weight, 'conv'), P.err, split=P.split, bias=nl.q.bias.detach(), out=q, out_f32=False)
         G.igemm(hn, P.weights(name + '.k', nl.k.weight, 'conv'), P.err, split=P.split, bias=nl.k.bias.detach(), out=k, out_f32=False)
         # v^T [tokens/8][channels][8]: weights as the A operand, tokens as columns, bias per row
-        wv = P.weights(name + '.v', nl.v.weight, 'conv')
-        c_rows = wv.b_rows
-        wgeom = G.Geom(1, 1, c, padded=False, r_img=G._round_up(c_rows, 128), m0=0, rows_alloc=c_rows)
-        assert c_rows % 128 == 0, 'attention width must be a multiple of 128'
+        wv = P.weights(name + '.v', nl.v.weight, 'conv', min_rows=128)      # used as the A operand: >= one 128-row tile
+        c_rows = G._round_up(wv.b_rows, 128)
+        assert c_rows == wv.b_rows
+        wgeom = G.Geom(1, 1, c, padded=False, r_img=c_rows, m0=0, rows_alloc=c_rows)
         wa = _View(wv.hi[0], wv.lo[0] if wv.lo is not None else None, wgeom)
         vt = P.bufs.get(name + '.vt')
         if vt is None:

@@ -79,7 +79,7 @@ class Act:
 class Weights:
     """B-operand planes [taps][k_pad/8][b_rows][8] packed once from a reference-layout parameter."""
 
-    def __init__(self, w, kind, taps=None, split=3, block_rows=256):
+    def __init__(self, w, kind, taps=None, split=3, block_rows=256, min_rows=0):
         """kind: 'conv' [co, ci, kh, kw] | 'convT' [ci, co, kh, kw] | 'linear' [n, k].
         taps: list of (src_index, dy, dx); default = all kh*kw taps of a 'same' convolution."""
         w = w.detach().contiguous().float()
@@ -103,6 +103,7 @@ class Weights:
         self.k_pad = _round_up(k, 64)
         self.b_rows = _round_up(n, 16) if n <= 16 else _round_up(n, 64) if n <= 64 else _round_up(n, 128) if n <= 128 \
             else _round_up(n, block_rows)
+        self.b_rows = max(self.b_rows, min_rows)
         self.taps = [(dy, dx) for _, dy, dx in taps]
         src = torch.tensor([t[0] for t in taps], dtype=torch.int32, device=dev)
         shape = (len(taps), self.k_pad // 8, self.b_rows, 8)

@@ -1,0 +1,47 @@
+"""CPU: slice sharding and the output gather (world_size 2, gloo)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpemsr_b200.volume import gather_slices, shard_range, window_indices
+
+
+def test_shard_range_partitions():
+    for n, w in ((125, 8), (125, 1), (7, 8), (0, 3), (16, 4)):
+        blocks = [shard_range(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    assert [b - a for a, b in (shard_range(125, 8, r) for r in range(8))] == [16] * 5 + [15] * 3
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_window_indices_replicate_edges():
+    assert window_indices(0, 125) == [0, 0, 0, 1, 2]          # output_GPEMSR.py:55-60
+    assert window_indices(1, 125) == [0, 0, 1, 2, 3]          # :71-76
+    assert window_indices(60, 125) == [58, 59, 60, 61, 62]
+    assert window_indices(123, 125) == [121, 122, 123, 124, 124]   # :100-105
+    assert window_indices(124, 125) == [122, 123, 124, 124, 124]   # :116-121
+
+
+def _worker(rank, world, port, n_units):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = shard_range(n_units, world, rank)
+    local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1) * torch.ones(1, 2, 3)
+    full = gather_slices(local, n_units, world, rank, dist)
+    assert full.shape == (n_units, 2, 3)
+    assert torch.equal(full[:, 0, 0], torch.arange(n_units, dtype=torch.float32))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_two_ranks_gloo():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, 7), nprocs=2, join=True)

@@ -64,6 +64,8 @@ if __name__ == '__main__':
     res = []
     if 'flow' in sys.argv[1:] or len(sys.argv) == 1:
         res += flow_warp_bench()
+    if 'vq1' in sys.argv[1:]:
+        res += vq_bench(sizes=((1 << 20, 512),))
     if 'vq' in sys.argv[1:] or len(sys.argv) == 1:
         res += vq_bench()
     for r in res:
