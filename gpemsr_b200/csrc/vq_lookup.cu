@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr int CMAX = 8;              // candidates a row may carry; more -> exact scan of every code for that row
+constexpr int CMAX = 16;             // candidate-list slots per row; more appends -> exact scan of every code for that row
 constexpr int VQ_BLOCK_N = 256;
 constexpr uint32_t OVERFLOW = 0xFFFFFFFFu;
 constexpr int FIN_ROWS = 32;         // rows per finalize block
@@ -42,7 +42,8 @@ struct Workspace {
   float* zz;              // [rows_pad]
   float* margin;          // [rows_pad]
   uint32_t* cand_cnt;     // [rows_pad]  0 = decided in the epilogue, n = ambiguous with n candidates, OVERFLOW
-  uint32_t* cand;         // [rows_pad][CMAX] code indices (ascending)
+  uint2* cand;            // [rows_pad][CMAX] (code, approx score), ascending code order
+  float* runmin;          // [rows_pad] final approximate minimum
   float* emax;            // [1] max_k |e_k|_2   (as float bits, written with atomicMax)
   int* err;               // [1] GEMM pipeline error flag
   size_t bytes;
@@ -60,7 +61,8 @@ Workspace carve(void* base, long long rows, int d, int k) {
   w.zz = (float*)take((size_t)rows_pad * 4);
   w.margin = (float*)take((size_t)rows_pad * 4);
   w.cand_cnt = (uint32_t*)take((size_t)rows_pad * 4);
-  w.cand = (uint32_t*)take((size_t)rows_pad * CMAX * 4);
+  w.cand = (uint2*)take((size_t)rows_pad * CMAX * 8);
+  w.runmin = (float*)take((size_t)rows_pad * 4);
   w.emax = (float*)take(4);
   w.err = (int*)take(4);
   w.bytes = (size_t)(p - (uintptr_t)base);
@@ -132,46 +134,23 @@ __global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long l
 
 // ---------------------------------------------------------------------------------------------------------------
 // GEMM epilogue: score_k = c_k + alpha * acc_k (minimised).  Per code tile: pass 1 lowers the row's running minimum,
-// pass 2 appends every code within `margin` of it (a superset of the codes within `margin` of the final minimum, since
-// the running minimum only decreases).  After the last tile the list is filtered against the final minimum.
+// pass 2 appends every code within `margin` of it straight to the row's candidate list in global memory (a predicated
+// store + counter bump: the lanes of a warp are different rows, so anything heavier would serialise).  The list is a
+// superset of the codes within `margin` of the FINAL minimum because the running minimum only decreases; vq_finalize
+// filters it against the final minimum.
 struct EpiArgExtremum {
   const float* c;
   const float* margin;
-  uint32_t* cand_cnt;
-  uint32_t* cand;
-  long long* idx_out;
+  uint32_t* cand_cnt;      // [rows]
+  uint2* cand;             // [rows][CMAX] (code, score bits), ascending code order
+  float* runmin_out;       // [rows]
   long long rows;
   float alpha;
 
   struct State {
     float runmin = INFINITY;
-    float evicted_min = INFINITY;        // smallest score ever dropped because the list was full
     uint32_t cnt = 0;
-    uint32_t idx[CMAX];
-    float val[CMAX];
   };
-
-  // Append (code, v).  When the list is full, first drop entries the lowered minimum has left behind; if it is still
-  // full, evict the largest score and remember it: the row only needs the exact fallback if the FINAL threshold
-  // reaches an evicted score.
-  __device__ __noinline__ void push(State& st, uint32_t code, float v, float thr) const {
-    if (st.cnt == CMAX) {
-      uint32_t n = 0;
-      for (uint32_t i = 0; i < CMAX; ++i)
-        if (st.val[i] <= thr) { st.idx[n] = st.idx[i]; st.val[n] = st.val[i]; ++n; }
-      st.cnt = n;
-    }
-    if (st.cnt == CMAX) {
-      uint32_t worst = 0;
-      for (uint32_t i = 1; i < CMAX; ++i)
-        if (st.val[i] > st.val[worst]) worst = i;
-      if (v >= st.val[worst]) { st.evicted_min = fminf(st.evicted_min, v); return; }
-      st.evicted_min = fminf(st.evicted_min, st.val[worst]);
-      for (uint32_t i = worst; i + 1 < CMAX; ++i) { st.idx[i] = st.idx[i + 1]; st.val[i] = st.val[i + 1]; }   // keep code order
-      st.cnt = CMAX - 1;
-    }
-    st.idx[st.cnt] = code; st.val[st.cnt] = v; ++st.cnt;
-  }
 
   __device__ __forceinline__ float min32(const uint32_t (&r)[32], const float* __restrict__ cc, float mn) const {
 #pragma unroll
@@ -183,28 +162,31 @@ struct EpiArgExtremum {
     return mn;
   }
   __device__ __forceinline__ void scan32(State& st, const uint32_t (&r)[32], const float* __restrict__ cc, uint32_t code0,
-                                         float thr) const {
+                                         float thr, uint2* __restrict__ list) const {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 ck = __ldg(reinterpret_cast<const float4*>(cc + j));
-      const float v0 = fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), v1 = fmaf(alpha, __uint_as_float(r[j + 1]), ck.y);
-      const float v2 = fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), v3 = fmaf(alpha, __uint_as_float(r[j + 3]), ck.w);
-      if (fminf(fminf(v0, v1), fminf(v2, v3)) <= thr) {
-        if (v0 <= thr) push(st, code0 + j + 0, v0, thr);
-        if (v1 <= thr) push(st, code0 + j + 1, v1, thr);
-        if (v2 <= thr) push(st, code0 + j + 2, v2, thr);
-        if (v3 <= thr) push(st, code0 + j + 3, v3, thr);
+      const float v[4] = {fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), fmaf(alpha, __uint_as_float(r[j + 1]), ck.y),
+                          fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), fmaf(alpha, __uint_as_float(r[j + 3]), ck.w)};
+      if (fminf(fminf(v[0], v[1]), fminf(v[2], v[3])) <= thr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (v[u] <= thr) {
+            if (st.cnt < CMAX) list[st.cnt] = make_uint2(code0 + j + u, __float_as_uint(v[u]));
+            ++st.cnt;
+          }
+        }
       }
     }
   }
 
-  // Two passes over the tile's 256 accumulator columns, TMEM loads software-pipelined one 32-column chunk ahead:
-  // pass 1 lowers the row's running minimum, pass 2 appends every code within `margin` of it (a superset of the codes
-  // within `margin` of the FINAL minimum, since the running minimum only decreases).
+  // TMEM loads are software-pipelined one 32-column chunk ahead of the arithmetic.
   __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int) const {
     const long long gr = m_tile * gemm::BLOCK_M + row;
+    const bool live = gr < rows;
     const float* cc = c + (size_t)n_tile * VQ_BLOCK_N;
-    const float mg = gr < rows ? __ldg(margin + gr) : 0.f;
+    const float mg = live ? __ldg(margin + gr) : 0.f;
+    uint2* list = cand + (size_t)(live ? gr : 0) * CMAX;
     uint32_t ra[32], rb[32];
     float mn = st.runmin;
     sm100::tmem_ld_32x32(tmem_acc, ra);
@@ -218,31 +200,19 @@ struct EpiArgExtremum {
       mn = min32(rb, cc + c0 + 32, mn);
     }
     st.runmin = mn;
-    const float thr = mn + mg;
+    const float thr = live ? mn + mg : -INFINITY;      // padding rows never append
 #pragma unroll 1
     for (int c0 = 0; c0 < VQ_BLOCK_N; c0 += 64) {
       sm100::tmem_ld_wait();
       sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);
-      scan32(st, ra, cc + c0, (uint32_t)(n_tile * VQ_BLOCK_N + c0), thr);
+      scan32(st, ra, cc + c0, (uint32_t)(n_tile * VQ_BLOCK_N + c0), thr, list);
       sm100::tmem_ld_wait();
       if (c0 + 64 < VQ_BLOCK_N) sm100::tmem_ld_32x32(tmem_acc + c0 + 64, ra);
-      scan32(st, rb, cc + c0 + 32, (uint32_t)(n_tile * VQ_BLOCK_N + c0 + 32), thr);
+      scan32(st, rb, cc + c0 + 32, (uint32_t)(n_tile * VQ_BLOCK_N + c0 + 32), thr, list);
     }
-    if (n_tile == n_tiles - 1 && gr < rows) {
-      if (st.evicted_min <= thr) { cand_cnt[gr] = OVERFLOW; return; }
-      uint32_t n = 0, only = 0;
-      for (uint32_t i = 0; i < st.cnt; ++i)
-        if (st.val[i] <= thr) { only = st.idx[i]; ++n; }
-      if (n <= 1) {                       // decided (n == 0 only for NaN rows: index 0)
-        idx_out[gr] = only;
-        cand_cnt[gr] = 0;
-      } else {
-        uint32_t* out = cand + (size_t)gr * CMAX;
-        uint32_t m = 0;
-        for (uint32_t i = 0; i < st.cnt; ++i)
-          if (st.val[i] <= thr) out[m++] = st.idx[i];
-        cand_cnt[gr] = m;
-      }
+    if (n_tile == n_tiles - 1 && live) {
+      cand_cnt[gr] = st.cnt > CMAX ? OVERFLOW : st.cnt;
+      runmin_out[gr] = mn;
     }
   }
 };
@@ -251,9 +221,21 @@ struct EpiArgExtremum {
 // finalize: a block owns FIN_ROWS consecutive rows of one image (consecutive hw).
 //   mode 0 (Codebook.forward):  d_k = (|z|^2 + |e_k|^2) - 2 * dot_k, minimise, lowest index on ties
 //   mode 1 (inference_lr):      l_k = dot_k + bias_k, maximise, lowest index on ties
+// Steps: (0) filter each row's candidate list against its final minimum; rows with one survivor are decided, the others
+// contribute (row, code) pairs to a block-wide work list; (A) stage the fp32 z tile transposed in shared memory (coalesced
+// reads along hw); (B) warps take pairs round-robin -- one coalesced fp32 dot product each -- so the load is balanced
+// whatever the mix of rows; (C) gather e[idx] (coalesced along d) into the transposed tile; (D) NCHW store along hw.
 __device__ __forceinline__ float warp_dot(const float* __restrict__ zt, int r, const float* __restrict__ wk, int d, int lane) {
   float acc = 0.f;
-  for (int i = lane; i < d; i += 32) acc = fmaf(zt[i * (FIN_ROWS + 1) + r], __ldg(wk + i), acc);
+  int i = lane;
+  for (; i + 96 < d; i += 128) {
+    const float w0 = __ldg(wk + i), w1 = __ldg(wk + i + 32), w2 = __ldg(wk + i + 64), w3 = __ldg(wk + i + 96);
+    acc = fmaf(zt[i * (FIN_ROWS + 1) + r], w0, acc);
+    acc = fmaf(zt[(i + 32) * (FIN_ROWS + 1) + r], w1, acc);
+    acc = fmaf(zt[(i + 64) * (FIN_ROWS + 1) + r], w2, acc);
+    acc = fmaf(zt[(i + 96) * (FIN_ROWS + 1) + r], w3, acc);
+  }
+  for (; i < d; i += 32) acc = fmaf(zt[i * (FIN_ROWS + 1) + r], __ldg(wk + i), acc);
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   return acc;
@@ -263,37 +245,68 @@ __device__ __forceinline__ float score_of(float dot, int mode, float zz, float c
   return -__fadd_rn(dot, -ck);          // ck = -bias_k ; negated logit so that "smaller is better"
 }
 
+constexpr int FIN_MAXPAIRS = FIN_ROWS * CMAX;
+
 __global__ void __launch_bounds__(FIN_THREADS)
 vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ table, long long hw,
             int blocks_per_image, int d, int k, int dq, int mode, const float* __restrict__ c, const float* __restrict__ zz,
-            const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand, float* __restrict__ zq,
-            long long* __restrict__ idx_out, float* __restrict__ sq_err) {
+            const float* __restrict__ margin, const float* __restrict__ runmin, const uint32_t* __restrict__ cand_cnt,
+            const uint2* __restrict__ cand, float* __restrict__ zq, long long* __restrict__ idx_out, float* __restrict__ sq_err) {
   extern __shared__ float zt[];                  // [max(d, dq)][FIN_ROWS + 1]
   __shared__ int s_idx[FIN_ROWS];
-  __shared__ uint32_t s_cnt[FIN_ROWS];
-  __shared__ int s_any;
+  __shared__ int s_first[FIN_ROWS + 1];          // first pair of each row (prefix sum)
+  __shared__ uint32_t s_pair[FIN_MAXPAIRS];      // (row << 16) | code
+  __shared__ float s_score[FIN_MAXPAIRS];
+  __shared__ int s_over[FIN_ROWS];
+  __shared__ int s_nover, s_npairs;
+  __shared__ float s_wbest[FIN_THREADS / 32];
+  __shared__ int s_wbestk[FIN_THREADS / 32];
+  constexpr int NW = FIN_THREADS / 32;
+  constexpr int LD = FIN_ROWS + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long bi = blockIdx.x / blocks_per_image;
   const long long p0 = (long long)(blockIdx.x % blocks_per_image) * FIN_ROWS;
   const int nrows = (int)min((long long)FIN_ROWS, hw - p0);
   const long long row0 = bi * hw + p0;
-  constexpr int LD = FIN_ROWS + 1;
 
-  if (threadIdx.x == 0) s_any = 0;
-  __syncthreads();
-  if (threadIdx.x < FIN_ROWS) {
-    const uint32_t n = threadIdx.x < nrows ? cand_cnt[row0 + threadIdx.x] : 0;
-    s_cnt[threadIdx.x] = n;
-    if (threadIdx.x < nrows && n == 0) s_idx[threadIdx.x] = (int)idx_out[row0 + threadIdx.x];
-    if (n != 0) s_any = 1;
+  // ---- step 0 (warp 0): filter candidate lists, build the pair list
+  if (warp == 0) {
+    int nsurv = 0, over = 0;
+    uint32_t mine[CMAX];
+    if (lane < nrows) {
+      const long long gr = row0 + lane;
+      const uint32_t n = cand_cnt[gr];
+      if (n == OVERFLOW) {
+        over = 1;
+      } else {
+        const float thr = runmin[gr] + margin[gr];
+        const uint2* cl = cand + (size_t)gr * CMAX;
+        for (uint32_t i = 0; i < n; ++i) {
+          const uint2 e = cl[i];
+          if (__uint_as_float(e.y) <= thr) mine[nsurv++] = e.x;
+        }
+        if (nsurv <= 1) s_idx[lane] = nsurv ? (int)mine[0] : 0;        // decided (0 survivors only for NaN rows)
+      }
+    }
+    const int np = nsurv >= 2 ? nsurv : 0;
+    int incl = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int first = incl - np;
+    s_first[lane] = first;
+    if (lane == 31) { s_first[32] = incl; s_npairs = incl; }
+    for (int i = 0; i < np; ++i) s_pair[first + i] = ((uint32_t)lane << 16) | mine[i];
+    const unsigned om = __ballot_sync(0xffffffffu, over);
+    if (over) s_over[__popc(om & ((1u << lane) - 1))] = lane;
+    if (lane == 0) s_nover = __popc(om);
   }
   __syncthreads();
-  const bool need_z = s_any != 0 || sq_err != nullptr;
+  const int npairs = s_npairs, nover = s_nover;
+  const bool need_z = npairs > 0 || nover > 0 || sq_err != nullptr;
 
-  // phase A: stage the fp32 z tile transposed ([d][row]) -- coalesced global reads, conflict-free smem writes
   if (need_z) {
+    // ---- step A: fp32 z tile, transposed ([d][row])
     const float* zb = z + bi * d * hw + p0 + (lane < nrows ? lane : 0);
-    constexpr int NW = FIN_THREADS / 32;
     int i = warp;
     for (; i + 7 * NW < d; i += 8 * NW) {            // 8 independent 128-byte loads in flight per warp
       float v[8];
@@ -304,33 +317,50 @@ vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const floa
     }
     for (; i < d; i += NW) zt[i * LD + lane] = __ldg(zb + (long long)i * hw);
     __syncthreads();
-    // phase B: warp-per-row fp32 re-score of the ambiguous rows
-    for (int r = warp; r < nrows; r += FIN_THREADS / 32) {
-      const uint32_t n = s_cnt[r];
-      if (n == 0) continue;
+    // ---- step B: one warp per (row, code) pair
+    for (int p = warp; p < npairs; p += NW) {
+      const uint32_t pr = s_pair[p];
+      const int r = (int)(pr >> 16), kk = (int)(pr & 0xFFFFu);
+      const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zz[row0 + r], c[kk]);
+      if (lane == 0) s_score[p] = sc;
+    }
+    // rows whose list overflowed (many duplicated / near-tied codes): every warp scans a slice of ALL codes
+    for (int o = 0; o < nover; ++o) {
+      const int r = s_over[o];
       const float zzr = zz[row0 + r];
       float bs = INFINITY;
-      int best = 0;
-      if (n == OVERFLOW) {               // more near-ties than the list holds (e.g. many duplicated codes): scan every code
-        for (int kk = 0; kk < k; ++kk) {
-          const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zzr, c[kk]);
-          if (sc < bs) { bs = sc; best = kk; }
-        }
-      } else {
-        for (uint32_t i = 0; i < n; ++i) {           // ascending code order; strict '<' keeps the lowest index on ties
-          const int kk = (int)cand[(size_t)(row0 + r) * CMAX + i];
-          const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zzr, c[kk]);
-          if (sc < bs) { bs = sc; best = kk; }
-        }
+      int bk = 0x7fffffff;
+      for (int kk = warp; kk < k; kk += NW) {
+        const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zzr, c[kk]);
+        if (sc < bs) { bs = sc; bk = kk; }
       }
-      if (lane == 0) { s_idx[r] = best; idx_out[row0 + r] = best; }
+      if (lane == 0) { s_wbest[warp] = bs; s_wbestk[warp] = bk; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float b = INFINITY; int bkk = 0x7fffffff;
+        for (int wv = 0; wv < NW; ++wv)
+          if (s_wbest[wv] < b || (s_wbest[wv] == b && s_wbestk[wv] < bkk)) { b = s_wbest[wv]; bkk = s_wbestk[wv]; }
+        s_idx[r] = bkk == 0x7fffffff ? 0 : bkk;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x < nrows) {
+      const int f = s_first[threadIdx.x], l = s_first[threadIdx.x + 1];
+      if (l > f) {
+        float bs = INFINITY; int best = 0;
+        for (int p = f; p < l; ++p)                                  // ascending code order; strict '<' keeps the lowest index
+          if (s_score[p] < bs) { bs = s_score[p]; best = (int)(s_pair[p] & 0xFFFFu); }
+        s_idx[threadIdx.x] = best;
+      }
     }
     __syncthreads();
   }
+  if (threadIdx.x < nrows) idx_out[row0 + threadIdx.x] = s_idx[threadIdx.x];
 
-  // phase C: gather e[idx] (coalesced along d) into the transposed tile, optionally accumulating (e - z)^2
+  // ---- step C: gather e[idx] (coalesced along d) into the transposed tile, optionally accumulating (e - z)^2
   float err = 0.f;
-  for (int r = warp; r < nrows; r += FIN_THREADS / 32) {
+  for (int r = warp; r < nrows; r += NW) {
     const float* src = table + (size_t)s_idx[r] * dq;
     int i = lane;
     for (; i + 96 < dq; i += 128) {
@@ -350,10 +380,10 @@ vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const floa
     }
   }
   __syncthreads();
-  // phase D: NCHW store, lane <-> consecutive hw
+  // ---- step D: NCHW store, lane <-> consecutive hw
   float* qb = zq + bi * dq * hw + p0;
   if (lane < nrows)
-    for (int i = warp; i < dq; i += FIN_THREADS / 32) __stcs(qb + (long long)i * hw + lane, zt[i * LD + lane]);
+    for (int i = warp; i < dq; i += NW) __stcs(qb + (long long)i * hw + lane, zt[i * LD + lane]);
   if (sq_err) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
@@ -391,6 +421,7 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
   using namespace gpemsr;
   if (b < 0 || d <= 0 || hw < 0 || k <= 0 || dq <= 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: bad shape b=%d d=%d hw=%lld k=%d dq=%d", b, d, hw, k, dq);
+  if (k > 65535) return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: more than 65535 codes");
   if (std::max(d, dq) > 1536)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: latent_dim %d > 1536 does not fit the finalize tile", std::max(d, dq));
   int rc = check_device_current();
@@ -419,7 +450,7 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
     op.a_hi = W.a; op.a_lo = nullptr; op.b_hi = W.b; op.b_lo = nullptr;
     op.a_rows = rows_pad; op.b_rows = k_pad; op.k = d_pad; op.taps = 1; op.a_row_off[0] = 0;
     op.m_tiles = rows_pad / gemm::BLOCK_M; op.n_tiles = n_tiles; op.a_row0 = 0; op.err_flag = W.err;
-    EpiArgExtremum epi{W.c, W.margin, W.cand_cnt, W.cand, idx, rows, alpha};
+    EpiArgExtremum epi{W.c, W.margin, W.cand_cnt, W.cand, W.runmin, rows, alpha};
     using Cfg = gemm::Config<VQ_BLOCK_N, 64, 1, 4>;
     auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum>;
     GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -433,7 +464,7 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
     const size_t smem = (size_t)std::max(d, dq) * (FIN_ROWS + 1) * sizeof(float);
     GPEMSR_CUDA_OK(cudaFuncSetAttribute(vq_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vq_finalize<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, smem, s>>>(
-        z, w, table, hw, blocks_per_image, d, k, dq, mode, W.c, W.zz, W.cand_cnt, W.cand, zq, idx,
+        z, w, table, hw, blocks_per_image, d, k, dq, mode, W.c, W.zz, W.margin, W.runmin, W.cand_cnt, W.cand, zq, idx,
         (mode == 0) ? sq_err_sum : nullptr);
     GPEMSR_LAUNCH_OK("vq_finalize");
   }
