@@ -189,6 +189,47 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   return GPEMSR_OK;
 }
 
+template <int BLOCK_N, int SPLIT>
+int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
+  using Epi = EpiConv<BLOCK_N>;
+  Epi e;
+  e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
+  e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
+  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.c_off = d.c_off;
+  e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
+  e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
+  auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
+  GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
+  kern<<<(unsigned)gx, gemm::NUM_THREADS, smem_bytes, s>>>(op, e);
+  GPEMSR_LAUNCH_OK("gemm_tapfuse_kernel<EpiConv>");
+  return GPEMSR_OK;
+}
+
+// Tap-fused plan: segments = distinct tap dy, each covering the dx range of all taps.  Returns the dynamic smem size, or 0
+// when the resident B plus >= 3 A stages do not fit.
+size_t plan_tapfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n, int wp) {
+  const int planes = d.split == 3 ? 2 : 1;
+  int dx_min = 1 << 20, dx_max = -(1 << 20), dys[3], n_seg = 0;
+  for (int t = 0; t < d.taps; ++t) {
+    dx_min = std::min(dx_min, d.tap_dx[t]); dx_max = std::max(dx_max, d.tap_dx[t]);
+    int sidx = -1;
+    for (int i = 0; i < n_seg; ++i) if (dys[i] == d.tap_dy[t]) sidx = i;
+    if (sidx < 0) { if (n_seg == 3) return 0; sidx = n_seg; dys[n_seg++] = d.tap_dy[t]; }
+    op.tap_seg[t] = sidx;
+  }
+  op.n_seg = n_seg;
+  op.seg_len = gemm::BLOCK_M + dx_max - dx_min;
+  for (int i = 0; i < n_seg; ++i) op.seg_row_off[i] = dys[i] * wp + dx_min;
+  for (int t = 0; t < d.taps; ++t) op.tap_dx[t] = d.tap_dx[t] - dx_min;
+  const size_t b_bytes = ((size_t)planes * d.taps * (d.k_pad / 8) * block_n * 16 + 1023) & ~(size_t)1023;
+  const size_t stage_bytes = (size_t)planes * n_seg * 2 * op.seg_len * 16;
+  const size_t budget = 227 * 1024 - 1024;
+  if (b_bytes + 3 * stage_bytes > budget) return 0;
+  op.nstage = (int)std::min<size_t>(8, (budget - b_bytes) / stage_bytes);
+  return b_bytes + (size_t)op.nstage * stage_bytes + 1024;
+}
+
 // ------------------------------------------------------------------------------------------------ pack / unpack
 __global__ void act_pack_nchw_kernel(const float* __restrict__ x, int c, Geom g, int c_off, float* __restrict__ f32,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -464,6 +505,13 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (d.b_rows < op.n_tiles * block_n) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: b_rows=%d < %d", d.b_rows, op.n_tiles * block_n);
   op.a_row0 = d.a_geom.m0; op.err_flag = d.err_flag;
   cudaStream_t s = (cudaStream_t)stream;
+  if (block_n <= 64 && op.n_tiles == 1) {          // narrow outputs: B resident in smem, taps share one A fetch
+    const size_t smem = plan_tapfuse(op, d, block_n, wp);
+    if (smem) {
+      if (d.split == 3) return block_n == 16 ? launch_fused<16, 3>(op, d, smem, s) : launch_fused<64, 3>(op, d, smem, s);
+      return block_n == 16 ? launch_fused<16, 1>(op, d, smem, s) : launch_fused<64, 1>(op, d, smem, s);
+    }
+  }
   if (d.split == 3) {
     switch (block_n) {
       case 16: return launch<16, 32, 3, 6>(op, d, s);

@@ -42,6 +42,13 @@ struct Operands {
   int n_tiles;                 // number of BLOCK_N column tiles
   long long a_row0;            // row of A that tile 0 / row 0 maps to (so shifts may be negative)
   int* err_flag;               // device int, set non-zero on a pipeline time-out
+  // ---- tap-fused mode (gemm_tapfuse_kernel): B resident in smem, A fetched once per k-slab as <= 3 row segments
+  int n_seg;                   // distinct tap dy values
+  int seg_row_off[3];          // first A row of segment s relative to the tile's first row (dy * wp + dx_min)
+  int seg_len;                 // rows per segment = 128 + (dx_max - dx_min)
+  int tap_seg[MAX_TAPS];       // segment of tap t
+  int tap_dx[MAX_TAPS];        // row offset of tap t inside its segment (dx - dx_min)
+  int nstage;                  // smem stages that fit next to the resident B
 };
 
 template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE>
@@ -65,6 +72,7 @@ struct Barriers {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t b_full;             // tap-fused mode: resident B has landed
   uint32_t tmem_base;
 };
 
@@ -200,6 +208,147 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
   if (warp == 1) {
     sm100::tc_fence_after();
     sm100::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tap-fused variant for narrow outputs (one column tile, B small enough to live in shared memory).
+//   * B (all taps, all k) is loaded ONCE per CTA and stays resident;
+//   * per 16-wide k-slab the producer fetches the A rows of the tile's neighbourhood once, as one segment per distinct
+//     tap dy (rows [r0 + dy*wp + dx_min, +128 + dx_max - dx_min)); every tap then reads its operand from the same
+//     stage at a 16-byte row offset (the canonical layout has uniform 16-byte rows, so a shift is a start address).
+// A 3x3 convolution thus reads each activation row 3x instead of 9x and never re-reads weights: the wide-image 64-channel
+// layers go from L2-operand-bound to MMA/epilogue-bound.
+template <int BLOCK_N, int SPLIT, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
+  constexpr int PLANES = SPLIT == 3 ? 2 : 1;
+  constexpr int KCH = 2;                                   // one UMMA k-step (16 bf16) per stage
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int kcells = op.k / 8;
+  const uint32_t b_tap_bytes = (uint32_t)kcells * BLOCK_N * 16;               // one tap, one plane
+  const uint32_t b_bytes = (uint32_t)PLANES * op.taps * b_tap_bytes;
+  const uint32_t seg_bytes = (uint32_t)op.seg_len * 16;                       // one 16-byte k-cell column of a segment
+  const uint32_t a_plane_bytes = (uint32_t)op.n_seg * KCH * seg_bytes;
+  const uint32_t stage_bytes = PLANES * a_plane_bytes;
+  uint8_t* b_res = smem;
+  uint8_t* stages = smem + ((b_bytes + 1023) & ~1023u);
+  Barriers* bars = reinterpret_cast<Barriers*>(stages + (size_t)op.nstage * stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kiters = op.k / 16;
+  const int nstage = op.nstage;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], 4); }
+    sm100::mbar_init(&bars->b_full, 1);
+    sm100::fence_mbar_init();
+  }
+  constexpr int TMEM_COLS = Config<BLOCK_N, 16, SPLIT, 2>::TMEM_COLS;
+  if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    bool ok = true;
+    if (blockIdx.x < op.m_tiles) {
+      if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->b_full, b_bytes);
+      __syncwarp();
+      const int ncopies = PLANES * op.taps * kcells;
+      for (int c = lane; c < ncopies; c += 32) {
+        const int plane = c / (op.taps * kcells), r = c % (op.taps * kcells);      // r = tap * kcells + kc
+        const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + (long long)r * op.b_rows * 8;
+        sm100::bulk_g2s(b_res + (size_t)c * BLOCK_N * 16, src, BLOCK_N * 16, &bars->b_full);
+      }
+    }
+    uint32_t stage = 0, phase = 0;
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      const long long a_row = op.a_row0 + m_tile * BLOCK_M;
+      for (int it = 0; it < kiters && ok; ++it) {
+        ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+        if (!ok) break;
+        uint8_t* sa = stages + (size_t)stage * stage_bytes;
+        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
+        __syncwarp();
+        const int ncopies = PLANES * op.n_seg * KCH;
+        for (int c = lane; c < ncopies; c += 32) {
+          const int plane = c / (op.n_seg * KCH), r = c % (op.n_seg * KCH), seg = r / KCH, kc = r % KCH;
+          const __nv_bfloat16* src = (plane ? op.a_lo : op.a_hi) +
+                                     ((long long)(it * KCH + kc) * op.a_rows + a_row + op.seg_row_off[seg]) * 8;
+          sm100::bulk_g2s(sa + (size_t)c * seg_bytes, src, seg_bytes, &bars->full[stage]);
+        }
+        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    if (blockIdx.x < op.m_tiles) ok = sm100::mbar_wait(&bars->b_full, 0, op.err_flag, 5);
+    const uint32_t sb0 = sm100::smem_u32(b_res);
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+      if (!ok) break;
+      sm100::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+      for (int it = 0; it < kiters && ok; ++it) {
+        ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        if (sm100::elect_one()) {
+          const uint32_t sa = sm100::smem_u32(stages + (size_t)stage * stage_bytes);
+          for (int t = 0; t < op.taps; ++t) {
+            const uint32_t a_addr = sa + (uint32_t)(op.tap_seg[t] * KCH) * seg_bytes + (uint32_t)op.tap_dx[t] * 16;
+            const uint32_t b_addr = sb0 + (uint32_t)t * b_tap_bytes + (uint32_t)(it * KCH) * (BLOCK_N * 16);
+            const uint64_t a_hi = sm100::smem_desc_kmajor_noswz(a_addr, seg_bytes, 128);
+            const uint64_t b_hi = sm100::smem_desc_kmajor_noswz(b_addr, BLOCK_N * 16, 128);
+            sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | t) != 0);
+            if constexpr (SPLIT == 3) {
+              const uint64_t a_lo = sm100::smem_desc_kmajor_noswz(a_addr + a_plane_bytes, seg_bytes, 128);
+              const uint64_t b_lo = sm100::smem_desc_kmajor_noswz(b_addr + (uint32_t)op.taps * b_tap_bytes, BLOCK_N * 16, 128);
+              sm100::umma_bf16(tmem_acc, a_lo, b_hi, idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
+            }
+          }
+          sm100::umma_commit(&bars->empty[stage]);
+          if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+      }
+      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      typename Epi::State st{};
+      ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+      if (!ok) break;
+      sm100::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epi.tile(st, tmem_acc, m_tile, 0, 1, row, q);
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+    }
+  }
+
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
