@@ -74,6 +74,7 @@ struct EpiConv {
   float* out_rowmajor;
   long long ld;
 
+  static constexpr int WARPS = BLOCK_N >= 64 ? 8 : 4;
   struct State {
     bool init = false, valid = false;
     int img = 0, y = 0, x = 0;
@@ -148,7 +149,7 @@ struct EpiConv {
     }
   }
 
-  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int, int row, int) const {
+  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int, int row, int part) const {
     const long long rel = m_tile * gemm::BLOCK_M + row;
     if (!st.init) {
       st.init = true;
@@ -156,8 +157,9 @@ struct EpiConv {
       if (bias_per_row && st.valid) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
     }
     constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
+    constexpr int SPAN = BLOCK_N / (WARPS / 4);          // columns this warp covers
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+    for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
       uint32_t r[CHUNK];
       if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + c0, r);
       else sm100::tmem_ld_32x16(tmem_acc + c0, r);
@@ -184,7 +186,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   const long long gx = std::min<long long>(op.m_tiles, sms);
   long long gy = 1;
   if (op.m_tiles < sms) gy = std::min<long long>(op.n_tiles, (sms + op.m_tiles - 1) / op.m_tiles);
-  kern<<<dim3((unsigned)gx, (unsigned)gy), gemm::NUM_THREADS, Cfg::SMEM_BYTES, s>>>(op, e);
+  kern<<<dim3((unsigned)gx, (unsigned)gy), gemm::num_threads<Epi>(), Cfg::SMEM_BYTES, s>>>(op, e);
   GPEMSR_LAUNCH_OK("gemm_kernel<EpiConv>");
   return GPEMSR_OK;
 }
@@ -201,7 +203,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
-  kern<<<(unsigned)gx, gemm::NUM_THREADS, smem_bytes, s>>>(op, e);
+  kern<<<(unsigned)gx, gemm::num_threads<Epi>(), smem_bytes, s>>>(op, e);
   GPEMSR_LAUNCH_OK("gemm_tapfuse_kernel<EpiConv>");
   return GPEMSR_OK;
 }

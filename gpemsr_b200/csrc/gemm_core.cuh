@@ -25,7 +25,8 @@
 namespace gemm {
 
 constexpr int BLOCK_M = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;          // 2 role warps + 4 epilogue warps (Epi::WARPS == 4)
+template <class Epi> constexpr int num_threads() { return 64 + 32 * Epi::WARPS; }
 constexpr int MAX_TAPS = 49;
 
 struct Operands {
@@ -79,14 +80,16 @@ struct Barriers {
 // Epilogue concept:
 //   struct Epi {
 //     struct State { ... };     // per-thread (= per-row) state, default-constructed at the start of every 128-row tile
+//     static constexpr int WARPS = 4 or 8;   // epilogue warps: with 8, two warps share a TMEM lane quarter and each takes
+//                                            // half of the tile's columns (`part` 0 / 1) -- twice the epilogue issue rate
 //     __device__ void tile(State&, uint32_t tmem_acc /*lane-adjusted*/, long long m_tile, int n_tile, int n_tiles,
-//                          int row_in_tile /*0..127 = this thread's row*/, int warp_q) const;
+//                          int row_in_tile /*0..127 = this thread's row*/, int part) const;
 //   };
 // The epilogue reads its accumulator with sm100::tmem_ld_32x32(tmem_acc + col, regs) and must finish with the
 // loads retired (tmem_ld_wait) before returning.
 
 template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
 gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
   using Cfg = Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,7 +102,7 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
     sm100::fence_mbar_init();
   }
   if (warp == 1) sm100::tmem_alloc<Cfg::TMEM_COLS>(&bars->tmem_base);
@@ -194,7 +197,7 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
         if (!ok) break;
         sm100::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
-        epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, q);
+        epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, (warp - 2) >> 2);
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
@@ -221,7 +224,7 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
 // A 3x3 convolution thus reads each activation row 3x instead of 9x and never re-reads weights: the wide-image 64-channel
 // layers go from L2-operand-bound to MMA/epilogue-bound.
 template <int BLOCK_N, int SPLIT, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
 gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
   constexpr int PLANES = SPLIT == 3 ? 2 : 1;
   constexpr int KCH = 2;                                   // one UMMA k-step (16 bf16) per stage
@@ -242,7 +245,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstage; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
     sm100::mbar_init(&bars->b_full, 1);
     sm100::fence_mbar_init();
   }
@@ -336,7 +339,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
       if (!ok) break;
       sm100::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epi.tile(st, tmem_acc, m_tile, 0, 1, row, q);
+      epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);
       sm100::tc_fence_before();
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);

@@ -31,6 +31,7 @@ struct EpiRowMajor {
 };
 template <int BLOCK_N>
 struct EpiRowMajorN : EpiRowMajor {
+  static constexpr int WARPS = 4;
   struct State {};
   __device__ __forceinline__ void tile(State&, uint32_t tmem_acc, long long m_tile, int n_tile, int, int row, int) const {
     this->template run<BLOCK_N>(tmem_acc, m_tile, n_tile, row);

@@ -147,6 +147,7 @@ struct EpiArgExtremum {
   long long rows;
   float alpha;
 
+  static constexpr int WARPS = 4;        // the row's running minimum and list are carried by ONE thread
   struct State {
     float runmin = INFINITY;
     uint32_t cnt = 0;

@@ -59,11 +59,50 @@ def vq_bench(sizes=((1 << 20, 512), (1 << 20, 256), (1 << 16, 512))):
     return out
 
 
+def conv_bench(which=None):
+    """Single conv layers of the bench step, fp32-faithful split-3 path: ms and algorithmic TFLOP/s."""
+    from gpemsr_b200 import igemm as G
+    cases = [('rb512_80', 5, 512, 512, 80, 3, {}), ('rb256_160', 5, 256, 256, 160, 3, {}), ('rb128_320', 5, 128, 128, 320, 3, {}),
+             ('rb64_640', 5, 64, 64, 640, 3, {}), ('hr64_1280', 1, 64, 64, 1280, 3, dict(act=G.ACT_LRELU, slope=0.1)),
+             ('up256_640', 1, 64, 256, 640, 3, dict(ps=True)), ('out1_1280', 5, 64, 1, 1280, 3, dict(nchw=True)),
+             ('q512_80', 5, 512, 512, 80, 1, {})]
+    out = []
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    for name, n, ci, co, s, ks, opt in cases:
+        if which and name not in which:
+            continue
+        g = G.Geom(n, s, s, True)
+        x = G.Act(g, ci, 'cuda', f32=False)
+        x.hi.normal_(); x.lo.normal_(std=0.004)
+        w = torch.randn(co, ci, ks, ks, device='cuda') * 0.05
+        b = torch.randn(co, device='cuda')
+        wt = G.Weights(w, 'conv')
+        kw = dict(split=3, bias=b, act=opt.get('act', G.ACT_NONE), slope=opt.get('slope', 0.0))
+        if opt.get('ps'):
+            y = G.Act(G.Geom(n, 2 * s, 2 * s, True), co // 4, 'cuda', f32=False)
+            fn = lambda: G.igemm(x, wt, err, out=y, up=2, pixel_shuffle=True, out_f32=False, **kw)
+        elif opt.get('nchw'):
+            img = torch.empty(n, co, s, s, device='cuda')
+            fn = lambda: G.igemm(x, wt, err, out_nchw=img, nchw_c=co, **kw)
+        else:
+            y = G.Act(g, co, 'cuda', f32=True)
+            fn = lambda: G.igemm(x, wt, err, out=y, **kw)
+        med, best = timeit(fn, iters=5, warm=2)
+        fl = 2.0 * n * s * s * co * ci * ks * ks
+        out.append(dict(op='conv', name=name, n=n, cin=ci, cout=co, hw=s, k=ks, ms=med, tflops=fl / med / 1e9,
+                        frac_of_split3_ceiling=fl / med / 1e9 / (1388.4 / 3)))
+        del x, wt
+    assert int(err.item()) == 0
+    return out
+
+
 if __name__ == '__main__':
     torch.cuda.init()
     res = []
     if 'flow' in sys.argv[1:] or len(sys.argv) == 1:
         res += flow_warp_bench()
+    if 'conv' in sys.argv[1:]:
+        res += conv_bench([a for a in sys.argv[2:]] or None)
     if 'vq1' in sys.argv[1:]:
         res += vq_bench(sizes=((1 << 20, 512),))
     if 'vq' in sys.argv[1:] or len(sys.argv) == 1:
