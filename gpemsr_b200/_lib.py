@@ -40,6 +40,9 @@ SIGNATURES = {
     'gpemsr_act_pack_nchw': (_i, [_p, _i, _p, _i, _p, _p, _p, _p]),
     'gpemsr_act_unpack_nchw': (_i, [_p, _i, _p, _i, _p, _p]),
     'gpemsr_pack_weights': (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _p, _p, _p]),
+    'gpemsr_igemm_plan': (_i, [_p, _p, _p]),
+    'gpemsr_pack_weights_tiled_bytes': (_sz, [_i, _i, _i, _i, _i]),
+    'gpemsr_pack_weights_tiled': (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _i, _p, _p]),
     'gpemsr_gn_stats': (_i, [_p, _i, _p, _p, _p]),
     'gpemsr_gn_scale_shift': (_i, [_p, _p, _p, _i, _i, _i, C.c_double, _f, _p, _p]),
     'gpemsr_affine_act': (_i, [_p, _i, _p, _p, _i, _f, _p, _p, _p, _p, _p, _p]),

@@ -298,6 +298,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int n, int k, l
   if (lo) *reinterpret_cast<uint4*>(lo + (size_t)t * 8) = l;
 }
 
+// [n_tile][tap][k-chunk][plane][k-cell][block_n][8]
+__global__ void pack_weights_tiled_kernel(const float* __restrict__ w, int n, int k, long long n_stride, long long k_stride, int taps,
+                                          const int* __restrict__ tap_src, int block_n, int kch, int planes, int kchunks, int n_tiles,
+                                          __nv_bfloat16* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_tiles * taps * kchunks * planes * kch * block_n;
+  if (t >= total) return;
+  long long r = t;
+  const int nn = (int)(r % block_n); r /= block_n;
+  const int kc = (int)(r % kch); r /= kch;
+  const int plane = (int)(r % planes); r /= planes;
+  const int kchunk = (int)(r % kchunks); r /= kchunks;
+  const int tap = (int)(r % taps); r /= taps;
+  const int row = (int)r * block_n + nn;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kk = (kchunk * kch + kc) * 8 + j;
+    v[j] = (row < n && kk < k) ? __ldg(w + row * n_stride + kk * k_stride + tap_src[tap]) : 0.f;
+  }
+  uint4 h, l;
+  split8(v, h, l);
+  *reinterpret_cast<uint4*>(out + (size_t)t * 8) = plane ? l : h;
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // per-channel sum / sum of squares over an image's rows (ring and tail rows are zero by construction)
 __global__ void gn_stats_kernel(const float* __restrict__ x, int c, Geom g, double* __restrict__ sums) {
@@ -458,6 +483,10 @@ __global__ void add_bilinear_base_kernel(const float* __restrict__ xc, int n, in
   out[t] += v;
 }
 
+int pick_block_n(const gpemsr_igemm_desc_t& d) {
+  return d.n_cols <= 16 && !d.pixel_shuffle ? 16 : d.n_cols <= 64 ? 64 : d.n_cols <= 128 ? 128 : 256;
+}
+
 int check_geom(const gpemsr_geom_t& g, const char* what) {
   using namespace gpemsr;
   if (g.n <= 0 || g.h <= 0 || g.w <= 0 || g.r_img <= 0 || (g.r_img % gemm::BLOCK_M) != 0)
@@ -484,18 +513,18 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (d.taps < 1 || d.taps > gemm::MAX_TAPS || d.k_pad <= 0 || d.k_pad % 64 || d.n_cols <= 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: taps=%d k_pad=%d n_cols=%d", d.taps, d.k_pad, d.n_cols);
   if (d.split != 1 && d.split != 3) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: split must be 1 or 3");
-  if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || !d.b_lo))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
+  if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || (!d.b_lo && !d.b_packed)))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
   if (d.up != 1 && d.up != 2) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: up must be 1 or 2");
   if (d.pixel_shuffle && (d.up != 2 || d.n_cols % 32)) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: pixel_shuffle needs up=2 and n_cols %% 32 == 0");
   if (d.c_off % 8) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: c_off must be a multiple of 8");
   if (d.out_rowmajor && (d.ld % 4)) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: ld must be a multiple of 4");
   if (!d.err_flag) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: err_flag is required");
 
-  const int block_n = d.n_cols <= 16 && !d.pixel_shuffle ? 16 : d.n_cols <= 64 ? 64 : d.n_cols <= 128 ? 128 : 256;
+  const int block_n = pick_block_n(d);
   gemm::Operands op{};
   op.a_hi = (const __nv_bfloat16*)d.a_hi; op.a_lo = (const __nv_bfloat16*)d.a_lo;
   op.b_hi = (const __nv_bfloat16*)d.b_hi; op.b_lo = (const __nv_bfloat16*)d.b_lo;
-  op.a_rows = d.a_geom.rows_alloc; op.b_rows = d.b_rows; op.k = d.k_pad; op.taps = d.taps;
+  op.a_rows = d.a_geom.rows_alloc; op.b_rows = d.b_rows; op.b_packed = d.b_packed; op.k = d.k_pad; op.taps = d.taps;
   const int wp = d.a_geom.padded ? d.a_geom.w + 2 : d.a_geom.w;
   for (int t = 0; t < d.taps; ++t) {
     if (!d.a_geom.padded && (d.tap_dy[t] || d.tap_dx[t])) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: shifted taps need a padded geometry");
@@ -504,11 +533,13 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   }
   op.m_tiles = (long long)d.a_geom.n * d.a_geom.r_img / gemm::BLOCK_M;
   op.n_tiles = (d.n_cols + block_n - 1) / block_n;
-  if (d.b_rows < op.n_tiles * block_n) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: b_rows=%d < %d", d.b_rows, op.n_tiles * block_n);
+  if (!d.b_packed && d.b_rows < op.n_tiles * block_n) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: b_rows=%d < %d", d.b_rows, op.n_tiles * block_n);
   op.a_row0 = d.a_geom.m0; op.err_flag = d.err_flag;
   cudaStream_t s = (cudaStream_t)stream;
   if (block_n <= 64 && op.n_tiles == 1) {          // narrow outputs: B resident in smem, taps share one A fetch
     const size_t smem = plan_tapfuse(op, d, block_n, wp);
+    if (smem && d.b_packed) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: this shape runs the tap-fused kernel, which needs "
+                                             "gpemsr_pack_weights() weights (see gpemsr_igemm_plan)");
     if (smem) {
       if (d.split == 3) return block_n == 16 ? launch_fused<16, 3>(op, d, smem, s) : launch_fused<64, 3>(op, d, smem, s);
       return block_n == 16 ? launch_fused<16, 1>(op, d, smem, s) : launch_fused<64, 1>(op, d, smem, s);
@@ -528,6 +559,43 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
     case 128: return launch<128, 64, 1, 5>(op, d, s);
     default: return launch<256, 64, 1, 4>(op, d, s);
   }
+}
+
+int gpemsr_igemm_plan(const gpemsr_igemm_desc_t* dp, int32_t* block_n, int32_t* tapfused) {
+  using namespace gpemsr;
+  if (!dp || !block_n || !tapfused) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm_plan: null argument");
+  if (dp->taps < 1 || dp->taps > gemm::MAX_TAPS || dp->k_pad <= 0 || dp->k_pad % 64 || dp->n_cols <= 0)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm_plan: taps=%d k_pad=%d n_cols=%d", dp->taps, dp->k_pad, dp->n_cols);
+  const int bn = pick_block_n(*dp);
+  *block_n = bn;
+  gemm::Operands op{};
+  const int n_tiles = (dp->n_cols + bn - 1) / bn;
+  *tapfused = (bn <= 64 && n_tiles == 1 && plan_tapfuse(op, *dp, bn, /*wp (irrelevant for the fit)*/ 0) != 0) ? 1 : 0;
+  return GPEMSR_OK;
+}
+
+size_t gpemsr_pack_weights_tiled_bytes(int n, int k_pad, int taps, int block_n, int split) {
+  if (n <= 0 || k_pad <= 0 || taps <= 0 || block_n <= 0) return 0;
+  const int planes = split == 3 ? 2 : 1;
+  const size_t n_tiles = (size_t)(n + block_n - 1) / block_n;
+  return n_tiles * taps * (size_t)k_pad * planes * block_n * 2;
+}
+
+int gpemsr_pack_weights_tiled(const float* w, int n, int k, int64_t n_stride, int64_t k_stride, int taps, const int32_t* tap_src,
+                              int block_n, int k_pad, int split, void* out, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  const int block_k = split == 3 ? 32 : 64;
+  if (!w || !out || !tap_src || n <= 0 || k <= 0 || taps <= 0 || k_pad < k || k_pad % block_k || (split != 1 && split != 3) ||
+      (block_n != 16 && block_n != 64 && block_n != 128 && block_n != 256))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "pack_weights_tiled: bad arguments");
+  const int planes = split == 3 ? 2 : 1, kch = block_k / 8, kchunks = k_pad / block_k, n_tiles = (n + block_n - 1) / block_n;
+  const long long total = (long long)n_tiles * taps * kchunks * planes * kch * block_n;
+  pack_weights_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, n, k, n_stride, k_stride, taps, tap_src, block_n, kch, planes, kchunks, n_tiles, (__nv_bfloat16*)out);
+  GPEMSR_LAUNCH_OK("pack_weights_tiled_kernel");
+  return GPEMSR_OK;
 }
 
 int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* g, int c_off, float* f32, void* hi, void* lo,

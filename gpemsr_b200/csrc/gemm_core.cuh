@@ -36,6 +36,8 @@ struct Operands {
   const __nv_bfloat16* b_lo;
   long long a_rows;            // allocated rows of A (k-chunk stride = a_rows * 16 B)
   int b_rows;                  // allocated rows of B per tap (>= n_tiles * BLOCK_N)
+  int b_packed;                // 1: B is [n_tile][tap][k-chunk][plane][k-cell][BLOCK_N][8] (one contiguous block per stage,
+                               //    b_lo unused); 0: plain K8-blocked [tap][K/8][b_rows][8] per plane
   int k;                       // reduction length per tap, multiple of BLOCK_K
   int taps;                    // number of shifted GEMMs accumulated into one tile
   int a_row_off[MAX_TAPS];     // row shift of A for every tap
@@ -88,7 +90,11 @@ struct Barriers {
 // The epilogue reads its accumulator with sm100::tmem_ld_32x32(tmem_acc + col, regs) and must finish with the
 // loads retired (tmem_ld_wait) before returning.
 
-template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, class Epi>
+// CLUSTER == 2: the two CTAs of a cluster work on neighbouring row tiles in lock-step and SHARE the B operand: each
+// loads half of every B stage and multicasts it into both shared memories, so weight / codebook traffic out of L2
+// (the binding resource of this kernel: ~6.3 KB/clk chip-wide) is halved.  A stage is recycled only when BOTH tensor
+// cores have consumed it (tcgen05.commit multicast onto both CTAs' `empty` barriers, which therefore count 2).
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, class Epi, int CLUSTER = 1>
 __global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
 gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
   using Cfg = Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
@@ -99,48 +105,69 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kiters_per_tap = op.k / BLOCK_K;
   const int kiters = op.taps * kiters_per_tap;
+  const uint32_t crank = CLUSTER > 1 ? sm100::cluster_ctarank() : 0;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CLUSTER) - 1);
+  // every CTA of a cluster runs the same number of row-tile iterations; surplus ones recompute the last tile and
+  // discard it, so the lock-step multicast protocol never has a missing partner
+  const long long n_iter = (op.m_tiles + gridDim.x - 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], CLUSTER); }
     for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
     sm100::fence_mbar_init();
   }
   if (warp == 1) sm100::tmem_alloc<Cfg::TMEM_COLS>(&bars->tmem_base);
   sm100::tc_fence_before();
-  __syncthreads();
+  if constexpr (CLUSTER > 1) sm100::cluster_sync_all(); else __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
     // ===================== producer: bulk copies HBM/L2 -> smem =====================
+    // The producer warp is on the critical path (one warp feeds the whole tensor pipe), so its loop is kept lean:
+    // every lane owns ONE copy slot whose source pointer is advanced incrementally, and packed weights arrive as a
+    // single copy per stage (one half per CTA when the cluster shares B).
     uint32_t stage = 0, phase = 0;
     bool ok = true;
-    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+    constexpr int NA = Cfg::PLANES * Cfg::KCH;                 // A copies per stage (one 16-byte-cell column each)
+    const int nb = op.b_packed ? 1 : NA;                       // B copy slots per stage
+    const bool is_a = lane < NA;
+    // with a cluster, B slot s of an unpacked operand is issued by CTA (s % CLUSTER); a packed stage is split in halves
+    const bool is_b = lane >= NA && lane < NA + nb && (CLUSTER == 1 || op.b_packed || ((lane - NA) % CLUSTER) == (int)crank);
+    const int slot = is_a ? lane : lane - NA;
+    const int plane = slot / Cfg::KCH, kc = slot % Cfg::KCH;
+    constexpr uint32_t kBStage = Cfg::PLANES * Cfg::B_PLANE_BYTES;
+    const uint32_t b_part = op.b_packed ? kBStage / CLUSTER : BLOCK_N * 16;     // bytes this CTA's B copy moves
+    const uint32_t sm_off = is_a ? (uint32_t)(plane * Cfg::A_PLANE_BYTES + kc * (BLOCK_M * 16))
+                                 : (uint32_t)(Cfg::PLANES * Cfg::A_PLANE_BYTES) +
+                                       (op.b_packed ? crank * b_part : (uint32_t)(plane * Cfg::B_PLANE_BYTES + kc * (BLOCK_N * 16)));
+    const uint32_t bytes = is_a ? BLOCK_M * 16 : b_part;
+    const long long a_kstep = (long long)Cfg::KCH * op.a_rows * 8;           // elements per k-chunk advance of A
+    const long long b_kstep = op.b_packed ? (long long)kBStage / 2 : (long long)Cfg::KCH * op.b_rows * 8;
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      const long long m_tile = min(blockIdx.x + i * gridDim.x, op.m_tiles - 1);
+      const __nv_bfloat16* a_tile = (plane ? op.a_lo : op.a_hi) + ((long long)kc * op.a_rows + op.a_row0 + m_tile * BLOCK_M) * 8;
       for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
-        for (int it = 0; it < kiters && ok; ++it) {
-          const int tap = it / kiters_per_tap, kc0 = (it % kiters_per_tap) * Cfg::KCH;
-          ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
-          if (!ok) break;
-          uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
-          if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
-          __syncwarp();
-          const long long a_row = op.a_row0 + m_tile * BLOCK_M + op.a_row_off[tap];
-          // one 16-byte-cell column per copy: A cell column = BLOCK_M*16 B, B cell column = BLOCK_N*16 B
-          for (int c = lane; c < Cfg::PLANES * Cfg::KCH * 2; c += 32) {
-            const int is_b = c / (Cfg::PLANES * Cfg::KCH);
-            const int r = c % (Cfg::PLANES * Cfg::KCH);
-            const int plane = r / Cfg::KCH, kc = r % Cfg::KCH;
-            if (!is_b) {
-              const __nv_bfloat16* src = (plane ? op.a_lo : op.a_hi) + ((long long)(kc0 + kc) * op.a_rows + a_row) * 8;
-              sm100::bulk_g2s(sa + plane * Cfg::A_PLANE_BYTES + kc * (BLOCK_M * 16), src, BLOCK_M * 16, &bars->full[stage]);
-            } else {
-              const long long brow = ((long long)tap * (op.k / 8) + (kc0 + kc)) * op.b_rows + (long long)n_tile * BLOCK_N;
-              const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + brow * 8;
-              sm100::bulk_g2s(sb + plane * Cfg::B_PLANE_BYTES + kc * (BLOCK_N * 16), src, BLOCK_N * 16, &bars->full[stage]);
+        const __nv_bfloat16* b_src;
+        if (op.b_packed) b_src = op.b_hi + (long long)n_tile * op.taps * kiters_per_tap * b_kstep + crank * (b_part / 2);
+        else b_src = (plane ? op.b_lo : op.b_hi) + ((long long)kc * op.b_rows + (long long)n_tile * BLOCK_N) * 8;
+        for (int tap = 0; tap < op.taps && ok; ++tap) {
+          const __nv_bfloat16* a_src = a_tile + (long long)op.a_row_off[tap] * 8;
+          for (int kci = 0; kci < kiters_per_tap; ++kci) {
+            ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+            if (!ok) break;
+            uint8_t* st = stages + stage * Cfg::STAGE_BYTES;
+            if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+            __syncwarp();
+            if (is_a) sm100::bulk_g2s(st + sm_off, a_src, bytes, &bars->full[stage]);
+            else if (is_b) {
+              if constexpr (CLUSTER > 1) sm100::bulk_g2s_multicast(st + sm_off, b_src, bytes, &bars->full[stage], kAllCtas);
+              else sm100::bulk_g2s(st + sm_off, b_src, bytes, &bars->full[stage]);
             }
+            a_src += a_kstep;
+            b_src += b_kstep;
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -149,7 +176,7 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
     uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
     bool ok = true;
-    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+    for (long long i = 0; i < n_iter && ok; ++i) {
       for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
         ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
         if (!ok) break;
@@ -175,7 +202,9 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
                 sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
               }
             }
-            sm100::umma_commit(&bars->empty[stage]);                        // smem stage reusable once these MMAs retire
+            // smem stage reusable once these MMAs retire (in BOTH CTAs when the cluster shares B)
+            if constexpr (CLUSTER > 1) sm100::umma_commit_multicast(&bars->empty[stage], kAllCtas);
+            else sm100::umma_commit(&bars->empty[stage]);
             if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);   // accumulator complete
           }
           __syncwarp();
@@ -190,14 +219,16 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     const int row = q * 32 + lane;
     uint32_t acc_buf = 0, acc_phase = 0;
     bool ok = true;
-    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      const long long m_tile = blockIdx.x + i * gridDim.x;
+      const bool live = m_tile < op.m_tiles;
       typename Epi::State st{};
       for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
         ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
         if (!ok) break;
         sm100::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
-        epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, (warp - 2) >> 2);
+        if (live) epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, (warp - 2) >> 2);
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
@@ -207,13 +238,12 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
   }
 
   sm100::tc_fence_before();
-  __syncthreads();
+  if constexpr (CLUSTER > 1) sm100::cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     sm100::tc_fence_after();
     sm100::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Tap-fused variant for narrow outputs (one column tile, B small enough to live in shared memory).
@@ -270,21 +300,24 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
       }
     }
     uint32_t stage = 0, phase = 0;
+    // one copy slot per lane, source pointer advanced incrementally (the producer warp is on the critical path)
+    const int ncopies = PLANES * op.n_seg * KCH;
+    const bool active = lane < ncopies;
+    const int cplane = lane / (op.n_seg * KCH), cr = lane % (op.n_seg * KCH), cseg = cr / KCH, ckc = cr % KCH;
+    const uint32_t sm_off = (uint32_t)lane * seg_bytes;
+    const long long a_kstep = (long long)KCH * op.a_rows * 8;
+    const __nv_bfloat16* a_base = (cplane ? op.a_lo : op.a_hi) +
+                                  ((long long)ckc * op.a_rows + op.a_row0 + (active ? op.seg_row_off[cseg] : 0)) * 8;
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-      const long long a_row = op.a_row0 + m_tile * BLOCK_M;
+      const __nv_bfloat16* src = a_base + m_tile * (BLOCK_M * 8);
       for (int it = 0; it < kiters && ok; ++it) {
         ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
         if (!ok) break;
         uint8_t* sa = stages + (size_t)stage * stage_bytes;
         if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
         __syncwarp();
-        const int ncopies = PLANES * op.n_seg * KCH;
-        for (int c = lane; c < ncopies; c += 32) {
-          const int plane = c / (op.n_seg * KCH), r = c % (op.n_seg * KCH), seg = r / KCH, kc = r % KCH;
-          const __nv_bfloat16* src = (plane ? op.a_lo : op.a_hi) +
-                                     ((long long)(it * KCH + kc) * op.a_rows + a_row + op.seg_row_off[seg]) * 8;
-          sm100::bulk_g2s(sa + (size_t)c * seg_bytes, src, seg_bytes, &bars->full[stage]);
-        }
+        if (active) sm100::bulk_g2s(sa + sm_off, src, seg_bytes, &bars->full[stage]);
+        src += a_kstep;
         if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
       }
     }

@@ -37,7 +37,7 @@ inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m
 
 struct Workspace {
   __nv_bfloat16* a;       // [d_pad/8][rows_pad][8]
-  __nv_bfloat16* b;       // [d_pad/8][k_pad][8]
+  __nv_bfloat16* b;       // [k_pad/256][d_pad/64][8][256][8] (tiled: one contiguous block per GEMM stage)
   float* c;               // [k_pad]   |e_k|^2 (or -bias_k); +inf for padding codes
   float* zz;              // [rows_pad]
   float* margin;          // [rows_pad]
@@ -88,7 +88,9 @@ __global__ void vq_prep_codes(const float* __restrict__ e, const float* __restri
       ss = fmaf(v1, v1, ss);
       h[j] = sm100::pack_bf16x2(v0, v1);
     }
-    *reinterpret_cast<uint4*>(b + ((size_t)kc * k_pad + code) * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+    // tiled layout [code tile][k-chunk of 64][k-cell][256 codes][8]: every GEMM stage is one contiguous 32 KB copy
+    const size_t cell = (((size_t)(code / VQ_BLOCK_N) * (d_pad / 64) + kc / 8) * 8 + (kc & 7)) * VQ_BLOCK_N + (code % VQ_BLOCK_N);
+    *reinterpret_cast<uint4*>(b + cell * 8) = make_uint4(h[0], h[1], h[2], h[3]);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -449,7 +451,7 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
   {
     gemm::Operands op{};
     op.a_hi = W.a; op.a_lo = nullptr; op.b_hi = W.b; op.b_lo = nullptr;
-    op.a_rows = rows_pad; op.b_rows = k_pad; op.k = d_pad; op.taps = 1; op.a_row_off[0] = 0;
+    op.a_rows = rows_pad; op.b_rows = k_pad; op.b_packed = 1; op.k = d_pad; op.taps = 1; op.a_row_off[0] = 0;
     op.m_tiles = rows_pad / gemm::BLOCK_M; op.n_tiles = n_tiles; op.a_row0 = 0; op.err_flag = W.err;
     EpiArgExtremum epi{W.c, W.margin, W.cand_cnt, W.cand, W.runmin, rows, alpha};
     using Cfg = gemm::Config<VQ_BLOCK_N, 64, 1, 4>;

@@ -24,7 +24,7 @@ class IgemmDesc(C.Structure):
     _fields_ = [('a_hi', C.c_void_p), ('a_lo', C.c_void_p), ('b_hi', C.c_void_p), ('b_lo', C.c_void_p),
                 ('a_geom', GeomC),
                 ('k_pad', C.c_int32), ('taps', C.c_int32), ('tap_dy', C.c_int32 * 49), ('tap_dx', C.c_int32 * 49),
-                ('b_rows', C.c_int32), ('n_cols', C.c_int32), ('split', C.c_int32),
+                ('b_rows', C.c_int32), ('b_packed', C.c_int32), ('n_cols', C.c_int32), ('split', C.c_int32),
                 ('scale', C.c_float), ('bias', C.c_void_p), ('bias_per_row', C.c_int32), ('act', C.c_int32),
                 ('slope', C.c_float), ('residual', C.c_void_p),
                 ('o_geom', GeomC),
@@ -79,7 +79,7 @@ class Act:
 class Weights:
     """B-operand planes [taps][k_pad/8][b_rows][8] packed once from a reference-layout parameter."""
 
-    def __init__(self, w, kind, taps=None, split=3, block_rows=256, min_rows=0):
+    def __init__(self, w, kind, taps=None, split=3, block_rows=256, min_rows=0, pixel_shuffle=False, plain=False):
         """kind: 'conv' [co, ci, kh, kw] | 'convT' [ci, co, kh, kw] | 'linear' [n, k].
         taps: list of (src_index, dy, dx); default = all kh*kw taps of a 'same' convolution."""
         w = w.detach().contiguous().float()
@@ -106,12 +106,27 @@ class Weights:
         self.b_rows = max(self.b_rows, min_rows)
         self.taps = [(dy, dx) for _, dy, dx in taps]
         src = torch.tensor([t[0] for t in taps], dtype=torch.int32, device=dev)
-        shape = (len(taps), self.k_pad // 8, self.b_rows, 8)
-        self.hi = torch.empty(shape, dtype=torch.bfloat16, device=dev)
-        self.lo = torch.empty(shape, dtype=torch.bfloat16, device=dev) if split == 3 else None
-        _lib.check(_lib.lib().gpemsr_pack_weights(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src),
-                                                  self.b_rows, self.k_pad, _lib.ptr(self.hi), _lib.ptr(self.lo),
-                                                  _lib.stream_ptr()))
+        L = _lib.lib()
+        # ask the library which kernel variant this shape runs: the streaming kernel wants the tiled single-copy layout
+        d = IgemmDesc()
+        d.n_cols, d.k_pad, d.taps, d.split, d.pixel_shuffle = n, self.k_pad, len(taps), split, int(pixel_shuffle)
+        for i, (dy, dx) in enumerate(self.taps):
+            d.tap_dy[i], d.tap_dx[i] = dy, dx
+        bn, fused = C.c_int32(), C.c_int32()
+        _lib.check(L.gpemsr_igemm_plan(C.byref(d), C.byref(bn), C.byref(fused)))
+        self.packed = (not fused.value) and min_rows == 0 and not plain
+        if self.packed:
+            nbytes = L.gpemsr_pack_weights_tiled_bytes(n, self.k_pad, len(taps), bn.value, split)
+            self.hi = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
+            self.lo = None
+            _lib.check(L.gpemsr_pack_weights_tiled(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src), bn.value,
+                                                   self.k_pad, split, _lib.ptr(self.hi), _lib.stream_ptr()))
+        else:
+            shape = (len(taps), self.k_pad // 8, self.b_rows, 8)
+            self.hi = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            self.lo = torch.empty(shape, dtype=torch.bfloat16, device=dev) if split == 3 else None
+            _lib.check(L.gpemsr_pack_weights(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src),
+                                             self.b_rows, self.k_pad, _lib.ptr(self.hi), _lib.ptr(self.lo), _lib.stream_ptr()))
         self._keep = (w, src)
 
 
@@ -137,6 +152,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
     d.a_geom = (a_geom or a.geom).c
     if w is not None:
         d.b_hi, d.b_lo, d.b_rows, d.k_pad = _p(w.hi), _p(w.lo), w.b_rows, w.k_pad
+        d.b_packed = int(w.packed)
         tp = w.taps
         d.n_cols = w.n if n_cols is None else n_cols
     else:

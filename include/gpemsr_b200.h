@@ -120,6 +120,7 @@ typedef struct gpemsr_igemm_desc {
   int32_t taps;                             /* 1..49 */
   int32_t tap_dy[49], tap_dx[49];           /* A row shift of tap t = dy * (w + 2) + dx */
   int32_t b_rows;                           /* allocated B rows per tap (multiple of block_n) */
+  int32_t b_packed;                         /* 1: b_hi is a gpemsr_pack_weights_tiled() buffer (b_lo unused) */
   int32_t n_cols;                           /* valid output columns (channels) */
   int32_t split;                            /* 3: hi/lo planes, fp32-faithful ; 1: single bf16 pass (a_lo/b_lo unused) */
   /* epilogue: v = act(scale * acc + bias) + residual */
@@ -153,6 +154,17 @@ GPEMSR_API int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom
  * n_stride = kh*kw, k_stride = co*kh*kw ; Linear [n, k]: n_stride = k, k_stride = 1, one tap. */
 GPEMSR_API int gpemsr_pack_weights(const float* w, int n, int k, int64_t n_stride, int64_t k_stride, int taps,
                         const int32_t* tap_src, int b_rows, int k_pad, void* hi, void* lo, gpemsr_stream_t stream);
+
+/* Which kernel variant gpemsr_igemm() will run for this descriptor (only n_cols, k_pad, taps, tap_dy/dx, split and
+ * pixel_shuffle are read): *block_n = column tile, *tapfused = 1 when the B-resident tap-fused kernel is used (it needs
+ * the plain gpemsr_pack_weights() layout; the streaming kernel is fastest with gpemsr_pack_weights_tiled()). */
+GPEMSR_API int gpemsr_igemm_plan(const gpemsr_igemm_desc_t* desc, int32_t* block_n, int32_t* tapfused);
+/* weights -> ONE buffer [n_tile][tap][k-chunk][plane][k-cell][block_n][8] so that every pipeline stage of the streaming
+ * kernel is a single contiguous bulk copy.  split = 3: planes (hi, lo), k-chunk = 32 ; split = 1: hi only, k-chunk = 64. */
+GPEMSR_API size_t gpemsr_pack_weights_tiled_bytes(int n, int k_pad, int taps, int block_n, int split);
+GPEMSR_API int gpemsr_pack_weights_tiled(const float* w, int n, int k, int64_t n_stride, int64_t k_stride, int taps,
+                              const int32_t* tap_src, int block_n, int k_pad, int split, void* out,
+                              gpemsr_stream_t stream);
 
 /* GroupNorm(32 groups, eps) over an fp32 master (model/blocks.py:5-6): stats -> per-(image, channel) scale/shift,
  * then y = act(x * scale + shift) (+ residual) written as fp32 master and/or hi/lo planes, optionally re-rowed
