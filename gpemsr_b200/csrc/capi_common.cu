@@ -1,6 +1,7 @@
 // Error reporting, device gate and launch counter shared by every entry point.
 #include "capi_common.h"
 #include <cstring>
+#include <cstdlib>
 
 namespace gpemsr {
 
@@ -39,6 +40,12 @@ int check_device_current() {
   int rc = device_is_sm100(dev);
   if (rc == GPEMSR_OK) cached_dev = dev;
   return rc;
+}
+
+bool use_clusters() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPEMSR_CLUSTER"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
 }
 
 int num_sms() {

@@ -13,6 +13,7 @@ int check_device_current();                 // GPEMSR_OK iff the current device 
 extern std::atomic<long long> g_launches;   // kernels launched by this library
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
+bool use_clusters();                      // GPEMSR_CLUSTER=0 disables the cluster-multicast kernels (A/B testing)
 
 #define GPEMSR_CUDA_OK(expr)                                                              \
   do {                                                                                    \
@@ -30,5 +31,17 @@ int num_sms();
                                  cudaGetErrorString(_e));                                 \
     ::gpemsr::count_launch();                                                             \
   } while (0)
+
+// launch with a thread-block cluster of `cluster_x` CTAs along x
+template <class Kern, class... Args>
+inline cudaError_t launch_cluster(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, unsigned cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 }  // namespace gpemsr

@@ -180,12 +180,21 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.c_off = d.c_off;
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
-  auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, Epi>;
-  GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int sms = gpemsr::num_sms();
-  const long long gx = std::min<long long>(op.m_tiles, sms);
+  long long gx = std::min<long long>(op.m_tiles, sms);
   long long gy = 1;
   if (op.m_tiles < sms) gy = std::min<long long>(op.n_tiles, (sms + op.m_tiles - 1) / op.m_tiles);
+  if (BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters()) {
+    // wide tiles are bound by operand traffic out of L2: pairs of CTAs share every B stage by multicast
+    auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, Epi, 2>;
+    GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    gx = (gx + 1) / 2 * 2;
+    GPEMSR_CUDA_OK(gpemsr::launch_cluster(kern, dim3((unsigned)gx, (unsigned)gy), dim3(gemm::num_threads<Epi>()), Cfg::SMEM_BYTES, s, 2, op, e));
+    gpemsr::count_launch();
+    return GPEMSR_OK;
+  }
+  auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, Epi>;
+  GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   kern<<<dim3((unsigned)gx, (unsigned)gy), gemm::num_threads<Epi>(), Cfg::SMEM_BYTES, s>>>(op, e);
   GPEMSR_LAUNCH_OK("gemm_kernel<EpiConv>");
   return GPEMSR_OK;

@@ -22,13 +22,11 @@
 //     u = ((n + 1) / 2) * (size - 1) ; [border: u = min(size-1, max(u, 0))]   (ATen unnormalize/clip)
 // then ATen's bilinear weights (x_se - x)(y_se - y)... and the accumulation order nw, ne, sw, se.
 #include "capi_common.h"
+#include <cstdlib>
 
 namespace {
 
-constexpr int TILE_W = 32;
-constexpr int TILE_H = 8;
-constexpr int THREADS = TILE_W * TILE_H;
-constexpr int CH_UNROLL = 4;
+constexpr int THREADS = 256;
 
 struct Taps {
   int o_nw, o_ne, o_sw, o_se;      // offsets inside one (n, c) plane, clamped into the plane
@@ -75,12 +73,15 @@ __device__ __forceinline__ Taps make_taps(float fx, float fy, int px, int py, in
   return t;
 }
 
-__global__ void __launch_bounds__(THREADS)
+template <int TILE_W, int TILE_H, int CH_UNROLL, int MIN_BLOCKS = 5>
+__global__ void __launch_bounds__(TILE_W * TILE_H, MIN_BLOCKS)
 flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
                  int c, int h, int w, int c_per_cta, int border, int align_corners) {
-  __shared__ int4 s_off[THREADS];
-  __shared__ float4 s_wgt[THREADS];
+  constexpr int NT = TILE_W * TILE_H;
+  __shared__ int4 s_off[NT];
+  __shared__ float4 s_wgt[NT];
 
+  static_assert(TILE_W % 32 == 0 && NT <= 1024, "tile");
   const int tx = threadIdx.x & (TILE_W - 1), ty = threadIdx.x / TILE_W;
   const int px = blockIdx.x * TILE_W + tx, py = blockIdx.y * TILE_H + ty;
   const int c_splits = (c + c_per_cta - 1) / c_per_cta;
@@ -169,6 +170,11 @@ extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c,
   if (reinterpret_cast<uintptr_t>(flow) & 7)
     return set_error(GPEMSR_ERR_BAD_ALIGN, "flow_warp: flow must be 8-byte aligned");
 
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("GPEMSR_FLOW_VARIANT"); variant = e ? atoi(e) : 0; }
+  const int TILE_W = variant == 2 || variant == 4 || variant == 10 ? 64 : variant == 3 ? 128 : 32;
+  const int TILE_H = variant == 9 ? 32 : variant == 10 || variant == 11 ? 16 : THREADS / TILE_W;
+  const int CH_UNROLL = variant == 1 || variant == 4 ? 8 : 4;
   const int tiles_x = (w + TILE_W - 1) / TILE_W, tiles_y = (h + TILE_H - 1) / TILE_H;
   // split channels across CTAs only when the pixel tiles alone cannot fill the chip (>= ~4 waves)
   const long long tiles = (long long)tiles_x * tiles_y * n;
@@ -183,8 +189,22 @@ extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c,
     return set_error(GPEMSR_ERR_BAD_SHAPE, "flow_warp: grid too large (n*c_splits=%lld, tiles_y=%d)",
                      (long long)n * c_splits, tiles_y);
   dim3 grid(tiles_x, tiles_y, n * c_splits);
-  flow_warp_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, flow, out, c, h, w, c_per_cta,
-                                                               padding_mode == GPEMSR_PAD_BORDER, align_corners);
+  const int bd = padding_mode == GPEMSR_PAD_BORDER;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (variant) {
+    case 1: flow_warp_kernel<32, 8, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 2: flow_warp_kernel<64, 4, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 3: flow_warp_kernel<128, 2, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 4: flow_warp_kernel<64, 4, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 5: flow_warp_kernel<32, 8, 4, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 6: flow_warp_kernel<32, 8, 4, 6><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 7: flow_warp_kernel<32, 8, 8, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 9: flow_warp_kernel<32, 32, 4, 1><<<grid, 1024, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 10: flow_warp_kernel<64, 16, 4, 1><<<grid, 1024, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 11: flow_warp_kernel<32, 16, 4, 2><<<grid, 512, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    case 8: flow_warp_kernel<32, 8, 2, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+    default: flow_warp_kernel<32, 8, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
+  }
   GPEMSR_LAUNCH_OK("flow_warp_kernel");
   return GPEMSR_OK;
 }

@@ -77,6 +77,7 @@ struct Barriers {
   uint64_t tmem_empty[2];
   uint64_t b_full;             // tap-fused mode: resident B has landed
   uint32_t tmem_base;
+  uint32_t tap_tab[2 * MAX_TAPS];   // tap-fused mode: per-tap descriptor start-address offsets
 };
 
 // Epilogue concept:
@@ -328,6 +329,16 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     bool ok = true;
     if (blockIdx.x < op.m_tiles) ok = sm100::mbar_wait(&bars->b_full, 0, op.err_flag, 5);
     const uint32_t sb0 = sm100::smem_u32(b_res);
+    // per-tap start-address offsets (16-byte units): [2t] = A (segment + dx shift), [2t+1] = B (tap block)
+    uint32_t* tap_tab = bars->tap_tab;
+    for (int t = lane; t < op.taps; t += 32) {
+      tap_tab[2 * t] = ((uint32_t)(op.tap_seg[t] * KCH) * seg_bytes + (uint32_t)op.tap_dx[t] * 16) >> 4;
+      tap_tab[2 * t + 1] = ((uint32_t)t * b_tap_bytes) >> 4;
+    }
+    __syncwarp();
+    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1
+    const uint32_t a_desc_lo = ((seg_bytes >> 4) & 0x3FFFu) << 16;           // LBO = one k-cell column of a segment
+    const uint32_t b_desc_lo = (((uint32_t)BLOCK_N * 16 >> 4) & 0x3FFFu) << 16;
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
       ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
       if (!ok) break;
@@ -338,18 +349,19 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
         if (!ok) break;
         sm100::tc_fence_after();
         if (sm100::elect_one()) {
-          const uint32_t sa = sm100::smem_u32(stages + (size_t)stage * stage_bytes);
+          // descriptors differ from a per-stage base only in the 14-bit start-address field (16-byte units): the issuing
+          // thread -- the serial bottleneck of this loop -- does two adds per MMA, offsets come from a smem table
+          const uint32_t a_lo0 = a_desc_lo + (sm100::smem_u32(stages + (size_t)stage * stage_bytes) >> 4);
+          const uint32_t b_lo0 = b_desc_lo + ((sb0 + (uint32_t)(it * KCH) * (BLOCK_N * 16)) >> 4);
           for (int t = 0; t < op.taps; ++t) {
-            const uint32_t a_addr = sa + (uint32_t)(op.tap_seg[t] * KCH) * seg_bytes + (uint32_t)op.tap_dx[t] * 16;
-            const uint32_t b_addr = sb0 + (uint32_t)t * b_tap_bytes + (uint32_t)(it * KCH) * (BLOCK_N * 16);
-            const uint64_t a_hi = sm100::smem_desc_kmajor_noswz(a_addr, seg_bytes, 128);
-            const uint64_t b_hi = sm100::smem_desc_kmajor_noswz(b_addr, BLOCK_N * 16, 128);
-            sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | t) != 0);
+            const uint32_t a_lo = a_lo0 + tap_tab[2 * t], b_lo = b_lo0 + tap_tab[2 * t + 1];
+            const uint64_t a_hi_d = ((uint64_t)kDescHi << 32) | a_lo, b_hi_d = ((uint64_t)kDescHi << 32) | b_lo;
+            sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
             if constexpr (SPLIT == 3) {
-              const uint64_t a_lo = sm100::smem_desc_kmajor_noswz(a_addr + a_plane_bytes, seg_bytes, 128);
-              const uint64_t b_lo = sm100::smem_desc_kmajor_noswz(b_addr + (uint32_t)op.taps * b_tap_bytes, BLOCK_N * 16, 128);
-              sm100::umma_bf16(tmem_acc, a_lo, b_hi, idesc, true);
-              sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
+              const uint64_t a_lo_d = ((uint64_t)kDescHi << 32) | (a_lo + (a_plane_bytes >> 4));
+              const uint64_t b_lo_d = ((uint64_t)kDescHi << 32) | (b_lo + (((uint32_t)op.taps * b_tap_bytes) >> 4));
+              sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi_d, b_lo_d, idesc, true);
             }
           }
           sm100::umma_commit(&bars->empty[stage]);

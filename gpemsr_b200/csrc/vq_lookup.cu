@@ -27,7 +27,9 @@
 
 namespace {
 
-constexpr int CMAX = 16;             // candidate-list slots per row; more appends -> exact scan of every code for that row
+constexpr int CMAX = 32;             // candidate-list slots per row (two sub-lists of CMAX/2, one per epilogue warp of the
+                                     // row); more appends -> exact scan of every code for that row
+constexpr int CSUB = CMAX / 2;
 constexpr int VQ_BLOCK_N = 256;
 constexpr uint32_t OVERFLOW = 0xFFFFFFFFu;
 constexpr int FIN_ROWS = 32;         // rows per finalize block
@@ -41,9 +43,9 @@ struct Workspace {
   float* c;               // [k_pad]   |e_k|^2 (or -bias_k); +inf for padding codes
   float* zz;              // [rows_pad]
   float* margin;          // [rows_pad]
-  uint32_t* cand_cnt;     // [rows_pad]  0 = decided in the epilogue, n = ambiguous with n candidates, OVERFLOW
+  uint32_t* cand_cnt;     // [rows_pad][2] appended candidates per (row, column half), OVERFLOW when > CSUB
   uint2* cand;            // [rows_pad][CMAX] (code, approx score), ascending code order
-  float* runmin;          // [rows_pad] final approximate minimum
+  float* runmin;          // [rows_pad][2] approximate minimum over each column half
   float* emax;            // [1] max_k |e_k|_2   (as float bits, written with atomicMax)
   int* err;               // [1] GEMM pipeline error flag
   size_t bytes;
@@ -60,9 +62,9 @@ Workspace carve(void* base, long long rows, int d, int k) {
   w.c = (float*)take((size_t)k_pad * 4);
   w.zz = (float*)take((size_t)rows_pad * 4);
   w.margin = (float*)take((size_t)rows_pad * 4);
-  w.cand_cnt = (uint32_t*)take((size_t)rows_pad * 4);
+  w.cand_cnt = (uint32_t*)take((size_t)rows_pad * 2 * 4);
   w.cand = (uint2*)take((size_t)rows_pad * CMAX * 8);
-  w.runmin = (float*)take((size_t)rows_pad * 4);
+  w.runmin = (float*)take((size_t)rows_pad * 2 * 4);
   w.emax = (float*)take(4);
   w.err = (int*)take(4);
   w.bytes = (size_t)(p - (uintptr_t)base);
@@ -149,7 +151,8 @@ struct EpiArgExtremum {
   long long rows;
   float alpha;
 
-  static constexpr int WARPS = 4;        // the row's running minimum and list are carried by ONE thread
+  static constexpr int WARPS = 8;        // two warps per TMEM lane quarter: each row is scanned by two threads, one per
+                                         // half of the tile's columns, with its own running minimum and sub-list
   struct State {
     float runmin = INFINITY;
     uint32_t cnt = 0;
@@ -175,7 +178,7 @@ struct EpiArgExtremum {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (v[u] <= thr) {
-            if (st.cnt < CMAX) list[st.cnt] = make_uint2(code0 + j + u, __float_as_uint(v[u]));
+            if (st.cnt < CSUB) list[st.cnt] = make_uint2(code0 + j + u, __float_as_uint(v[u]));
             ++st.cnt;
           }
         }
@@ -184,38 +187,42 @@ struct EpiArgExtremum {
   }
 
   // TMEM loads are software-pipelined one 32-column chunk ahead of the arithmetic.
-  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int) const {
+  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int part) const {
+    constexpr int SPAN = VQ_BLOCK_N / 2;                       // columns per epilogue warp
     const long long gr = m_tile * gemm::BLOCK_M + row;
     const bool live = gr < rows;
-    const float* cc = c + (size_t)n_tile * VQ_BLOCK_N;
+    const int cbase = part * SPAN;
+    const float* cc = c + (size_t)n_tile * VQ_BLOCK_N + cbase;
     const float mg = live ? __ldg(margin + gr) : 0.f;
-    uint2* list = cand + (size_t)(live ? gr : 0) * CMAX;
+    uint2* list = cand + ((size_t)(live ? gr : 0) * 2 + part) * CSUB;
+    const uint32_t tm = tmem_acc + cbase;
     uint32_t ra[32], rb[32];
     float mn = st.runmin;
-    sm100::tmem_ld_32x32(tmem_acc, ra);
+    sm100::tmem_ld_32x32(tm, ra);
 #pragma unroll 1
-    for (int c0 = 0; c0 < VQ_BLOCK_N; c0 += 64) {
+    for (int c0 = 0; c0 < SPAN; c0 += 64) {
       sm100::tmem_ld_wait();
-      sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);
+      sm100::tmem_ld_32x32(tm + c0 + 32, rb);
       mn = min32(ra, cc + c0, mn);
       sm100::tmem_ld_wait();
-      sm100::tmem_ld_32x32(tmem_acc + ((c0 + 64) & (VQ_BLOCK_N - 1)), ra);     // wraps to column 0 for pass 2
+      sm100::tmem_ld_32x32(tm + ((c0 + 64) & (SPAN - 1)), ra);       // wraps to the first column for pass 2
       mn = min32(rb, cc + c0 + 32, mn);
     }
     st.runmin = mn;
     const float thr = live ? mn + mg : -INFINITY;      // padding rows never append
+    const uint32_t code_base = (uint32_t)(n_tile * VQ_BLOCK_N + cbase);
 #pragma unroll 1
-    for (int c0 = 0; c0 < VQ_BLOCK_N; c0 += 64) {
+    for (int c0 = 0; c0 < SPAN; c0 += 64) {
       sm100::tmem_ld_wait();
-      sm100::tmem_ld_32x32(tmem_acc + c0 + 32, rb);
-      scan32(st, ra, cc + c0, (uint32_t)(n_tile * VQ_BLOCK_N + c0), thr, list);
+      sm100::tmem_ld_32x32(tm + c0 + 32, rb);
+      scan32(st, ra, cc + c0, code_base + c0, thr, list);
       sm100::tmem_ld_wait();
-      if (c0 + 64 < VQ_BLOCK_N) sm100::tmem_ld_32x32(tmem_acc + c0 + 64, ra);
-      scan32(st, rb, cc + c0 + 32, (uint32_t)(n_tile * VQ_BLOCK_N + c0 + 32), thr, list);
+      if (c0 + 64 < SPAN) sm100::tmem_ld_32x32(tm + c0 + 64, ra);
+      scan32(st, rb, cc + c0 + 32, code_base + c0 + 32, thr, list);
     }
     if (n_tile == n_tiles - 1 && live) {
-      cand_cnt[gr] = st.cnt > CMAX ? OVERFLOW : st.cnt;
-      runmin_out[gr] = mn;
+      cand_cnt[gr * 2 + part] = st.cnt > CSUB ? OVERFLOW : st.cnt;
+      runmin_out[gr * 2 + part] = mn;
     }
   }
 };
@@ -278,15 +285,18 @@ vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const floa
     uint32_t mine[CMAX];
     if (lane < nrows) {
       const long long gr = row0 + lane;
-      const uint32_t n = cand_cnt[gr];
-      if (n == OVERFLOW) {
+      const uint32_t n0 = cand_cnt[gr * 2], n1 = cand_cnt[gr * 2 + 1];
+      if (n0 == OVERFLOW || n1 == OVERFLOW) {
         over = 1;
       } else {
-        const float thr = runmin[gr] + margin[gr];
-        const uint2* cl = cand + (size_t)gr * CMAX;
-        for (uint32_t i = 0; i < n; ++i) {
-          const uint2 e = cl[i];
-          if (__uint_as_float(e.y) <= thr) mine[nsurv++] = e.x;
+        const float thr = fminf(runmin[gr * 2], runmin[gr * 2 + 1]) + margin[gr];
+        for (int part = 0; part < 2; ++part) {
+          const uint2* cl = cand + ((size_t)gr * 2 + part) * CSUB;
+          const uint32_t n = part ? n1 : n0;
+          for (uint32_t i = 0; i < n; ++i) {
+            const uint2 e = cl[i];
+            if (__uint_as_float(e.y) <= thr) mine[nsurv++] = e.x;
+          }
         }
         if (nsurv <= 1) s_idx[lane] = nsurv ? (int)mine[0] : 0;        // decided (0 survivors only for NaN rows)
       }
@@ -352,8 +362,10 @@ vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const floa
       const int f = s_first[threadIdx.x], l = s_first[threadIdx.x + 1];
       if (l > f) {
         float bs = INFINITY; int best = 0;
-        for (int p = f; p < l; ++p)                                  // ascending code order; strict '<' keeps the lowest index
-          if (s_score[p] < bs) { bs = s_score[p]; best = (int)(s_pair[p] & 0xFFFFu); }
+        for (int p = f; p < l; ++p) {                                // lowest index wins ties (the two sub-lists interleave)
+          const int kk = (int)(s_pair[p] & 0xFFFFu);
+          if (s_score[p] < bs || (s_score[p] == bs && kk < best)) { bs = s_score[p]; best = kk; }
+        }
         s_idx[threadIdx.x] = best;
       }
     }
@@ -455,10 +467,17 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
     op.m_tiles = rows_pad / gemm::BLOCK_M; op.n_tiles = n_tiles; op.a_row0 = 0; op.err_flag = W.err;
     EpiArgExtremum epi{W.c, W.margin, W.cand_cnt, W.cand, W.runmin, rows, alpha};
     using Cfg = gemm::Config<VQ_BLOCK_N, 64, 1, 4>;
-    auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum>;
-    GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    const int grid = (int)std::min<long long>(op.m_tiles, num_sms());
-    kern<<<grid, gemm::NUM_THREADS, Cfg::SMEM_BYTES, s>>>(op, epi);
+    if (op.m_tiles >= 2 && use_clusters()) {       // CTA pairs share every codebook stage by multicast (halves L2 traffic)
+      auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum, 2>;
+      GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      const int grid = (int)((std::min<long long>(op.m_tiles, num_sms()) + 1) / 2 * 2);
+      GPEMSR_CUDA_OK(launch_cluster(kern, dim3(grid), dim3(gemm::num_threads<EpiArgExtremum>()), Cfg::SMEM_BYTES, s, 2, op, epi));
+    } else {
+      auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum>;
+      GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      const int grid = (int)std::min<long long>(op.m_tiles, num_sms());
+      kern<<<grid, gemm::num_threads<EpiArgExtremum>(), Cfg::SMEM_BYTES, s>>>(op, epi);
+    }
     GPEMSR_LAUNCH_OK("gemm_kernel<EpiArgExtremum>");
   }
   {
