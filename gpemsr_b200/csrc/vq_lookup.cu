@@ -18,8 +18,9 @@
 //                                     conversion), |z|^2 and the candidate margin per row; ONE pass over z
 //   gemm_kernel<EpiArgExtremum>    -> a CTA owns 128 rows and sweeps all code tiles; the epilogue thread of a row carries
 //                                     the running minimum and a <= 8 entry candidate list across the tiles
-//   vq_finalize     32-row blocks: z tile staged (transposed) in smem, warp-per-row fp32 re-score of ambiguous rows,
-//                   code-vector gather transposed through smem so that both e reads and NCHW z_q writes are coalesced
+//   vq_rescore      32-row blocks: ambiguous rows only; fp32 z staged transposed in smem chunk by chunk, (row, code) pairs
+//                   re-scored by warps round-robin -> final int64 indices
+//   vq_gather       e[idx] -> NCHW z_q through a smem transpose (coalesced code reads and coalesced stores)
 #include "capi_common.h"
 #include "gemm_core.cuh"
 #include <algorithm>
@@ -228,58 +229,42 @@ struct EpiArgExtremum {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// finalize: a block owns FIN_ROWS consecutive rows of one image (consecutive hw).
+// vq_rescore: a block owns FIN_ROWS consecutive rows of one image (consecutive hw) and decides their indices.
 //   mode 0 (Codebook.forward):  d_k = (|z|^2 + |e_k|^2) - 2 * dot_k, minimise, lowest index on ties
 //   mode 1 (inference_lr):      l_k = dot_k + bias_k, maximise, lowest index on ties
-// Steps: (0) filter each row's candidate list against its final minimum; rows with one survivor are decided, the others
-// contribute (row, code) pairs to a block-wide work list; (A) stage the fp32 z tile transposed in shared memory (coalesced
-// reads along hw); (B) warps take pairs round-robin -- one coalesced fp32 dot product each -- so the load is balanced
-// whatever the mix of rows; (C) gather e[idx] (coalesced along d) into the transposed tile; (D) NCHW store along hw.
-__device__ __forceinline__ float warp_dot(const float* __restrict__ zt, int r, const float* __restrict__ wk, int d, int lane) {
-  float acc = 0.f;
-  int i = lane;
-  for (; i + 96 < d; i += 128) {
-    const float w0 = __ldg(wk + i), w1 = __ldg(wk + i + 32), w2 = __ldg(wk + i + 64), w3 = __ldg(wk + i + 96);
-    acc = fmaf(zt[i * (FIN_ROWS + 1) + r], w0, acc);
-    acc = fmaf(zt[(i + 32) * (FIN_ROWS + 1) + r], w1, acc);
-    acc = fmaf(zt[(i + 64) * (FIN_ROWS + 1) + r], w2, acc);
-    acc = fmaf(zt[(i + 96) * (FIN_ROWS + 1) + r], w3, acc);
-  }
-  for (; i < d; i += 32) acc = fmaf(zt[i * (FIN_ROWS + 1) + r], __ldg(wk + i), acc);
-#pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  return acc;
-}
+// (0) warp 0 filters each row's candidate sub-lists against the row's final minimum; rows with one survivor are decided,
+// the others contribute (row, code) pairs to a block-wide work list (blocks without pairs exit without touching z);
+// (1) the fp32 z tile is staged transposed through shared memory in 128-channel chunks (coalesced reads along hw) and
+// warps take pairs round-robin, one coalesced fp32 partial dot product per (pair, chunk), so the load is balanced
+// whatever the mix of rows; (2) the exact scores pick the winner.  The small per-chunk tile keeps many blocks resident.
 __device__ __forceinline__ float score_of(float dot, int mode, float zz, float ck) {
   if (mode == 0) return __fsub_rn(__fadd_rn(zz, ck), __fmul_rn(2.0f, dot));
   return -__fadd_rn(dot, -ck);          // ck = -bias_k ; negated logit so that "smaller is better"
 }
 
 constexpr int FIN_MAXPAIRS = FIN_ROWS * CMAX;
+constexpr int FIN_DCH = 128;                     // channels staged per chunk
 
 __global__ void __launch_bounds__(FIN_THREADS)
-vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ table, long long hw,
-            int blocks_per_image, int d, int k, int dq, int mode, const float* __restrict__ c, const float* __restrict__ zz,
-            const float* __restrict__ margin, const float* __restrict__ runmin, const uint32_t* __restrict__ cand_cnt,
-            const uint2* __restrict__ cand, float* __restrict__ zq, long long* __restrict__ idx_out, float* __restrict__ sq_err) {
-  extern __shared__ float zt[];                  // [max(d, dq)][FIN_ROWS + 1]
+vq_rescore(const float* __restrict__ z, const float* __restrict__ w, long long hw, int blocks_per_image, int d, int k, int mode,
+           const float* __restrict__ c, const float* __restrict__ zz, const float* __restrict__ margin,
+           const float* __restrict__ runmin, const uint32_t* __restrict__ cand_cnt, const uint2* __restrict__ cand,
+           long long* __restrict__ idx_out) {
+  constexpr int NW = FIN_THREADS / 32;
+  constexpr int LD = FIN_ROWS + 1;
+  __shared__ float zt[FIN_DCH * LD];
   __shared__ int s_idx[FIN_ROWS];
   __shared__ int s_first[FIN_ROWS + 1];          // first pair of each row (prefix sum)
   __shared__ uint32_t s_pair[FIN_MAXPAIRS];      // (row << 16) | code
-  __shared__ float s_score[FIN_MAXPAIRS];
+  __shared__ float s_score[FIN_MAXPAIRS];        // fp32 dot products, accumulated chunk by chunk
   __shared__ int s_over[FIN_ROWS];
   __shared__ int s_nover, s_npairs;
-  __shared__ float s_wbest[FIN_THREADS / 32];
-  __shared__ int s_wbestk[FIN_THREADS / 32];
-  constexpr int NW = FIN_THREADS / 32;
-  constexpr int LD = FIN_ROWS + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long bi = blockIdx.x / blocks_per_image;
   const long long p0 = (long long)(blockIdx.x % blocks_per_image) * FIN_ROWS;
   const int nrows = (int)min((long long)FIN_ROWS, hw - p0);
   const long long row0 = bi * hw + p0;
 
-  // ---- step 0 (warp 0): filter candidate lists, build the pair list
   if (warp == 0) {
     int nsurv = 0, over = 0;
     uint32_t mine[CMAX];
@@ -315,90 +300,119 @@ vq_finalize(const float* __restrict__ z, const float* __restrict__ w, const floa
   }
   __syncthreads();
   const int npairs = s_npairs, nover = s_nover;
-  const bool need_z = npairs > 0 || nover > 0 || sq_err != nullptr;
 
-  if (need_z) {
-    // ---- step A: fp32 z tile, transposed ([d][row])
+  if (npairs > 0) {
     const float* zb = z + bi * d * hw + p0 + (lane < nrows ? lane : 0);
-    int i = warp;
-    for (; i + 7 * NW < d; i += 8 * NW) {            // 8 independent 128-byte loads in flight per warp
-      float v[8];
+    for (int d0 = 0; d0 < d; d0 += FIN_DCH) {
+      const int dn = min(FIN_DCH, d - d0);
+      // stage z[d0 .. d0+dn) x 32 rows, transposed: 8 independent 128-byte loads in flight per warp
+      {
+        float v[FIN_DCH / NW];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(zb + (long long)(i + u * NW) * hw);
+        for (int u = 0; u < FIN_DCH / NW; ++u) { const int dd = warp + u * NW; v[u] = dd < dn ? __ldg(zb + (long long)(d0 + dd) * hw) : 0.f; }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) zt[(i + u * NW) * LD + lane] = v[u];
-    }
-    for (; i < d; i += NW) zt[i * LD + lane] = __ldg(zb + (long long)i * hw);
-    __syncthreads();
-    // ---- step B: one warp per (row, code) pair
-    for (int p = warp; p < npairs; p += NW) {
-      const uint32_t pr = s_pair[p];
-      const int r = (int)(pr >> 16), kk = (int)(pr & 0xFFFFu);
-      const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zz[row0 + r], c[kk]);
-      if (lane == 0) s_score[p] = sc;
-    }
-    // rows whose list overflowed (many duplicated / near-tied codes): every warp scans a slice of ALL codes
-    for (int o = 0; o < nover; ++o) {
-      const int r = s_over[o];
-      const float zzr = zz[row0 + r];
-      float bs = INFINITY;
-      int bk = 0x7fffffff;
-      for (int kk = warp; kk < k; kk += NW) {
-        const float sc = score_of(warp_dot(zt, r, w + (size_t)kk * d, d, lane), mode, zzr, c[kk]);
-        if (sc < bs) { bs = sc; bk = kk; }
+        for (int u = 0; u < FIN_DCH / NW; ++u) zt[(warp + u * NW) * LD + lane] = v[u];
       }
-      if (lane == 0) { s_wbest[warp] = bs; s_wbestk[warp] = bk; }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        float b = INFINITY; int bkk = 0x7fffffff;
-        for (int wv = 0; wv < NW; ++wv)
-          if (s_wbest[wv] < b || (s_wbest[wv] == b && s_wbestk[wv] < bkk)) { b = s_wbest[wv]; bkk = s_wbestk[wv]; }
-        s_idx[r] = bkk == 0x7fffffff ? 0 : bkk;
+      for (int p = warp; p < npairs; p += NW) {
+        const uint32_t pr = s_pair[p];
+        const int r = (int)(pr >> 16), kk = (int)(pr & 0xFFFFu);
+        const float* wk = w + (size_t)kk * d + d0;
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < FIN_DCH / 32; ++u) {
+          const int dd = lane + 32 * u;
+          acc = fmaf(zt[dd * LD + r], dd < dn ? __ldg(wk + dd) : 0.f, acc);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_score[p] = d0 ? s_score[p] + acc : acc;
       }
       __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x < nrows) {
       const int f = s_first[threadIdx.x], l = s_first[threadIdx.x + 1];
       if (l > f) {
+        const float zzr = zz[row0 + threadIdx.x];
         float bs = INFINITY; int best = 0;
         for (int p = f; p < l; ++p) {                                // lowest index wins ties (the two sub-lists interleave)
           const int kk = (int)(s_pair[p] & 0xFFFFu);
-          if (s_score[p] < bs || (s_score[p] == bs && kk < best)) { bs = s_score[p]; best = kk; }
+          const float sc = score_of(s_score[p], mode, zzr, c[kk]);
+          if (sc < bs || (sc == bs && kk < best)) { bs = sc; best = kk; }
         }
         s_idx[threadIdx.x] = best;
       }
     }
+  }
+  // rows whose sub-lists overflowed (many duplicated / near-tied codes; rare): exact scan of ALL codes, z read in place
+  for (int o = 0; o < nover; ++o) {
+    __shared__ float s_wbest[NW];
+    __shared__ int s_wbestk[NW];
+    const int r = s_over[o];
+    const float* zr = z + bi * d * hw + p0 + r;
+    const float zzr = zz[row0 + r];
+    float bs = INFINITY;
+    int bk = 0x7fffffff;
+    for (int kk = warp; kk < k; kk += NW) {
+      float acc = 0.f;
+      for (int i = lane; i < d; i += 32) acc = fmaf(__ldg(zr + (long long)i * hw), __ldg(w + (size_t)kk * d + i), acc);
+#pragma unroll
+      for (int of = 16; of; of >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, of);
+      const float sc = score_of(acc, mode, zzr, c[kk]);
+      if (sc < bs) { bs = sc; bk = kk; }
+    }
+    if (lane == 0) { s_wbest[warp] = bs; s_wbestk[warp] = bk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = INFINITY; int bkk = 0x7fffffff;
+      for (int wv = 0; wv < NW; ++wv)
+        if (s_wbest[wv] < b || (s_wbest[wv] == b && s_wbestk[wv] < bkk)) { b = s_wbest[wv]; bkk = s_wbestk[wv]; }
+      s_idx[r] = bkk == 0x7fffffff ? 0 : bkk;
+    }
     __syncthreads();
   }
+  __syncthreads();
   if (threadIdx.x < nrows) idx_out[row0 + threadIdx.x] = s_idx[threadIdx.x];
+}
 
-  // ---- step C: gather e[idx] (coalesced along d) into the transposed tile, optionally accumulating (e - z)^2
-  float err = 0.f;
-  for (int r = warp; r < nrows; r += NW) {
-    const float* src = table + (size_t)s_idx[r] * dq;
-    int i = lane;
-    for (; i + 96 < dq; i += 128) {
-      float ev[4];
+// vq_gather: z_q[b, :, hw] = table[idx[b, hw], :] -- the embedding gather and the NHWC->NCHW permute of codebook.py:24,30
+// in one pass: code vectors are read coalesced along d, transposed through shared memory and stored coalesced along hw.
+// Optionally accumulates sum((z_q - z)^2) for the loss (codebook.py:26).
+constexpr int GA_DCH = 128;
+__global__ void __launch_bounds__(256)
+vq_gather(const float* __restrict__ table, const long long* __restrict__ idx, long long hw, int blocks_per_image, int dq,
+          float* __restrict__ zq, const float* __restrict__ z, float* __restrict__ sq_err) {
+  constexpr int LD = FIN_ROWS + 1;
+  __shared__ float t[GA_DCH * LD];
+  __shared__ int s_idx[FIN_ROWS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bi = blockIdx.x / blocks_per_image;
+  const long long p0 = (long long)(blockIdx.x % blocks_per_image) * FIN_ROWS;
+  const int nrows = (int)min((long long)FIN_ROWS, hw - p0);
+  const int d0 = blockIdx.y * GA_DCH, dn = min(GA_DCH, dq - d0);
+  if (threadIdx.x < FIN_ROWS) s_idx[threadIdx.x] = threadIdx.x < nrows ? (int)idx[bi * hw + p0 + threadIdx.x] : 0;
+  __syncthreads();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) ev[u] = __ldg(src + i + 32 * u);
+  for (int rr = 0; rr < FIN_ROWS / 8; ++rr) {
+    const int r = warp + 8 * rr;
+    const float* src = table + (size_t)s_idx[r] * dq + d0;
+    float v[GA_DCH / 32];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (sq_err) { const float dl = ev[u] - zt[(i + 32 * u) * LD + r]; err = fmaf(dl, dl, err); }
-        zt[(i + 32 * u) * LD + r] = ev[u];
-      }
-    }
-    for (; i < dq; i += 32) {
-      const float ev = __ldg(src + i);
-      if (sq_err) { const float dl = ev - zt[i * LD + r]; err = fmaf(dl, dl, err); }
-      zt[i * LD + r] = ev;
-    }
+    for (int u = 0; u < GA_DCH / 32; ++u) v[u] = (lane + 32 * u) < dn ? __ldg(src + lane + 32 * u) : 0.f;
+#pragma unroll
+    for (int u = 0; u < GA_DCH / 32; ++u) t[(lane + 32 * u) * LD + r] = v[u];
   }
   __syncthreads();
-  // ---- step D: NCHW store, lane <-> consecutive hw
-  float* qb = zq + bi * dq * hw + p0;
-  if (lane < nrows)
-    for (int i = warp; i < dq; i += NW) __stcs(qb + (long long)i * hw + lane, zt[i * LD + lane]);
+  float err = 0.f;
+  if (lane < nrows) {
+    float* qb = zq + (bi * dq + d0) * hw + p0 + lane;
+    const float* zb = z ? z + (bi * dq + d0) * hw + p0 + lane : nullptr;
+    for (int dd = warp; dd < dn; dd += 8) {
+      const float v = t[dd * LD + lane];
+      __stcs(qb + (long long)dd * hw, v);
+      if (zb) { const float dl = v - __ldg(zb + (long long)dd * hw); err = fmaf(dl, dl, err); }
+    }
+  }
   if (sq_err) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
@@ -437,8 +451,6 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
   if (b < 0 || d <= 0 || hw < 0 || k <= 0 || dq <= 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: bad shape b=%d d=%d hw=%lld k=%d dq=%d", b, d, hw, k, dq);
   if (k > 65535) return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: more than 65535 codes");
-  if (std::max(d, dq) > 1536)
-    return set_error(GPEMSR_ERR_BAD_SHAPE, "vq lookup: latent_dim %d > 1536 does not fit the finalize tile", std::max(d, dq));
   int rc = check_device_current();
   if (rc != GPEMSR_OK) return rc;
   const long long rows = (long long)b * hw;
@@ -481,14 +493,15 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
     GPEMSR_LAUNCH_OK("gemm_kernel<EpiArgExtremum>");
   }
   {
-    if (sq_err_sum) GPEMSR_CUDA_OK(cudaMemsetAsync(sq_err_sum, 0, sizeof(float), s));
     const int blocks_per_image = (int)((hw + FIN_ROWS - 1) / FIN_ROWS);
-    const size_t smem = (size_t)std::max(d, dq) * (FIN_ROWS + 1) * sizeof(float);
-    GPEMSR_CUDA_OK(cudaFuncSetAttribute(vq_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vq_finalize<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, smem, s>>>(
-        z, w, table, hw, blocks_per_image, d, k, dq, mode, W.c, W.zz, W.margin, W.runmin, W.cand_cnt, W.cand, zq, idx,
-        (mode == 0) ? sq_err_sum : nullptr);
-    GPEMSR_LAUNCH_OK("vq_finalize");
+    vq_rescore<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, 0, s>>>(
+        z, w, hw, blocks_per_image, d, k, mode, W.c, W.zz, W.margin, W.runmin, W.cand_cnt, W.cand, idx);
+    GPEMSR_LAUNCH_OK("vq_rescore");
+    const bool want_err = mode == 0 && sq_err_sum != nullptr;
+    if (want_err) GPEMSR_CUDA_OK(cudaMemsetAsync(sq_err_sum, 0, sizeof(float), s));
+    dim3 grid((unsigned)((long long)b * blocks_per_image), (unsigned)((dq + GA_DCH - 1) / GA_DCH));
+    vq_gather<<<grid, 256, 0, s>>>(table, idx, hw, blocks_per_image, dq, zq, want_err ? z : nullptr, want_err ? sq_err_sum : nullptr);
+    GPEMSR_LAUNCH_OK("vq_gather");
   }
   return GPEMSR_OK;
 }
