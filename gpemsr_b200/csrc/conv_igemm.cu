@@ -79,14 +79,14 @@ struct EpiConv {
     bool init = false, valid = false;
     int img = 0, y = 0, x = 0;
     float row_bias = 0.f;
+    long long orow = 0;        // output row of (up*y + py, up*x + px) in the blocked outputs
+    long long nchw0 = 0;       // offset of (img, channel 0, Y, X) in out_nchw
   };
 
-  // one cell = 8 consecutive output channels of one output pixel
-  __device__ __forceinline__ void store_cell(const State& st, float (&v)[8], int col0, int dy, int dx) const {
-    const int Y = up * st.y + py + dy, X = up * st.x + px + dx;
-    const int ch0 = c_off + col0;
+  // one cell = 8 consecutive output channels of one output pixel; (dy, dx) only differ from 0 under PixelShuffle
+  __device__ __forceinline__ void store_cell(const State& st, float (&v)[8], int ch0, int dy, int dx) const {
     if (out_f32 || out_hi || residual) {
-      const long long orow = place_row(og, st.img, Y, X);
+      const long long orow = st.orow + (long long)dy * (og.padded ? og.w + 2 : og.w) + dx;
       const size_t cell = ((size_t)(ch0 >> 3) * og.rows_alloc + orow) * 8;
       if (residual) {
         const float4 r0 = *reinterpret_cast<const float4*>(residual + cell), r1 = *reinterpret_cast<const float4*>(residual + cell + 4);
@@ -104,22 +104,44 @@ struct EpiConv {
       }
     }
     if (out_nchw) {
-      const long long Ho = (long long)up * ag.h, Wo = (long long)up * ag.w;
+      const long long Wo = (long long)up * ag.w, plane = (long long)up * ag.h * Wo;
+      float* p = out_nchw + st.nchw0 + (long long)ch0 * plane + (long long)dy * Wo + dx;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (ch0 + j < nchw_c) out_nchw[(((long long)st.img * nchw_c + ch0 + j) * Ho + Y) * Wo + X] = v[j];
+        if (ch0 + j < nchw_c) p[(long long)j * plane] = v[j];
     }
   }
 
   template <int CHUNK>
   __device__ __forceinline__ void chunk(const State& st, const uint32_t (&r)[CHUNK], int col0, long long rel) const {
     float f[CHUNK];
+    const bool full = col0 + CHUNK <= n_cols;
+    // v = scale * acc + bias  (flag tests are hoisted out of the column loops: they are uniform for the launch)
+    if (bias_per_row) {
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) {
-      const int col = col0 + j;
-      float v = scale * __uint_as_float(r[j]);
-      v += bias_per_row ? st.row_bias : ((bias && col < n_cols) ? __ldg(bias + col) : 0.f);
-      f[j] = col < n_cols ? apply_act(v, act, slope) : 0.f;
+      for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), st.row_bias);
+    } else if (bias && full) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+        f[j] = fmaf(scale, __uint_as_float(r[j]), b4.x); f[j + 1] = fmaf(scale, __uint_as_float(r[j + 1]), b4.y);
+        f[j + 2] = fmaf(scale, __uint_as_float(r[j + 2]), b4.z); f[j + 3] = fmaf(scale, __uint_as_float(r[j + 3]), b4.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j)
+        f[j] = fmaf(scale, __uint_as_float(r[j]), (bias && col0 + j < n_cols) ? __ldg(bias + col0 + j) : 0.f);
+    }
+    if (act == GPEMSR_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) f[j] = fmaxf(f[j], 0.f);
+    } else if (act == GPEMSR_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
+    }
+    if (!full) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) if (col0 + j >= n_cols) f[j] = 0.f;
     }
     if (out_rowmajor) {
 #pragma unroll
@@ -134,7 +156,7 @@ struct EpiConv {
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = f[4 * j + sub];
-          store_cell(st, v, col0 >> 2, sub >> 1, sub & 1);
+          store_cell(st, v, c_off + (col0 >> 2), sub >> 1, sub & 1);
         }
       }
     } else {
@@ -144,7 +166,7 @@ struct EpiConv {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = f[8 * g + j];
-        store_cell(st, v, col0 + 8 * g, 0, 0);
+        store_cell(st, v, c_off + col0 + 8 * g, 0, 0);
       }
     }
   }
@@ -154,7 +176,13 @@ struct EpiConv {
     if (!st.init) {
       st.init = true;
       st.valid = decode_row(ag, rel, st.img, st.y, st.x);
-      if (bias_per_row && st.valid) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
+      if (st.valid) {
+        if (bias_per_row) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
+        const int Y = up * st.y + py, X = up * st.x + px;
+        st.orow = place_row(og, st.img, Y, X);
+        const long long Wo = (long long)up * ag.w, Ho = (long long)up * ag.h;
+        st.nchw0 = ((long long)st.img * nchw_c * Ho + Y) * Wo + X;
+      }
     }
     constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
     constexpr int SPAN = BLOCK_N / (WARPS / 4);          // columns this warp covers

@@ -47,7 +47,7 @@ struct Workspace {
   uint32_t* cand_cnt;     // [rows_pad][2] appended candidates per (row, column half), OVERFLOW when > CSUB
   uint2* cand;            // [rows_pad][CMAX] (code, approx score), ascending code order
   float* runmin;          // [rows_pad][2] approximate minimum over each column half
-  float* emax;            // [1] max_k |e_k|_2   (as float bits, written with atomicMax)
+  float* emax;            // [2] max_k |e_k|_2 and max_k |e_k - bf16(e_k)|_2 (float bits, written with atomicMax)
   int* err;               // [1] GEMM pipeline error flag
   size_t bytes;
 };
@@ -66,7 +66,7 @@ Workspace carve(void* base, long long rows, int d, int k) {
   w.cand_cnt = (uint32_t*)take((size_t)rows_pad * 2 * 4);
   w.cand = (uint2*)take((size_t)rows_pad * CMAX * 8);
   w.runmin = (float*)take((size_t)rows_pad * 2 * 4);
-  w.emax = (float*)take(4);
+  w.emax = (float*)take(8);
   w.err = (int*)take(4);
   w.bytes = (size_t)(p - (uintptr_t)base);
   return w;
@@ -79,7 +79,7 @@ __global__ void vq_prep_codes(const float* __restrict__ e, const float* __restri
   const int code = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (code >= k_pad) return;
-  float ss = 0.f;
+  float ss = 0.f, sd = 0.f;                 // |e_k|^2 and |e_k - bf16(e_k)|^2
   for (int kc = lane; kc < d_pad / 8; kc += 32) {
     uint32_t h[4];
 #pragma unroll
@@ -89,6 +89,9 @@ __global__ void vq_prep_codes(const float* __restrict__ e, const float* __restri
       const float v1 = (code < k && d0 + 1 < d) ? e[(size_t)code * d + d0 + 1] : 0.f;
       ss = fmaf(v0, v0, ss);
       ss = fmaf(v1, v1, ss);
+      const float r0 = v0 - sm100::bf16_round(v0), r1 = v1 - sm100::bf16_round(v1);
+      sd = fmaf(r0, r0, sd);
+      sd = fmaf(r1, r1, sd);
       h[j] = sm100::pack_bf16x2(v0, v1);
     }
     // tiled layout [code tile][k-chunk of 64][k-cell][256 codes][8]: every GEMM stage is one contiguous 32 KB copy
@@ -96,17 +99,23 @@ __global__ void vq_prep_codes(const float* __restrict__ e, const float* __restri
     *reinterpret_cast<uint4*>(b + cell * 8) = make_uint4(h[0], h[1], h[2], h[3]);
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
   if (lane == 0) {
     c[code] = (code >= k) ? INFINITY : (mode == 0 ? ss : -bias[code]);
-    if (code < k) atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(ss)));   // non-negative floats order like ints
+    if (code < k) {                                     // non-negative floats order like ints
+      atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(ss) * 1.0000002f));
+      atomicMax(reinterpret_cast<int*>(emax) + 1, __float_as_int(sqrtf(sd) * 1.0000002f));
+    }
   }
 }
 
 // rows: one thread per row; consecutive threads <-> consecutive hw, so the NCHW reads (stride hw between the 8 values of
 // a cell) and the blocked 16-byte cell writes are both coalesced.  One pass over z produces the bf16 operand, |z|^2 and
-//   margin = |alpha| * 2 * 1.25 * (2^-8 + 2^-18) * |z| * max|e|     (two scores, each off by at most the bound; x1.25 for
-//            the tensor core's own accumulation rounding)  +  2^-20 * (|z|^2 + max|e|^2 + 1)  (fp32 quantisation of the
+// the candidate margin.  With dz = z - bf16(z), de_k = e_k - bf16(e_k) the approximate score of code k is off by
+//   |alpha| |z.e_k - bf16(z).bf16(e_k)| = |alpha| |dz.e_k + bf16(z).de_k| <= |alpha| (|dz| |e_k| + |bf16(z)| |de_k|)
+// (Cauchy-Schwarz; |dz| is measured, not bounded by 2^-9 |z|, which tightens the margin ~1.7x on typical data), so
+//   margin = 2 * 1.05 * |alpha| * (|dz| max|e| + |z| (1 + 2^-8) max|de|)   (two scores; x1.05 covers the tensor core's
+//            fp32 accumulation, <= 512 * 2^-23 relative)  +  2^-20 * (|z|^2 + max|e|^2 + 1)  (fp32 quantisation of the
 //            reference's own (|z|^2 + |e|^2) - 2 z.e and summation-order noise)
 __global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long long hw, int d, int d_pad, long long rows_pad,
                              float alpha_abs, const float* __restrict__ emax, __nv_bfloat16* __restrict__ a,
@@ -116,7 +125,7 @@ __global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long l
   const bool live = r < rows;
   const long long bi = live ? r / hw : 0, p = live ? r % hw : 0;
   const float* src = z + bi * d * hw + p;
-  float s = 0.f;
+  float s = 0.f, sdz = 0.f;
   for (int kc = 0; kc < d_pad / 8; ++kc) {
     float v[8];
 #pragma unroll
@@ -125,15 +134,20 @@ __global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long l
       v[j] = (live && dd < d) ? __ldg(src + (long long)dd * hw) : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s = fmaf(v[j], v[j], s);
+    for (int j = 0; j < 8; ++j) {
+      s = fmaf(v[j], v[j], s);
+      const float rj = v[j] - sm100::bf16_round(v[j]);
+      sdz = fmaf(rj, rj, sdz);
+    }
     *reinterpret_cast<uint4*>(a + ((size_t)kc * rows_pad + r) * 8) =
         make_uint4(sm100::pack_bf16x2(v[0], v[1]), sm100::pack_bf16x2(v[2], v[3]), sm100::pack_bf16x2(v[4], v[5]),
                    sm100::pack_bf16x2(v[6], v[7]));
   }
   if (live) {
     zz[r] = s;
-    const float em = *emax;
-    margin[r] = alpha_abs * 2.0f * 1.25f * (0x1p-8f + 0x1p-18f) * sqrtf(s) * em + 0x1p-20f * (s + em * em + 1.0f);
+    const float em = emax[0], dem = emax[1];
+    const float bound = sqrtf(sdz) * 1.0000002f * em + sqrtf(s) * (1.0f + 0x1p-8f) * dem;
+    margin[r] = alpha_abs * 2.0f * 1.05f * bound + 0x1p-20f * (s + em * em + 1.0f);
   }
 }
 
@@ -232,7 +246,7 @@ struct EpiArgExtremum {
 // vq_rescore: a block owns FIN_ROWS consecutive rows of one image (consecutive hw) and decides their indices.
 //   mode 0 (Codebook.forward):  d_k = (|z|^2 + |e_k|^2) - 2 * dot_k, minimise, lowest index on ties
 //   mode 1 (inference_lr):      l_k = dot_k + bias_k, maximise, lowest index on ties
-// (0) warp 0 filters each row's candidate sub-lists against the row's final minimum; rows with one survivor are decided,
+// (0) the warps filter each row's candidate sub-lists (one coalesced read per row) against the row's final minimum; rows with one survivor are decided,
 // the others contribute (row, code) pairs to a block-wide work list (blocks without pairs exit without touching z);
 // (1) the fp32 z tile is staged transposed through shared memory in 128-channel chunks (coalesced reads along hw) and
 // warps take pairs round-robin, one coalesced fp32 partial dot product per (pair, chunk), so the load is balanced
@@ -265,55 +279,74 @@ vq_rescore(const float* __restrict__ z, const float* __restrict__ w, long long h
   const int nrows = (int)min((long long)FIN_ROWS, hw - p0);
   const long long row0 = bi * hw + p0;
 
-  if (warp == 0) {
-    int nsurv = 0, over = 0;
-    uint32_t mine[CMAX];
-    if (lane < nrows) {
-      const long long gr = row0 + lane;
+  // ---- step 0: every warp filters two rows; a row's two 16-entry sub-lists are one coalesced 256-byte read
+  static_assert(CSUB == 16, "one candidate entry per lane");
+  __shared__ uint16_t s_tmp[FIN_ROWS][2 * CSUB];
+  __shared__ int s_cnt[FIN_ROWS];
+  __shared__ unsigned s_overmask;
+  if (threadIdx.x == 0) s_overmask = 0;
+  __syncthreads();
+  for (int r = warp; r < FIN_ROWS; r += NW) {
+    int cnt = 0;
+    if (r < nrows) {
+      const long long gr = row0 + r;
       const uint32_t n0 = cand_cnt[gr * 2], n1 = cand_cnt[gr * 2 + 1];
       if (n0 == OVERFLOW || n1 == OVERFLOW) {
-        over = 1;
+        if (lane == 0) atomicOr(&s_overmask, 1u << r);
       } else {
         const float thr = fminf(runmin[gr * 2], runmin[gr * 2 + 1]) + margin[gr];
-        for (int part = 0; part < 2; ++part) {
-          const uint2* cl = cand + ((size_t)gr * 2 + part) * CSUB;
-          const uint32_t n = part ? n1 : n0;
-          for (uint32_t i = 0; i < n; ++i) {
-            const uint2 e = cl[i];
-            if (__uint_as_float(e.y) <= thr) mine[nsurv++] = e.x;
-          }
+        const uint2 e = cand[(size_t)gr * 2 * CSUB + lane];
+        const bool keep = (uint32_t)(lane & (CSUB - 1)) < (lane < CSUB ? n0 : n1) && __uint_as_float(e.y) <= thr;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        cnt = __popc(m);
+        if (keep) s_tmp[r][__popc(m & ((1u << lane) - 1))] = (uint16_t)e.x;
+        if (cnt <= 1) {                                                   // decided (0 survivors only for NaN rows)
+          const int only = __shfl_sync(0xffffffffu, (int)e.x, m ? __ffs(m) - 1 : 0);
+          if (lane == 0) s_idx[r] = cnt ? only : 0;
         }
-        if (nsurv <= 1) s_idx[lane] = nsurv ? (int)mine[0] : 0;        // decided (0 survivors only for NaN rows)
       }
     }
-    const int np = nsurv >= 2 ? nsurv : 0;
+    if (lane == 0) s_cnt[r] = cnt >= 2 ? cnt : 0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int np = s_cnt[lane];
     int incl = np;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int first = incl - np;
-    s_first[lane] = first;
+    s_first[lane] = incl - np;
     if (lane == 31) { s_first[32] = incl; s_npairs = incl; }
-    for (int i = 0; i < np; ++i) s_pair[first + i] = ((uint32_t)lane << 16) | mine[i];
-    const unsigned om = __ballot_sync(0xffffffffu, over);
-    if (over) s_over[__popc(om & ((1u << lane) - 1))] = lane;
+    const unsigned om = s_overmask;
+    if ((om >> lane) & 1u) s_over[__popc(om & ((1u << lane) - 1))] = lane;
     if (lane == 0) s_nover = __popc(om);
+  }
+  __syncthreads();
+  for (int r = warp; r < FIN_ROWS; r += NW) {
+    const int np = s_cnt[r], f = s_first[r];
+    if (lane < np) s_pair[f + lane] = ((uint32_t)r << 16) | s_tmp[r][lane];
   }
   __syncthreads();
   const int npairs = s_npairs, nover = s_nover;
 
   if (npairs > 0) {
     const float* zb = z + bi * d * hw + p0 + (lane < nrows ? lane : 0);
+    constexpr int PER = FIN_DCH / NW;
+    float v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { const int dd = warp + u * NW; v[u] = dd < d ? __ldg(zb + (long long)dd * hw) : 0.f; }
     for (int d0 = 0; d0 < d; d0 += FIN_DCH) {
       const int dn = min(FIN_DCH, d - d0);
-      // stage z[d0 .. d0+dn) x 32 rows, transposed: 8 independent 128-byte loads in flight per warp
-      {
-        float v[FIN_DCH / NW];
+      // stage z[d0 .. d0+dn) x 32 rows, transposed; the NEXT chunk's loads are issued before the dot products below
 #pragma unroll
-        for (int u = 0; u < FIN_DCH / NW; ++u) { const int dd = warp + u * NW; v[u] = dd < dn ? __ldg(zb + (long long)(d0 + dd) * hw) : 0.f; }
-#pragma unroll
-        for (int u = 0; u < FIN_DCH / NW; ++u) zt[(warp + u * NW) * LD + lane] = v[u];
-      }
+      for (int u = 0; u < PER; ++u) zt[(warp + u * NW) * LD + lane] = v[u];
       __syncthreads();
+      if (d0 + FIN_DCH < d) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int dd = d0 + FIN_DCH + warp + u * NW;
+          v[u] = dd < d ? __ldg(zb + (long long)dd * hw) : 0.f;
+        }
+      }
       for (int p = warp; p < npairs; p += NW) {
         const uint32_t pr = s_pair[p];
         const int r = (int)(pr >> 16), kk = (int)(pr & 0xFFFFu);
