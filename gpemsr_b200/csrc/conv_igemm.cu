@@ -66,7 +66,7 @@ struct EpiConv {
   int bias_per_row, act;
   float slope;
   const float* residual;
-  int up, py, px, pixel_shuffle, c_off;
+  int up, py, px, pixel_shuffle, phase_cols, c_off;
   float* out_f32;
   __nv_bfloat16 *out_hi, *out_lo;
   float* out_nchw;
@@ -159,6 +159,15 @@ struct EpiConv {
           store_cell(st, v, c_off + (col0 >> 2), sub >> 1, sub & 1);
         }
       }
+    } else if (phase_cols) {             // the four parity phases of a ConvTranspose2d side by side along the columns
+      const int ph = col0 / phase_cols, ch = col0 - ph * phase_cols;
+#pragma unroll
+      for (int g = 0; g < CHUNK / 8; ++g) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = f[8 * g + j];
+        store_cell(st, v, c_off + ch + 8 * g, ph >> 1, ph & 1);
+      }
     } else {
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
@@ -205,7 +214,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
-  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.c_off = d.c_off;
+  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.phase_cols = d.phase_cols; e.c_off = d.c_off;
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   const int sms = gpemsr::num_sms();
@@ -234,7 +243,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
-  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.c_off = d.c_off;
+  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.phase_cols = d.phase_cols; e.c_off = d.c_off;
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
@@ -553,6 +562,8 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || (!d.b_lo && !d.b_packed)))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
   if (d.up != 1 && d.up != 2) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: up must be 1 or 2");
   if (d.pixel_shuffle && (d.up != 2 || d.n_cols % 32)) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: pixel_shuffle needs up=2 and n_cols %% 32 == 0");
+  if (d.phase_cols && (d.up != 2 || d.phase_cols % 32 || d.n_cols != 4 * d.phase_cols || d.pixel_shuffle))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: phase_cols needs up=2, phase_cols %% 32 == 0 and n_cols == 4 * phase_cols");
   if (d.c_off % 8) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: c_off must be a multiple of 8");
   if (d.out_rowmajor && (d.ld % 4)) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: ld must be a multiple of 4");
   if (!d.err_flag) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: err_flag is required");

@@ -143,6 +143,15 @@ class Decoder(nn.Module):
         og = G.Geom(g.n, 2 * g.h, 2 * g.w, True)
         cout = ub.upblock.weight.shape[1]
         y = P.act(name + '.out', og, cout, f32=need_f32)
+        if cout % 32 == 0 and cout <= 64:
+            # narrow up-blocks are bound by memory traffic: run the four phases as ONE GEMM with 4*cout columns
+            wt = P.wts.get(name + '.merged')
+            if wt is None:
+                wt = G.Weights(G.convT_merged_weight(ub.upblock.weight.detach()), 'conv', taps='offsets01', split=P.split)
+                wt.bias4 = ub.upblock.bias.detach().repeat(4).contiguous()
+                P.wts[name + '.merged'] = wt
+            G.igemm(x, wt, P.err, split=P.split, bias=wt.bias4, out=y, up=2, phase_cols=cout, out_f32=need_f32)
+            return y
         for py in (0, 1):
             for px in (0, 1):
                 wt = P.weights(f'{name}.p{py}{px}', ub.upblock.weight, 'convT', taps=G.convT_phase_taps(py, px))

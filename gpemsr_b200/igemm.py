@@ -28,7 +28,8 @@ class IgemmDesc(C.Structure):
                 ('scale', C.c_float), ('bias', C.c_void_p), ('bias_per_row', C.c_int32), ('act', C.c_int32),
                 ('slope', C.c_float), ('residual', C.c_void_p),
                 ('o_geom', GeomC),
-                ('up', C.c_int32), ('py', C.c_int32), ('px', C.c_int32), ('pixel_shuffle', C.c_int32), ('c_off', C.c_int32),
+                ('up', C.c_int32), ('py', C.c_int32), ('px', C.c_int32), ('pixel_shuffle', C.c_int32), ('phase_cols', C.c_int32),
+                ('c_off', C.c_int32),
                 ('out_f32', C.c_void_p), ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
                 ('out_nchw', C.c_void_p), ('nchw_c', C.c_int32),
                 ('out_rowmajor', C.c_void_p), ('ld', C.c_int64),
@@ -89,6 +90,8 @@ class Weights:
             n, k, n_stride, k_stride = co, ci, ci * kh * kw, kh * kw
             if taps is None:
                 taps = [(ky * kw + kx, ky - kh // 2, kx - kw // 2) for ky in range(kh) for kx in range(kw)]
+            elif taps == 'offsets01':          # kernel index == input offset (merged ConvTranspose phases)
+                taps = [(ky * kw + kx, ky, kx) for ky in range(kh) for kx in range(kw)]
         elif kind == 'convT':
             ci, co, kh, kw = w.shape
             n, k, n_stride, k_stride = co, ci, kh * kw, co * kh * kw
@@ -137,12 +140,27 @@ def convT_phase_taps(py, px):
     return [(ky * 3 + kx, dy, dx) for ky, dy in ks[py] for kx, dx in ks[px]]
 
 
+def convT_merged_weight(w):
+    """ConvTranspose2d(k3, s2, p1, op1) weight [ci, co, 3, 3] -> dense [4*co, ci, 2, 2]: the four output-parity phases side
+    by side along the output channels, over the union of their taps (input offsets (dy, dx) in {0,1}^2); taps a phase does
+    not use are zero.  Used where the layer is bound by memory traffic, not MMAs: one launch reads the input once and writes
+    whole output cells."""
+    ci, co = w.shape[0], w.shape[1]
+    m = torch.zeros(4 * co, ci, 2, 2, dtype=torch.float32, device=w.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            p = py * 2 + px
+            for src, dy, dx in convT_phase_taps(py, px):
+                m[p * co:(p + 1) * co, :, dy, dx] = w[:, :, src // 3, src % 3].t()
+    return m
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
 
 def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row=False, act=ACT_NONE, slope=0.0,
-          residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, c_off=0,
+          residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, phase_cols=0, c_off=0,
           out_f32=True, out_planes=True, out_nchw=None, nchw_c=0, out_rowmajor=None, ld=0,
           b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None):
     """One fused implicit-GEMM launch.  `a`: Act (A operand); `w`: Weights or None when b_* are given explicitly;
@@ -168,7 +186,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
     d.residual = _p(residual)
     og = o_geom or (out.geom if out is not None else (a_geom or a.geom))
     d.o_geom = og.c
-    d.up, d.py, d.px, d.pixel_shuffle, d.c_off = up, py, px, int(pixel_shuffle), c_off
+    d.up, d.py, d.px, d.pixel_shuffle, d.phase_cols, d.c_off = up, py, px, int(pixel_shuffle), phase_cols, c_off
     if out is not None:
         d.out_f32 = _p(out.f32) if out_f32 else None
         d.out_hi = _p(out.hi) if out_planes else None

@@ -134,6 +134,8 @@ typedef struct gpemsr_igemm_desc {
   int32_t up;                               /* 1: same resolution ; 2: output pixel (2y + py, 2x + px) */
   int32_t py, px;
   int32_t pixel_shuffle;                    /* 1: column c*4 + dy*2 + dx -> channel c at (2y + dy, 2x + dx) (up must be 2) */
+  int32_t phase_cols;                       /* > 0: parity phases merged along the columns: column p*phase_cols + c is channel c
+                                               of output pixel (2y + p/2, 2x + p%2) (up must be 2, phase_cols % 32 == 0) */
   int32_t c_off;                            /* first output channel (multiple of 8) inside the output tensors */
   float* out_f32;                           /* fp32 master [co_pad/8][o_geom.rows_alloc][8] or NULL */
   void* out_hi; void* out_lo;               /* bf16 planes or NULL */
