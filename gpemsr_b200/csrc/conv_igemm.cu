@@ -159,6 +159,19 @@ struct EpiConv {
           store_cell(st, v, c_off + (col0 >> 2), sub >> 1, sub & 1);
         }
       }
+    } else if (phase_cols && (phase_cols & 31)) {
+      // few channels per phase (the composed up-block + output conv: phase_cols = image channels): scalar NCHW scatter
+      if (out_nchw) {
+        const long long Wo = (long long)up * ag.w, plane = (long long)up * ag.h * Wo;
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          const int col = col0 + j;
+          if (col < n_cols) {
+            const int ph = col / phase_cols, ch = col - ph * phase_cols;
+            out_nchw[st.nchw0 + (long long)ch * plane + (long long)(ph >> 1) * Wo + (ph & 1)] = f[j];
+          }
+        }
+      }
     } else if (phase_cols) {             // the four parity phases of a ConvTranspose2d side by side along the columns
       const int ph = col0 / phase_cols, ch = col0 - ph * phase_cols;
 #pragma unroll
@@ -533,6 +546,39 @@ int pick_block_n(const gpemsr_igemm_desc_t& d) {
   return d.n_cols <= 16 && !d.pixel_shuffle ? 16 : d.n_cols <= 64 ? 64 : d.n_cols <= 128 ? 128 : 256;
 }
 
+// Exact evaluation of a 4-phase, 3x3-tap, position-class-dependent linear map on the one-pixel border ring of the 2x
+// output (the composed up-block + output conv has different weights where the output conv's zero padding cuts taps off).
+//   out[img, ch, 2a+py, 2b+px] = bias[cls][ch] + sum_ci sum_{dy,dx} x[ci, a+dy, b+dx] * wc[cls][ph][ch][ci][dy+1][dx+1]
+// cls = ry * 3 + rx with ry in {0: top row, 1: interior, 2: bottom row} of the OUTPUT, likewise rx.
+__global__ void border_phase_conv_kernel(const float* __restrict__ xf32, int cin, Geom g, const float* __restrict__ wc,
+                                         const float* __restrict__ bias, int cout, float* __restrict__ out) {
+  const int Ho = 2 * g.h, Wo = 2 * g.w;
+  const int per_img = 2 * Wo + 2 * (Ho - 2);                      // ring pixels of one output image
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)g.n * per_img * cout) return;
+  const int ch = (int)(t % cout);
+  const long long r = t / cout;
+  const int img = (int)(r / per_img);
+  int q = (int)(r % per_img), oy, ox;
+  if (q < Wo) { oy = 0; ox = q; }
+  else if (q < 2 * Wo) { oy = Ho - 1; ox = q - Wo; }
+  else { q -= 2 * Wo; oy = 1 + (q >> 1); ox = (q & 1) ? Wo - 1 : 0; }
+  const int ry = oy == 0 ? 0 : (oy == Ho - 1 ? 2 : 1), rx = ox == 0 ? 0 : (ox == Wo - 1 ? 2 : 1);
+  const int a = oy >> 1, b = ox >> 1, ph = (oy & 1) * 2 + (ox & 1);
+  const float* wp = wc + ((((size_t)(ry * 3 + rx) * 4 + ph) * cout + ch) * cin) * 9;
+  float acc = bias[(ry * 3 + rx) * cout + ch];
+  for (int ci = 0; ci < cin; ++ci) {
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const long long row = place_row(g, img, a + dy, b + dx);   // the zero ring supplies out-of-image inputs
+        acc = fmaf(xf32[((size_t)(ci >> 3) * g.rows_alloc + row) * 8 + (ci & 7)], __ldg(wp + ci * 9 + (dy + 1) * 3 + dx + 1), acc);
+      }
+  }
+  out[(((long long)img * cout + ch) * Ho + oy) * Wo + ox] = acc;
+}
+
 int check_geom(const gpemsr_geom_t& g, const char* what) {
   using namespace gpemsr;
   if (g.n <= 0 || g.h <= 0 || g.w <= 0 || g.r_img <= 0 || (g.r_img % gemm::BLOCK_M) != 0)
@@ -562,8 +608,10 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || (!d.b_lo && !d.b_packed)))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
   if (d.up != 1 && d.up != 2) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: up must be 1 or 2");
   if (d.pixel_shuffle && (d.up != 2 || d.n_cols % 32)) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: pixel_shuffle needs up=2 and n_cols %% 32 == 0");
-  if (d.phase_cols && (d.up != 2 || d.phase_cols % 32 || d.n_cols != 4 * d.phase_cols || d.pixel_shuffle))
-    return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: phase_cols needs up=2, phase_cols %% 32 == 0 and n_cols == 4 * phase_cols");
+  if (d.phase_cols && (d.up != 2 || d.n_cols != 4 * d.phase_cols || d.pixel_shuffle ||
+                       ((d.phase_cols % 32) && (d.out_f32 || d.out_hi || !d.out_nchw || d.n_cols > 16))))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: phase_cols needs up=2, n_cols == 4 * phase_cols and either phase_cols %% 32 == 0 "
+                     "or an NCHW-only output with n_cols <= 16");
   if (d.c_off % 8) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: c_off must be a multiple of 8");
   if (d.out_rowmajor && (d.ld % 4)) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: ld must be a multiple of 4");
   if (!d.err_flag) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: err_flag is required");
@@ -744,6 +792,20 @@ int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t
   dim3 grid((unsigned)((t_pad / 8 + 31) / 32), (unsigned)((t_pad + 31) / 32));
   softmax_write_kernel<<<grid, 1024, 0, st>>>(s, t, ld, t_pad, row_stats, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo);
   GPEMSR_LAUNCH_OK("softmax_write_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_border_phase_conv(const float* x_f32, int cin, const gpemsr_geom_t* g, const float* wc, const float* bias, int cout,
+                             float* out_nchw, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x_f32 || !g || !wc || !bias || !out_nchw || cin <= 0 || cout <= 0 || !g->padded)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "border_phase_conv: bad arguments");
+  if ((rc = check_geom(*g, "border_phase_conv")) != GPEMSR_OK) return rc;
+  const long long total = (long long)g->n * (4LL * g->w + 2 * (2LL * g->h - 2)) * cout;
+  border_phase_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x_f32, cin, to_geom(*g), wc, bias, cout, out_nchw);
+  GPEMSR_LAUNCH_OK("border_phase_conv_kernel");
   return GPEMSR_OK;
 }
 

@@ -86,9 +86,10 @@ class _Plan:
 class Decoder(nn.Module):
     """Drop-in for ``model.decoder.Decoder`` (same ``args`` dict)."""
 
-    def __init__(self, args, precision='fp32'):
+    def __init__(self, args, precision='fp32', compose_final=True):
         super().__init__()
         self.args = args
+        self.compose_final = compose_final
         self.channel_list = args['channel_list']
         self.num_res_blocks = args['num_resblock_per_scale']
         self.num_input_resblck = args['num_input_resblck']
@@ -217,6 +218,23 @@ class Decoder(nn.Module):
                 bias=nl.proj_out.bias.detach(), residual=x.f32, out=y)
         return y
 
+    def _final_stage(self, P, ub, x, img):
+        """Last UpBlock + output conv (model/decoder.py:31,33) composed into ONE 4-phase GEMM on the up-block's input
+        grid: the 64 x 16h x 16w intermediate (the largest tensor of the decoder, which the reference never returns) is not
+        materialised.  The one-pixel ring of the image, where the conv's zero padding changes the weights, is then
+        re-evaluated exactly with per-class weights."""
+        co = self.output_layer.out_channels
+        st = P.wts.get('final')
+        if st is None:
+            wc, bias = G.compose_upblock_conv(ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias)
+            dev = ub.upblock.weight.device
+            w_int = wc[4].reshape(4 * co, wc.shape[3], 3, 3).contiguous().to(dev)          # phase-major output channels
+            st = dict(wt=G.Weights(w_int, 'conv', split=P.split), b_int=bias[4].repeat(4).contiguous().to(dev),
+                      wc=wc.contiguous().to(dev), bias=bias.contiguous().to(dev))
+            P.wts['final'] = st
+        G.igemm(x, st['wt'], P.err, split=P.split, bias=st['b_int'], up=2, phase_cols=co, out_nchw=img, nchw_c=co)
+        G.border_phase_conv(x, st['wc'], st['bias'], co, img)
+
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def multi_scale_feat_calculate(self, x):                  # model/decoder.py:40-57
@@ -257,6 +275,12 @@ class Decoder(nn.Module):
                     feats.append(G.unpack_nchw(cur))
             else:
                 last = li == nlayers - 1
+                if last and self.compose_final and 4 * self.output_layer.out_channels <= 16:
+                    img = torch.empty(n, self.output_layer.out_channels, 2 * cur.geom.h, 2 * cur.geom.w, dtype=torch.float32,
+                                      device=x.device)
+                    self._final_stage(P, mod, cur, img)
+                    self._last_plan = P
+                    return feats, img
                 cur = self._up_block(P, name, mod, cur, need_f32=not last)
         img = torch.empty(n, self.output_layer.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
         wt = P.weights('output_layer', self.output_layer.weight, 'conv')

@@ -155,6 +155,51 @@ def convT_merged_weight(w):
     return m
 
 
+def compose_upblock_conv(wt, bu, wo, bo):
+    """Compose ConvTranspose2d(k3, s2, p1, op1) [weight wt: ci x c x 3 x 3, bias bu] with a following zero-padded 3x3
+    Conv2d [weight wo: co x c x 3 x 3, bias bo] (no non-linearity in between: model/decoder.py:31,33) into a 4-phase,
+    3x3-tap linear map on the INPUT grid:
+
+        out[co, 2a+py, 2b+px] = bias[cls][co] + sum_ci sum_{dy,dx in -1..1} x[ci, a+dy, b+dx] * wc[cls][py*2+px][co][ci][dy+1][dx+1]
+
+    `cls = ry*3 + rx` is the position class of the output pixel (0 first row/col, 1 interior, 2 last row/col): the conv's
+    zero padding removes the taps that fall outside the up-sampled image, so ring pixels have their own weights.
+    Derivation: the conv reads U at o + t (t in -1..1); U[P] = sum_k x[(P + 1 - k) / 2] * wt[k] over the k of matching
+    parity; with P = 2a + p + t this is x[a + d] for d = (p + t + 1 - k) / 2.  Done once per module in float64."""
+    wt64, wo64 = wt.detach().double().cpu(), wo.detach().double().cpu()
+    bu64, bo64 = bu.detach().double().cpu(), bo.detach().double().cpu()
+    ci, co = wt64.shape[0], wo64.shape[0]
+    wc = torch.zeros(9, 4, co, ci, 3, 3, dtype=torch.float64)
+    bias = torch.zeros(9, co, dtype=torch.float64)
+    valid = {0: (0, 1), 1: (-1, 0, 1), 2: (-1, 0)}           # taps t that stay inside, per position class
+    for ry in range(3):
+        for rx in range(3):
+            cls = ry * 3 + rx
+            bias[cls] = bo64
+            for ty in valid[ry]:
+                for tx in valid[rx]:
+                    wo_t = wo64[:, :, ty + 1, tx + 1]                      # co x c
+                    bias[cls] += wo_t @ bu64
+                    for py in range(2):
+                        for px in range(2):
+                            for ky in range(3):
+                                ny = py + ty + 1 - ky
+                                if ny % 2:
+                                    continue
+                                for kx in range(3):
+                                    nx = px + tx + 1 - kx
+                                    if nx % 2:
+                                        continue
+                                    wc[cls, py * 2 + px, :, :, ny // 2 + 1, nx // 2 + 1] += wo_t @ wt64[:, :, ky, kx].t()
+    return wc.float(), bias.float()
+
+
+def border_phase_conv(x, wc, bias, cout, out):
+    g = x.geom.c
+    _lib.check(_lib.lib().gpemsr_border_phase_conv(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(wc), _lib.ptr(bias), cout,
+                                                   _lib.ptr(out), _lib.stream_ptr()))
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 

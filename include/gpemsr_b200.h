@@ -185,6 +185,13 @@ GPEMSR_API int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t*
 GPEMSR_API int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t_pad, float* row_stats /* [t,2] */,
                                 void* p_hi, void* p_lo, gpemsr_stream_t stream);
 
+/* Border ring of a 2x-upsampling, 4-phase, 3x3-tap linear map whose weights depend on the output position class (top /
+ * interior / bottom) x (left / interior / right): wc [9][4][cout][cin][3][3], bias [9][cout].  Used by the decoder's final
+ * stage, where ConvTranspose2d (model/blocks.py:35) and the output conv (model/decoder.py:33) are composed into one
+ * GEMM and only the ring, where the conv's zero padding cuts taps off, needs these exact per-class weights. */
+GPEMSR_API int gpemsr_border_phase_conv(const float* x_f32, int cin, const gpemsr_geom_t* g, const float* wc,
+                             const float* bias, int cout, float* out_nchw, gpemsr_stream_t stream);
+
 /* out[i, 0, y, x] += bilinear_upsample(x_center, scale, align_corners=False)  (model/GPEMSR.py:452-455) */
 GPEMSR_API int gpemsr_add_bilinear_base(const float* x_center, int n, int h, int w, int scale, float* out,
                              gpemsr_stream_t stream);

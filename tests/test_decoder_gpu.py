@@ -83,6 +83,11 @@ def test_decoder_small_golden(golden, cuda_dev):
         assert e <= 1e-4 * max(1.0, m), (i, e, m)
     img = dec(T(g['x']).cuda())
     assert _err(img, g['feat4'])[0] <= 1e-4
+    # the un-composed final stage (separate UpBlock phases + output conv) must agree too
+    dec2 = gpemsr_b200.Decoder(cfg, compose_final=False).cuda()
+    dec2.load_state_dict(dec.state_dict(), strict=True)
+    assert _err(dec2(T(g['x']).cuda()), g['feat4'])[0] <= 1e-4
+    dec2.check()
 
 
 def test_decoder_reference_width_golden(golden, cuda_dev):

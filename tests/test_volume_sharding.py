@@ -45,3 +45,28 @@ def _worker(rank, world, port, n_units):
 def test_gather_two_ranks_gloo():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, 7), nprocs=2, join=True)
+
+
+def test_compose_upblock_conv_matches_torch():
+    """Host-side weight preprocessing: ConvTranspose2d(k3,s2,p1,op1) followed by a zero-padded 3x3 conv, composed into a
+    4-phase 3x3 map with per-border-class weights, equals the two-step evaluation (CPU, float64 reference)."""
+    import torch.nn.functional as F
+    from gpemsr_b200.igemm import compose_upblock_conv
+    torch.manual_seed(0)
+    ci, c, co = 5, 6, 2
+    wt, bu = torch.randn(ci, c, 3, 3, dtype=torch.float64), torch.randn(c, dtype=torch.float64)
+    wo, bo = torch.randn(co, c, 3, 3, dtype=torch.float64), torch.randn(co, dtype=torch.float64)
+    x = torch.randn(1, ci, 4, 5, dtype=torch.float64)
+    ref = F.conv2d(F.conv_transpose2d(x, wt, bu, 2, 1, 1), wo, bo, 1, 1)
+    wc, bias = compose_upblock_conv(wt, bu, wo, bo)
+    wc, bias = wc.double(), bias.double()
+    H, W = 4, 5
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for oy in range(2 * H):
+        for ox in range(2 * W):
+            ry = 0 if oy == 0 else (2 if oy == 2 * H - 1 else 1)
+            rx = 0 if ox == 0 else (2 if ox == 2 * W - 1 else 1)
+            a, b, ph = oy // 2, ox // 2, (oy & 1) * 2 + (ox & 1)
+            out[0, :, oy, ox] = bias[ry * 3 + rx] + torch.einsum('oikl,ikl->o', wc[ry * 3 + rx, ph], xp[0, :, a:a + 3, b:b + 3])
+    assert (out - ref).abs().max().item() < 1e-5
