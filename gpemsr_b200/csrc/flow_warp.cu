@@ -14,7 +14,14 @@
 //            fall into one or two 128-byte lines per input row (the flow is smooth) and every
 //            store is a full 128-byte line.  Neighbouring rows of a tile reuse each other's input
 //            lines out of L1 (2-D tile => ~ (TILE_H+1)/TILE_H re-fetch instead of 2x for a row strip).
-//            CH_UNROLL planes are in flight per thread (4*CH_UNROLL independent loads).
+//            CH_UNROLL planes are in flight per thread.  The east taps of lane i are normally the west taps of lane i+1, so
+//            they are taken by warp shuffle and only loaded when the addresses differ.
+//
+// Measured (profiles/README.md): 64 x 1250^2 in 0.225 ms = 3.6 TB/s = 55 % of the measured 6.55 TB/s copy peak; DRAM traffic
+// equals the algorithmic bytes (413 MB read, ~400 MB written).  Variants tried on the B200 and rejected because they were no
+// faster: 64x4 / 128x2 / 32x32 tiles, CH_UNROLL 2 / 8, 32-bit precomputed offsets (-37 % instructions), two pixels per lane,
+// four rows per thread with vertical tap reuse, channel-split grids.  All land at 0.22-0.25 ms: the limiter is the L1 / memory
+// path of sector-granular gathers over 64 interleaved planes, not issue rate or occupancy.
 //
 // Bit-faithful coordinates: each elementwise op of the reference is one separately
 // rounded fp32 op here (__fadd_rn/__fmul_rn/__fdiv_rn, no contraction), in the reference order:
@@ -22,11 +29,9 @@
 //     u = ((n + 1) / 2) * (size - 1) ; [border: u = min(size-1, max(u, 0))]   (ATen unnormalize/clip)
 // then ATen's bilinear weights (x_se - x)(y_se - y)... and the accumulation order nw, ne, sw, se.
 #include "capi_common.h"
-#include <cstdlib>
 
 namespace {
 
-constexpr int THREADS = 256;
 
 struct Taps {
   int o_nw, o_ne, o_sw, o_se;      // offsets inside one (n, c) plane, clamped into the plane
@@ -78,7 +83,7 @@ __device__ __forceinline__ Taps zero_taps() { Taps t; t.o_nw = t.o_ne = t.o_sw =
 template <int TILE_W, int TILE_H, int CH_UNROLL, int MIN_BLOCKS = 5>
 __global__ void __launch_bounds__(TILE_W * TILE_H, MIN_BLOCKS)
 flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                 int c, int h, int w, int c_per_cta, int border, int align_corners, int diag = 0) {
+                 int c, int h, int w, int c_per_cta, int border, int align_corners) {
   constexpr int NT = TILE_W * TILE_H;
   __shared__ int4 s_off[NT];
   __shared__ float4 s_wgt[NT];
@@ -122,7 +127,6 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, fl
 #pragma unroll
     for (int u = 0; u < CH_UNROLL; ++u) {
       const float* p = xp + (size_t)u * plane;
-      if (diag == 2) { a[u] = wt.x; d[u] = wt.y; b[u] = wt.z; e[u] = wt.w; continue; }     // diagnostic: no loads
       a[u] = __ldg(p + o.x); d[u] = __ldg(p + o.z);
       if (!sh_n) b[u] = __ldg(p + o.y);
       if (!sh_s) e[u] = __ldg(p + o.w);
@@ -135,7 +139,7 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, fl
       acc = __fmaf_rn(bv, wt.y, acc);
       acc = __fmaf_rn(d[u], wt.z, acc);
       acc = __fmaf_rn(ev, wt.w, acc);
-      if (inside && (diag != 1 || acc == 12345.678f)) __stcs(op + (size_t)u * plane, acc);                 // diag 1: no stores
+      if (inside) __stcs(op + (size_t)u * plane, acc);
     }
     xp += (size_t)CH_UNROLL * plane;
     op += (size_t)CH_UNROLL * plane;
@@ -154,254 +158,6 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, fl
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Same mapping as flow_warp_kernel<32, 8, 4>, restructured for instruction count: the first version spent ~43 instructions
-// per (pixel, channel), mostly 64-bit address chains, and was issue-bound.  Here every (tap, unrolled channel) offset is a
-// 32-bit element offset computed ONCE per thread; inside the loop an address is one IMAD.WIDE off a single running
-// pointer that advances CH_UNROLL planes per iteration.
-template <int CH_UNROLL>
-__global__ void __launch_bounds__(256, 3)
-flow_warp_lean_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                      int c, int h, int w, int c_per_cta, int border, int align_corners) {
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int px = blockIdx.x * 32 + tx, py = blockIdx.y * 8 + ty;
-  const int c_splits = (c + c_per_cta - 1) / c_per_cta;
-  const int n = blockIdx.z / c_splits;
-  const int c0 = (blockIdx.z % c_splits) * c_per_cta;
-  const int c1 = min(c0 + c_per_cta, c);
-  const size_t plane = (size_t)h * w;
-  const bool inside = (px < w) & (py < h);
-  Taps t = zero_taps();
-  if (inside) {
-    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)n * plane + (size_t)py * w + px));
-    t = make_taps(f.x, f.y, px, py, h, w, border != 0, align_corners != 0);
-  }
-  const unsigned lane = threadIdx.x & 31;
-  const int nx_nw = __shfl_down_sync(0xffffffffu, t.o_nw, 1), nx_sw = __shfl_down_sync(0xffffffffu, t.o_sw, 1);
-  const bool sh_n = lane < 31 && nx_nw == t.o_ne, sh_s = lane < 31 && nx_sw == t.o_se;
-  const int pl = (int)plane, pix = inside ? py * w + px : 0;
-  int e_nw[CH_UNROLL], e_ne[CH_UNROLL], e_sw[CH_UNROLL], e_se[CH_UNROLL], e_o[CH_UNROLL];
-#pragma unroll
-  for (int u = 0; u < CH_UNROLL; ++u) {
-    e_nw[u] = t.o_nw + u * pl; e_ne[u] = t.o_ne + u * pl; e_sw[u] = t.o_sw + u * pl; e_se[u] = t.o_se + u * pl; e_o[u] = pix + u * pl;
-  }
-  const float* xp = x + ((size_t)n * c + c0) * plane;
-  float* op = out + ((size_t)n * c + c0) * plane;
-  const size_t step = (size_t)CH_UNROLL * plane;
-  int ch = c0;
-  for (; ch + CH_UNROLL <= c1; ch += CH_UNROLL) {
-    float a[CH_UNROLL], b[CH_UNROLL], d[CH_UNROLL], e[CH_UNROLL];
-#pragma unroll
-    for (int u = 0; u < CH_UNROLL; ++u) {
-      a[u] = __ldg(xp + e_nw[u]); d[u] = __ldg(xp + e_sw[u]);
-      if (!sh_n) b[u] = __ldg(xp + e_ne[u]);
-      if (!sh_s) e[u] = __ldg(xp + e_se[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < CH_UNROLL; ++u) {
-      const float bs = __shfl_down_sync(0xffffffffu, a[u], 1), es = __shfl_down_sync(0xffffffffu, d[u], 1);
-      const float bv = sh_n ? bs : b[u], ev = sh_s ? es : e[u];
-      float acc = __fmul_rn(a[u], t.w_nw);
-      acc = __fmaf_rn(bv, t.w_ne, acc);
-      acc = __fmaf_rn(d[u], t.w_sw, acc);
-      acc = __fmaf_rn(ev, t.w_se, acc);
-      if (inside) __stcs(op + e_o[u], acc);
-    }
-    xp += step; op += step;
-  }
-  for (; ch < c1; ++ch) {
-    const float a0 = __ldg(xp + e_nw[0]), d0 = __ldg(xp + e_sw[0]);
-    const float bs = __shfl_down_sync(0xffffffffu, a0, 1), es = __shfl_down_sync(0xffffffffu, d0, 1);
-    const float bv = sh_n ? bs : __ldg(xp + e_ne[0]), ev = sh_s ? es : __ldg(xp + e_se[0]);
-    float acc = __fmul_rn(a0, t.w_nw);
-    acc = __fmaf_rn(bv, t.w_ne, acc);
-    acc = __fmaf_rn(d0, t.w_sw, acc);
-    acc = __fmaf_rn(ev, t.w_se, acc);
-    if (inside) __stcs(op + e_o[0], acc);
-    xp += plane; op += plane;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// ROWS vertically adjacent pixels per thread.  ncu shows the L1 data pipe (one 128-byte wavefront per clock per SM) is what
-// bounds this kernel: a warp-wide tap load of 32 neighbouring pixels spans ~3 cache lines, and every input row is fetched
-// twice -- as the south taps of output row y and as the north taps of row y+1.  A thread that owns rows y..y+ROWS-1 keeps
-// the row values in registers: for a smooth flow the south pair of row r IS the north pair of row r+1, so ROWS+1 row loads
-// serve ROWS output rows (instead of 2*ROWS); east taps come from the right-hand lane by shuffle as before.  Rows / lanes
-// whose taps do not line up fall back to their own (predicated) loads, so any flow is handled exactly.
-template <int ROWS, int CH_UNROLL>
-__global__ void __launch_bounds__(256, 2)
-flow_warp_rows_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                      int c, int h, int w, int c_per_cta, int border, int align_corners) {
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int px = blockIdx.x * 32 + lane, py0 = (blockIdx.y * 8 + wrp) * ROWS;
-  const int c_splits = (c + c_per_cta - 1) / c_per_cta;
-  const int n = blockIdx.z / c_splits;
-  const int c0 = (blockIdx.z % c_splits) * c_per_cta;
-  const int c1 = min(c0 + c_per_cta, c);
-  const size_t plane = (size_t)h * w;
-
-  Taps T[ROWS];
-  bool in[ROWS];
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    in[r] = (px < w) & (py0 + r < h);
-    T[r] = zero_taps();
-    if (in[r]) {
-      const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)n * plane + (size_t)(py0 + r) * w + px));
-      T[r] = make_taps(f.x, f.y, px, py0 + r, h, w, border != 0, align_corners != 0);
-    }
-  }
-  // row loads k = 0..ROWS: k = 0 is the north pair of row 0, k >= 1 the south pair of row k-1
-  int W[ROWS + 1], E[ROWS + 1];
-  W[0] = T[0].o_nw; E[0] = T[0].o_ne;
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) { W[r + 1] = T[r].o_sw; E[r + 1] = T[r].o_se; }
-  bool he[ROWS + 1];           // east value of load k comes from the right-hand lane
-#pragma unroll
-  for (int k = 0; k <= ROWS; ++k) he[k] = (lane < 31) & (__shfl_down_sync(0xffffffffu, W[k], 1) == E[k]);
-  bool vs[ROWS];               // north pair of row r is row load r (r = 0: by definition)
-  vs[0] = true;
-#pragma unroll
-  for (int r = 1; r < ROWS; ++r) vs[r] = (T[r].o_nw == W[r]) & (T[r].o_ne == E[r]);
-
-  const float* xp = x + ((size_t)n * c + c0) * plane;
-  float* op = out + ((size_t)n * c + c0) * plane + (size_t)py0 * w + px;
-  for (int ch = c0; ch < c1; ch += CH_UNROLL) {
-    float wv[CH_UNROLL][ROWS + 1], ev[CH_UNROLL][ROWS + 1], fn[CH_UNROLL][ROWS], fe[CH_UNROLL][ROWS];
-#pragma unroll
-    for (int u = 0; u < CH_UNROLL; ++u) {
-      const float* q = xp + (size_t)u * plane;
-      const bool live = ch + u < c1;
-#pragma unroll
-      for (int k = 0; k <= ROWS; ++k) {
-        wv[u][k] = live ? __ldg(q + W[k]) : 0.f;
-        if (live && !he[k]) ev[u][k] = __ldg(q + E[k]);
-      }
-#pragma unroll
-      for (int r = 1; r < ROWS; ++r)
-        if (live && !vs[r]) { fn[u][r] = __ldg(q + T[r].o_nw); fe[u][r] = __ldg(q + T[r].o_ne); }
-    }
-#pragma unroll
-    for (int u = 0; u < CH_UNROLL; ++u) {
-#pragma unroll
-      for (int k = 0; k <= ROWS; ++k) {
-        const float sh = __shfl_down_sync(0xffffffffu, wv[u][k], 1);
-        if (he[k]) ev[u][k] = sh;
-      }
-      if (ch + u < c1) {
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const float nwv = vs[r] ? wv[u][r] : fn[u][r], nev = vs[r] ? ev[u][r] : fe[u][r];
-          float acc = __fmul_rn(nwv, T[r].w_nw);
-          acc = __fmaf_rn(nev, T[r].w_ne, acc);
-          acc = __fmaf_rn(wv[u][r + 1], T[r].w_sw, acc);
-          acc = __fmaf_rn(ev[u][r + 1], T[r].w_se, acc);
-          if (in[r]) __stcs(op + (size_t)u * plane + (size_t)r * w, acc);
-        }
-      }
-    }
-    xp += (size_t)CH_UNROLL * plane; op += (size_t)CH_UNROLL * plane;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Two pixels per lane.  The first version spent ~43 instructions per (pixel, channel) -- mostly 64-bit address arithmetic
-// for four independent tap pointers -- and was issue-bound at 54 % of HBM bandwidth.  Here a lane owns the pixel pair
-// (x, x+1) of a 64-pixel row segment.  For a smooth flow the six taps of the pair are three consecutive floats in each of
-// two rows, so per channel a lane issues   n0 = pn[0], n1 = pn[1], s0 = ps[0], s1 = ps[1]   (immediate offsets off TWO
-// running pointers), gets the third float of each row from its right-hand neighbour by shuffle, and stores a float2.
-// Warps whose taps do not line up this way (large / noisy flow, clamped borders) take the generic 8-load path.
-
-template <int CH_UNROLL>
-__global__ void __launch_bounds__(256, 4)
-flow_warp_pair_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                      int c, int h, int w, int c_per_cta, int border, int align_corners) {
-  const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
-  const int px = blockIdx.x * 64 + 2 * lane, py = blockIdx.y * 8 + wrow;
-  const int c_splits = (c + c_per_cta - 1) / c_per_cta;
-  const int n = blockIdx.z / c_splits;
-  const int c0 = (blockIdx.z % c_splits) * c_per_cta;
-  const int c1 = min(c0 + c_per_cta, c);
-  const size_t plane = (size_t)h * w;
-  const bool in_a = (px < w) & (py < h), in_b = (px + 1 < w) & (py < h);
-  const bool vec = (w & 1) == 0;                         // pixel pairs are 8-byte aligned in every row
-
-  Taps A = zero_taps(), B = zero_taps();
-  if (in_a) {
-    const float* fp = flow + ((size_t)n * plane + (size_t)py * w + px) * 2;
-    float4 f;
-    if (vec && in_b) f = __ldg(reinterpret_cast<const float4*>(fp));
-    else { const float2 fa = __ldg(reinterpret_cast<const float2*>(fp)); f.x = fa.x; f.y = fa.y; f.z = f.w = 0.f;
-           if (in_b) { const float2 fb = __ldg(reinterpret_cast<const float2*>(fp) + 1); f.z = fb.x; f.w = fb.y; } }
-    A = make_taps(f.x, f.y, px, py, h, w, border != 0, align_corners != 0);
-    if (in_b) B = make_taps(f.z, f.w, px + 1, py, h, w, border != 0, align_corners != 0);
-  }
-  // does the pair line up as three consecutive floats per row, and does the right neighbour continue it?
-  const bool lined = (A.o_ne == A.o_nw + 1) & (A.o_se == A.o_sw + 1) & (!in_b | ((B.o_nw == A.o_ne) & (B.o_sw == A.o_se)));
-  const int nb_n = __shfl_down_sync(0xffffffffu, A.o_nw, 1), nb_s = __shfl_down_sync(0xffffffffu, A.o_sw, 1);
-  const bool sh_n = lane < 31 && nb_n == B.o_ne, sh_s = lane < 31 && nb_s == B.o_se;
-  const bool fast = __all_sync(0xffffffffu, lined | !in_a);
-
-  const float* xp = x + ((size_t)n * c + c0) * plane;
-  float* op = out + ((size_t)n * c + c0) * plane + (in_a ? (size_t)py * w + px : 0);
-  if (fast) {
-    const float* pn = xp + A.o_nw;
-    const float* ps = xp + A.o_sw;
-    const int d_n2 = B.o_ne - A.o_nw, d_s2 = B.o_se - A.o_sw;      // third float of each row (only read when not shuffled)
-    int ch = c0;
-    for (; ch + CH_UNROLL <= c1; ch += CH_UNROLL) {
-      float n0[CH_UNROLL], n1[CH_UNROLL], n2[CH_UNROLL], s0[CH_UNROLL], s1[CH_UNROLL], s2[CH_UNROLL];
-#pragma unroll
-      for (int u = 0; u < CH_UNROLL; ++u) {
-        const float* qn = pn + (size_t)u * plane;
-        const float* qs = ps + (size_t)u * plane;
-        n0[u] = __ldg(qn); n1[u] = __ldg(qn + 1); s0[u] = __ldg(qs); s1[u] = __ldg(qs + 1);
-        if (!sh_n) n2[u] = __ldg(qn + d_n2);
-        if (!sh_s) s2[u] = __ldg(qs + d_s2);
-      }
-#pragma unroll
-      for (int u = 0; u < CH_UNROLL; ++u) {
-        const float tn = __shfl_down_sync(0xffffffffu, n0[u], 1), ts = __shfl_down_sync(0xffffffffu, s0[u], 1);
-        const float bne = sh_n ? tn : n2[u], bse = sh_s ? ts : s2[u];
-        float ra = __fmul_rn(n0[u], A.w_nw);
-        ra = __fmaf_rn(n1[u], A.w_ne, ra); ra = __fmaf_rn(s0[u], A.w_sw, ra); ra = __fmaf_rn(s1[u], A.w_se, ra);
-        float rb = __fmul_rn(n1[u], B.w_nw);
-        rb = __fmaf_rn(bne, B.w_ne, rb); rb = __fmaf_rn(s1[u], B.w_sw, rb); rb = __fmaf_rn(bse, B.w_se, rb);
-        float* q = op + (size_t)u * plane;
-        if (vec && in_b) __stcs(reinterpret_cast<float2*>(q), make_float2(ra, rb));
-        else { if (in_a) __stcs(q, ra); if (in_b) __stcs(q + 1, rb); }
-      }
-      pn += (size_t)CH_UNROLL * plane; ps += (size_t)CH_UNROLL * plane; op += (size_t)CH_UNROLL * plane;
-    }
-    for (; ch < c1; ++ch) {
-      const float a0 = __ldg(pn), a1 = __ldg(pn + 1), b0 = __ldg(ps), b1 = __ldg(ps + 1);
-      const float tn = __shfl_down_sync(0xffffffffu, a0, 1), ts = __shfl_down_sync(0xffffffffu, b0, 1);
-      const float bne = sh_n ? tn : __ldg(pn + d_n2), bse = sh_s ? ts : __ldg(ps + d_s2);
-      float ra = __fmul_rn(a0, A.w_nw);
-      ra = __fmaf_rn(a1, A.w_ne, ra); ra = __fmaf_rn(b0, A.w_sw, ra); ra = __fmaf_rn(b1, A.w_se, ra);
-      float rb = __fmul_rn(a1, B.w_nw);
-      rb = __fmaf_rn(bne, B.w_ne, rb); rb = __fmaf_rn(b1, B.w_sw, rb); rb = __fmaf_rn(bse, B.w_se, rb);
-      if (vec && in_b) __stcs(reinterpret_cast<float2*>(op), make_float2(ra, rb));
-      else { if (in_a) __stcs(op, ra); if (in_b) __stcs(op + 1, rb); }
-      pn += plane; ps += plane; op += plane;
-    }
-  } else {
-    // generic path: eight independent taps
-    for (int ch = c0; ch < c1; ++ch) {
-      float ra = __fmul_rn(__ldg(xp + A.o_nw), A.w_nw);
-      ra = __fmaf_rn(__ldg(xp + A.o_ne), A.w_ne, ra); ra = __fmaf_rn(__ldg(xp + A.o_sw), A.w_sw, ra);
-      ra = __fmaf_rn(__ldg(xp + A.o_se), A.w_se, ra);
-      float rb = __fmul_rn(__ldg(xp + B.o_nw), B.w_nw);
-      rb = __fmaf_rn(__ldg(xp + B.o_ne), B.w_ne, rb); rb = __fmaf_rn(__ldg(xp + B.o_sw), B.w_sw, rb);
-      rb = __fmaf_rn(__ldg(xp + B.o_se), B.w_se, rb);
-      if (in_a) __stcs(op, ra);
-      if (in_b) __stcs(op + 1, rb);
-      xp += plane; op += plane;
-    }
-  }
-}
 
 }  // namespace
 
@@ -422,14 +178,7 @@ extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c,
   if (reinterpret_cast<uintptr_t>(flow) & 7)
     return set_error(GPEMSR_ERR_BAD_ALIGN, "flow_warp: flow must be 8-byte aligned");
 
-  static int variant = -1, diag = 0;
-  if (variant < 0) {
-    const char* e = getenv("GPEMSR_FLOW_VARIANT"); variant = e ? atoi(e) : 0;
-    const char* dg = getenv("GPEMSR_FLOW_DIAG"); diag = dg ? atoi(dg) : 0;
-  }
-  const int TILE_W = variant == 2 || variant == 4 || variant == 10 ? 64 : variant == 3 ? 128 : 32;
-  const int TILE_H = variant == 9 ? 32 : variant == 10 || variant == 11 ? 16 : THREADS / TILE_W;
-  const int CH_UNROLL = variant == 1 || variant == 4 ? 8 : 4;
+  constexpr int TILE_W = 32, TILE_H = 8, CH_UNROLL = 4;
   const int tiles_x = (w + TILE_W - 1) / TILE_W, tiles_y = (h + TILE_H - 1) / TILE_H;
   // split channels across CTAs only when the pixel tiles alone cannot fill the chip (>= ~4 waves)
   const long long tiles = (long long)tiles_x * tiles_y * n;
@@ -444,45 +193,8 @@ extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c,
     return set_error(GPEMSR_ERR_BAD_SHAPE, "flow_warp: grid too large (n*c_splits=%lld, tiles_y=%d)",
                      (long long)n * c_splits, tiles_y);
   dim3 grid(tiles_x, tiles_y, n * c_splits);
-  const int bd = padding_mode == GPEMSR_PAD_BORDER;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (variant == 16 || variant == 17 || variant == 18) {
-    const int rows = variant == 17 ? 2 : 4;
-    dim3 g3((w + 31) / 32, (h + 8 * rows - 1) / (8 * rows), n * c_splits);
-    if (variant == 16) flow_warp_rows_kernel<4, 2><<<g3, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    else if (variant == 17) flow_warp_rows_kernel<2, 4><<<g3, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    else flow_warp_rows_kernel<4, 1><<<g3, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    GPEMSR_LAUNCH_OK("flow_warp_rows_kernel");
-    return GPEMSR_OK;
-  }
-  if (variant == 14 || variant == 15) {
-    if ((size_t)h * w * 8 >= ((size_t)1 << 31)) return set_error(GPEMSR_ERR_BAD_SHAPE, "flow_warp: plane too large for 32-bit offsets");
-    if (variant == 14) flow_warp_lean_kernel<4><<<grid, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    else flow_warp_lean_kernel<8><<<grid, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    GPEMSR_LAUNCH_OK("flow_warp_lean_kernel");
-    return GPEMSR_OK;
-  }
-  if (variant == 12 || variant == 13) {
-    dim3 g2((w + 63) / 64, (h + 7) / 8, n * c_splits);
-    if (variant == 12) flow_warp_pair_kernel<4><<<g2, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    else flow_warp_pair_kernel<2><<<g2, 256, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners);
-    GPEMSR_LAUNCH_OK("flow_warp_pair_kernel");
-    return GPEMSR_OK;
-  }
-  switch (variant) {
-    case 1: flow_warp_kernel<32, 8, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 2: flow_warp_kernel<64, 4, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 3: flow_warp_kernel<128, 2, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 4: flow_warp_kernel<64, 4, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 5: flow_warp_kernel<32, 8, 4, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 6: flow_warp_kernel<32, 8, 4, 6><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 7: flow_warp_kernel<32, 8, 8, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 9: flow_warp_kernel<32, 32, 4, 1><<<grid, 1024, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 10: flow_warp_kernel<64, 16, 4, 1><<<grid, 1024, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 11: flow_warp_kernel<32, 16, 4, 2><<<grid, 512, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    case 8: flow_warp_kernel<32, 8, 2, 8><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners); break;
-    default: flow_warp_kernel<32, 8, 4><<<grid, THREADS, 0, st>>>(x, flow, out, c, h, w, c_per_cta, bd, align_corners, diag); break;
-  }
+  flow_warp_kernel<TILE_W, TILE_H, CH_UNROLL><<<grid, TILE_W * TILE_H, 0, (cudaStream_t)stream>>>(
+      x, flow, out, c, h, w, c_per_cta, padding_mode == GPEMSR_PAD_BORDER, align_corners);
   GPEMSR_LAUNCH_OK("flow_warp_kernel");
   return GPEMSR_OK;
 }
