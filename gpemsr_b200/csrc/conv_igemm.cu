@@ -73,6 +73,8 @@ struct EpiConv {
   int nchw_c;
   float* out_rowmajor;
   long long ld;
+  double* gn_sums;
+  int gn_cpg;
 
   static constexpr int WARPS = BLOCK_N >= 64 ? 8 : 4;
   struct State {
@@ -112,6 +114,38 @@ struct EpiConv {
     }
   }
 
+  // fused GroupNorm statistics: per group of CPG channels, the sum and sum of squares of this warp's 32 rows
+  template <int CHUNK, int CPG>
+  __device__ __forceinline__ void group_stats_t(const State& st, const float (&f)[CHUNK], int col0) const {
+    const int lane = threadIdx.x & 31;
+    constexpr int G = CPG < CHUNK ? CPG : CHUNK;           // a 32-channel group spans the whole 16-column chunk of N = 16 tiles
+#pragma unroll
+    for (int g0 = 0; g0 < CHUNK; g0 += G) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int j = 0; j < G; ++j) { s += f[g0 + j]; q = fmaf(f[g0 + j], f[g0 + j], q); }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+      const int col = col0 + g0;
+      if (lane == 0 && col < n_cols) {
+        double* dst = gn_sums + ((size_t)st.img * (n_cols / gn_cpg) + col / gn_cpg) * 2;
+        atomicAdd(dst, (double)s);
+        atomicAdd(dst + 1, (double)q);
+      }
+    }
+  }
+  template <int CHUNK>
+  __device__ __forceinline__ void group_stats(const State& st, const float (&f)[CHUNK], int col0) const {
+    switch (gn_cpg) {
+      case 1: group_stats_t<CHUNK, 1>(st, f, col0); break;
+      case 2: group_stats_t<CHUNK, 2>(st, f, col0); break;
+      case 4: group_stats_t<CHUNK, 4>(st, f, col0); break;
+      case 8: group_stats_t<CHUNK, 8>(st, f, col0); break;
+      case 16: group_stats_t<CHUNK, 16>(st, f, col0); break;
+      default: group_stats_t<CHUNK, 32>(st, f, col0); break;
+    }
+  }
+
   template <int CHUNK>
   __device__ __forceinline__ void chunk(const State& st, const uint32_t (&r)[CHUNK], int col0, long long rel) const {
     float f[CHUNK];
@@ -143,6 +177,14 @@ struct EpiConv {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (col0 + j >= n_cols) f[j] = 0.f;
     }
+    if (gn_sums) {                       // all 32 lanes take part; rows outside the image contribute zeros
+      if (!st.valid) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) f[j] = 0.f;
+      }
+      group_stats<CHUNK>(st, f, col0);
+    }
+    if (!st.valid) return;
     if (out_rowmajor) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 4)
@@ -215,7 +257,7 @@ struct EpiConv {
       else sm100::tmem_ld_32x16(tmem_acc + c0, r);
       sm100::tmem_ld_wait();
       const int col0 = n_tile * BLOCK_N + c0;
-      if (st.valid && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
+      if ((st.valid || gn_sums) && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
     }
   }
 };
@@ -230,6 +272,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.phase_cols = d.phase_cols; e.c_off = d.c_off;
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
+  e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   const int sms = gpemsr::num_sms();
   long long gx = std::min<long long>(op.m_tiles, sms);
   long long gy = 1;
@@ -259,6 +302,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.phase_cols = d.phase_cols; e.c_off = d.c_off;
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
+  e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
@@ -413,13 +457,18 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int c, Geom g, doub
   }
 }
 
-__global__ void gn_scale_shift_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      int n, int c, int groups, double count, float eps, float* __restrict__ ss) {
+__global__ void gn_scale_shift_kernel(const double* __restrict__ sums, int per_group, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int n, int c, int groups, double count, float eps,
+                                      float* __restrict__ ss) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * c) return;
   const int img = t / c, ch = t % c, cpg = c / groups, g0 = (ch / cpg) * cpg;
   double s = 0, q = 0;
-  for (int j = 0; j < cpg; ++j) { s += sums[((size_t)img * c + g0 + j) * 2]; q += sums[((size_t)img * c + g0 + j) * 2 + 1]; }
+  if (per_group) {
+    s = sums[((size_t)img * groups + ch / cpg) * 2]; q = sums[((size_t)img * groups + ch / cpg) * 2 + 1];
+  } else {
+    for (int j = 0; j < cpg; ++j) { s += sums[((size_t)img * c + g0 + j) * 2]; q += sums[((size_t)img * c + g0 + j) * 2 + 1]; }
+  }
   const double cnt = count * cpg, mean = s / cnt;
   double var = q / cnt - mean * mean;
   if (var < 0) var = 0;
@@ -432,7 +481,7 @@ __global__ void gn_scale_shift_kernel(const double* __restrict__ sums, const flo
 // y = act(x * scale + shift) (+ residual); re-rowed into `og` when it differs from `g`
 __global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, const float* __restrict__ ss, int act, float slope,
                                   const float* __restrict__ residual, Geom og, float* __restrict__ out_f32,
-                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_nchw) {
   const long long hw = (long long)g.h * g.w;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (img, cell, pixel)
   const int cells = (c + 7) / 8;
@@ -466,6 +515,13 @@ __global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, co
     split8(v, h, l);
     *reinterpret_cast<uint4*>(out_hi + ocell) = h;
     if (out_lo) *reinterpret_cast<uint4*>(out_lo + ocell) = l;
+  }
+  if (out_nchw) {                        // the reference-layout copy returned to the caller (lanes <-> consecutive pixels)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = cc * 8 + j;
+      if (ch < c) out_nchw[((long long)img * c + ch) * hw + p] = v[j];
+    }
   }
 }
 
@@ -615,6 +671,12 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (d.c_off % 8) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: c_off must be a multiple of 8");
   if (d.out_rowmajor && (d.ld % 4)) return set_error(GPEMSR_ERR_BAD_ALIGN, "igemm: ld must be a multiple of 4");
   if (!d.err_flag) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: err_flag is required");
+  if (d.gn_sums) {
+    const int g = d.gn_cpg;
+    if (!(g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) || d.n_cols % g || d.pixel_shuffle || d.phase_cols || d.up != 1)
+      return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: gn_sums needs gn_cpg in {1,2,4,8,16,32} dividing n_cols and a same-resolution output");
+    GPEMSR_CUDA_OK(cudaMemsetAsync(d.gn_sums, 0, (size_t)d.a_geom.n * (d.n_cols / g) * 2 * sizeof(double), (cudaStream_t)stream));
+  }
 
   const int block_n = pick_block_n(d);
   gemm::Operands op{};
@@ -750,14 +812,14 @@ int gpemsr_gn_stats(const float* x_f32, int c, const gpemsr_geom_t* g, double* c
   return GPEMSR_OK;
 }
 
-int gpemsr_gn_scale_shift(const double* chan_sums, const float* gamma, const float* beta, int n, int c, int groups,
-                          double count_per_channel, float eps, float* scale_shift, gpemsr_stream_t stream) {
+int gpemsr_gn_scale_shift(const double* chan_sums, int sums_per_group, const float* gamma, const float* beta, int n, int c,
+                          int groups, double count_per_channel, float eps, float* scale_shift, gpemsr_stream_t stream) {
   using namespace gpemsr;
   int rc = check_device_current();
   if (rc != GPEMSR_OK) return rc;
   if (!chan_sums || !gamma || !beta || !scale_shift || n <= 0 || c <= 0 || groups <= 0 || c % groups)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "gn_scale_shift: bad arguments (c=%d groups=%d)", c, groups);
-  gn_scale_shift_kernel<<<(n * c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chan_sums, gamma, beta, n, c, groups,
+  gn_scale_shift_kernel<<<(n * c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chan_sums, sums_per_group, gamma, beta, n, c, groups,
                                                                             count_per_channel, eps, scale_shift);
   GPEMSR_LAUNCH_OK("gn_scale_shift_kernel");
   return GPEMSR_OK;
@@ -765,7 +827,7 @@ int gpemsr_gn_scale_shift(const double* chan_sums, const float* gamma, const flo
 
 int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const float* scale_shift, int act, float slope,
                       const float* residual, const gpemsr_geom_t* og, float* out_f32, void* out_hi, void* out_lo,
-                      gpemsr_stream_t stream) {
+                      float* out_nchw, gpemsr_stream_t stream) {
   using namespace gpemsr;
   int rc = check_device_current();
   if (rc != GPEMSR_OK) return rc;
@@ -774,7 +836,8 @@ int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const f
   if (g->n != og->n || g->h != og->h || g->w != og->w) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: geometries differ in shape");
   const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
   affine_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x_f32, c, to_geom(*g), scale_shift, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+      x_f32, c, to_geom(*g), scale_shift, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+      out_nchw);
   GPEMSR_LAUNCH_OK("affine_act_kernel");
   return GPEMSR_OK;
 }

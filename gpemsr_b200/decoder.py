@@ -119,23 +119,30 @@ class Decoder(nn.Module):
         wt = P.weights(name, mod.weight, 'conv')
         G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), out=out, **kw)
 
-    def _res_block(self, P, name, rb, x):
+    def _res_block(self, P, name, rb, x, nchw_out=None):
         """x + ReLU(GN(conv(ReLU(GN(conv(x))))))  (model/blocks.py:25-29); x carries fp32 master + planes."""
         g, c = x.geom, rb.out_channels
         raw = P.act(f'raw{g.key()}_{c}', g, c, f32=True, planes=False)
         h = P.act(f'h{g.key()}_{c}', g, c, f32=False)
         y = P.act(name + '.out', g, c, f32=True)
         sc = P.scratch(g.n, c)
-        self._conv(P, name + '.block.0', rb.block[0], x, raw, out_planes=False)
-        G.group_norm_act(raw, rb.block[1].weight.detach(), rb.block[1].bias.detach(), sc, h, act=G.ACT_RELU, out_f32=False)
-        self._conv(P, name + '.block.3', rb.block[3], h, raw, out_planes=False)
+        # GroupNorm statistics ride in the conv epilogue when a group spans whole 8-channel cells (c >= 256); for narrow
+        # layers the per-group shuffles and atomics cost more than the separate reduction pass (measured), so they keep it
+        cpg = c // 32
+        fused = cpg >= 8
+        st_kw = dict(gn_sums=sc.sums, gn_cpg=cpg) if fused else {}
+        self._conv(P, name + '.block.0', rb.block[0], x, raw, out_planes=False, **st_kw)
+        G.group_norm_act(raw, rb.block[1].weight.detach(), rb.block[1].bias.detach(), sc, h, act=G.ACT_RELU, out_f32=False,
+                         fused_stats=fused)
+        self._conv(P, name + '.block.3', rb.block[3], h, raw, out_planes=False, **st_kw)
         if rb.in_channels != rb.out_channels:
             short = P.act(name + '.short', g, c, f32=True, planes=False)
             self._conv(P, name + '.channel_up', rb.channel_up, x, short, out_planes=False)
             res = short.f32
         else:
             res = x.f32
-        G.group_norm_act(raw, rb.block[4].weight.detach(), rb.block[4].bias.detach(), sc, y, act=G.ACT_RELU, residual=res)
+        G.group_norm_act(raw, rb.block[4].weight.detach(), rb.block[4].bias.detach(), sc, y, act=G.ACT_RELU, residual=res,
+                         fused_stats=fused, out_nchw=nchw_out)
         return y
 
     def _up_block(self, P, name, ub, x, need_f32):
@@ -269,10 +276,12 @@ class Decoder(nn.Module):
             if isinstance(mod, NonLocalBlock):
                 cur = self._non_local(P, name, mod, cur)
             elif isinstance(mod, ResidualBlock):
-                cur = self._res_block(P, name, mod, cur)
                 nxt = self.feat_extract[li + 1] if li + 1 < nlayers else None
+                nchw = None
                 if want_feats and isinstance(nxt, UpBlock):    # the tensors model/decoder.py:46/51 collects
-                    feats.append(G.unpack_nchw(cur))
+                    nchw = torch.empty(n, mod.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
+                    feats.append(nchw)                         # written by the block's last GroupNorm pass, no extra copy
+                cur = self._res_block(P, name, mod, cur, nchw_out=nchw)
             else:
                 last = li == nlayers - 1
                 if last and self.compose_final and 4 * self.output_layer.out_channels <= 16:

@@ -33,6 +33,7 @@ class IgemmDesc(C.Structure):
                 ('out_f32', C.c_void_p), ('out_hi', C.c_void_p), ('out_lo', C.c_void_p),
                 ('out_nchw', C.c_void_p), ('nchw_c', C.c_int32),
                 ('out_rowmajor', C.c_void_p), ('ld', C.c_int64),
+                ('gn_sums', C.c_void_p), ('gn_cpg', C.c_int32),
                 ('err_flag', C.c_void_p)]
 
 
@@ -207,7 +208,7 @@ def _p(t):
 def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row=False, act=ACT_NONE, slope=0.0,
           residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, phase_cols=0, c_off=0,
           out_f32=True, out_planes=True, out_nchw=None, nchw_c=0, out_rowmajor=None, ld=0,
-          b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None):
+          b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None, gn_sums=None, gn_cpg=0):
     """One fused implicit-GEMM launch.  `a`: Act (A operand); `w`: Weights or None when b_* are given explicitly;
     `out`: Act receiving fp32 master / planes (whichever it owns and the flags allow)."""
     d = IgemmDesc()
@@ -238,6 +239,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
         d.out_lo = _p(out.lo) if out_planes else None
     d.out_nchw, d.nchw_c = _p(out_nchw), nchw_c
     d.out_rowmajor, d.ld = _p(out_rowmajor), ld
+    d.gn_sums, d.gn_cpg = _p(gn_sums), gn_cpg
     d.err_flag = _p(err)
     _lib.check(_lib.lib().gpemsr_igemm(C.byref(d), _lib.stream_ptr()))
 
@@ -265,18 +267,21 @@ class GroupNormScratch:
 
 
 def group_norm_act(x, gamma, beta, scratch, out, act=ACT_NONE, slope=0.0, residual=None, groups=32, eps=1e-6,
-                   out_f32=True, out_planes=True):
-    """GroupNorm(32, eps=1e-6) of the fp32 master of `x` (model/blocks.py:5-6), then act (+ residual) into `out`."""
+                   out_f32=True, out_planes=True, out_nchw=None, fused_stats=False):
+    """GroupNorm(32, eps=1e-6) of the fp32 master of `x` (model/blocks.py:5-6), then act (+ residual) into `out`.
+    fused_stats: the producing GEMM already accumulated per-group sums into scratch.sums (igemm gn_sums=...)."""
     L = _lib.lib()
     g = x.geom.c
     og = out.geom.c
     st = _lib.stream_ptr()
-    _lib.check(L.gpemsr_gn_stats(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.sums), st))
-    _lib.check(L.gpemsr_gn_scale_shift(_lib.ptr(scratch.sums), _lib.ptr(gamma), _lib.ptr(beta), x.geom.n, x.c, groups,
-                                       float(x.geom.h * x.geom.w), eps, _lib.ptr(scratch.ss), st))
+    if not fused_stats:
+        _lib.check(L.gpemsr_gn_stats(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.sums), st))
+    _lib.check(L.gpemsr_gn_scale_shift(_lib.ptr(scratch.sums), int(fused_stats), _lib.ptr(gamma), _lib.ptr(beta), x.geom.n, x.c,
+                                       groups, float(x.geom.h * x.geom.w), eps, _lib.ptr(scratch.ss), st))
     _lib.check(L.gpemsr_affine_act(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.ss), act, slope, _lib.ptr(residual),
                                    C.byref(og), _lib.ptr(out.f32) if out_f32 else None,
-                                   _lib.ptr(out.hi) if out_planes else None, _lib.ptr(out.lo) if out_planes else None, st))
+                                   _lib.ptr(out.hi) if out_planes else None, _lib.ptr(out.lo) if out_planes else None,
+                                   _lib.ptr(out_nchw), st))
 
 
 def softmax_rows_blocked(s, t, ld, t_pad, stats, p_hi, p_lo):

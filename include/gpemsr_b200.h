@@ -141,6 +141,9 @@ typedef struct gpemsr_igemm_desc {
   void* out_hi; void* out_lo;               /* bf16 planes or NULL */
   float* out_nchw; int32_t nchw_c;          /* reference layout [n, nchw_c, up*h, up*w] or NULL */
   float* out_rowmajor; int64_t ld;          /* [rows, ld] fp32 (attention scores), rows relative to m0, or NULL */
+  double* gn_sums; int32_t gn_cpg;          /* optional fused GroupNorm statistics of the stored values: [n][n_cols/gn_cpg][2]
+                                               doubles (sum, sum of squares per image and group of gn_cpg channels), zeroed by
+                                               the call; gn_cpg in {1,2,4,8,16,32} */
   int32_t* err_flag;                        /* device int: set when the pipeline times out (never hangs) */
 } gpemsr_igemm_desc_t;
 
@@ -173,12 +176,13 @@ GPEMSR_API int gpemsr_pack_weights_tiled(const float* w, int n, int k, int64_t n
  * into a compact geometry (attention tokens).  chan_sums: [n, c, 2] doubles (zeroed by gn_stats). */
 GPEMSR_API int gpemsr_gn_stats(const float* x_f32, int c, const gpemsr_geom_t* g, double* chan_sums,
                     gpemsr_stream_t stream);
-GPEMSR_API int gpemsr_gn_scale_shift(const double* chan_sums, const float* gamma, const float* beta, int n, int c,
-                          int groups, double count_per_channel, float eps, float* scale_shift /* [n, c, 2] */,
-                          gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_gn_scale_shift(const double* sums, int sums_per_group /* 0: [n,c,2] per channel, 1: [n,groups,2] */,
+                          const float* gamma, const float* beta, int n, int c, int groups, double count_per_channel,
+                          float eps, float* scale_shift /* [n, c, 2] */, gpemsr_stream_t stream);
 GPEMSR_API int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const float* scale_shift,
                       int act, float slope, const float* residual, const gpemsr_geom_t* og,
-                      float* out_f32, void* out_hi, void* out_lo, gpemsr_stream_t stream);
+                      float* out_f32, void* out_hi, void* out_lo, float* out_nchw /* [n,c,h,w] or NULL */,
+                      gpemsr_stream_t stream);
 
 /* softmax over the last dim of fp32 scores s [t, ld] (first t columns valid; model/blocks.py:76) ->
  * probabilities as K8-blocked bf16 A operand planes [t_pad/8][t_pad][8] (hi, lo). */
