@@ -141,7 +141,7 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '25',
                                           '-i', str(self.index)], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -288,7 +288,7 @@ def config_block(world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -330,14 +330,15 @@ def main():
         torch.cuda.synchronize()
 
     W = max(args.warmup, 3)
-    for _ in range(W):
-        step(dev_in)
-    hp.dec.check(); hp.tail.check()
-
-    # ---- value: inputs resident in HBM
-    barrier()
-    l0 = gpemsr_b200.kernel_launches()
+    # nvidia-smi needs ~100 ms to start sampling: it runs from the warm-up on (same kernels, same load) through the timed region
     with ClockSampler(local) as cs:
+        for _ in range(W):
+            step(dev_in)
+        hp.dec.check(); hp.tail.check()
+
+        # ---- value: inputs resident in HBM
+        barrier()
+        l0 = gpemsr_b200.kernel_launches()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(args.steps):
@@ -352,24 +353,40 @@ def main():
     ms_total = float(t.item())
     value = world * args.steps * hr_px / 1e6 / (ms_total / 1e3)
 
-    # ---- e2e: every step input from pinned host memory, HR slice read back
-    stage = {k: torch.empty_like(v) for k, v in dev_in.items()}
-    out_host = torch.empty(1, 1, SCALE * LR, SCALE * LR).pin_memory()
+    # ---- e2e: every step input from pinned host memory, HR slice read back.  The volume driver's schedule: the H2D copy
+    # of step i+1 runs on a copy stream while step i computes (two staging sets), the HR slice is read back per step.
+    stage = [{k: torch.empty_like(v) for k, v in dev_in.items()} for _ in range(2)]
+    out_host = [torch.empty(1, 1, SCALE * LR, SCALE * LR).pin_memory() for _ in range(2)]
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    d2h = out_host.numel() * 4
+    d2h = out_host[0].numel() * 4
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]     # staging set filled
+    freed = [torch.cuda.Event() for _ in range(2)]     # staging set consumed by its step
 
-    def e2e_step():
-        for k in stage:
-            stage[k].copy_(host_in[k], non_blocking=True)
-        out_host.copy_(step(stage), non_blocking=True)
+    def e2e_run(n_steps):
+        for b in range(2):
+            freed[b].record(main_stream)
+        for i in range(n_steps + 1):
+            if i < n_steps:                            # prefetch step i
+                b = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[b])
+                    for k in stage[b]:
+                        stage[b][k].copy_(host_in[k], non_blocking=True)
+                    ready[b].record(copy_stream)
+            if i >= 1:                                 # compute step i-1
+                b = (i - 1) & 1
+                main_stream.wait_event(ready[b])
+                out = step(stage[b])
+                freed[b].record(main_stream)
+                out_host[b].copy_(out, non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
     barrier()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e2.record()
     barrier()
     t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
