@@ -579,6 +579,67 @@ __global__ void softmax_write_kernel(const float* __restrict__ s, long long t, l
   }
 }
 
+// ---- softmax over scores stored as K8-blocked fp32 cells [t_pad/8][rows_alloc][8] (row i = query, cell = 8 consecutive keys).
+// Lanes <-> consecutive rows, so every cell access of a warp is one contiguous 1 KB run; no transpose is needed because the
+// probabilities are written back in the same cell order (that is the A-operand layout of the P v^T GEMM).
+// pass 1: per (row, part) online (max, sum exp) over a slice of the key cells
+__global__ void softmax_cells_partial_kernel(const float* __restrict__ s, long long t, long long rows_alloc, int cells_per_part,
+                                             float* __restrict__ part) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t) return;
+  const long long ncell = (t + 7) / 8;
+  const long long c0 = (long long)blockIdx.y * cells_per_part, c1 = min(ncell, c0 + cells_per_part);
+  float m = -INFINITY, sum = 0.f;
+  for (long long jc = c0; jc < c1; ++jc) {
+    const float* p = s + (jc * rows_alloc + i) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { if (jc * 8 + j >= t) v[j] = -INFINITY; cm = fmaxf(cm, v[j]); }
+    const float mn = fmaxf(m, cm);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += expf(v[j] - mn);
+    sum = sum * expf(m - mn) + acc;
+    m = mn;
+  }
+  part[((long long)blockIdx.y * t + i) * 2] = m;
+  part[((long long)blockIdx.y * t + i) * 2 + 1] = sum;
+}
+// pass 2: combine the parts -> stats[i] = (max, sum exp)
+__global__ void softmax_cells_combine_kernel(const float* __restrict__ part, long long t, int parts, float* __restrict__ stats) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t) return;
+  float m = -INFINITY;
+  for (int p = 0; p < parts; ++p) m = fmaxf(m, part[((long long)p * t + i) * 2]);
+  float sum = 0.f;
+  for (int p = 0; p < parts; ++p) sum += part[((long long)p * t + i) * 2 + 1] * expf(part[((long long)p * t + i) * 2] - m);
+  stats[i * 2] = m;
+  stats[i * 2 + 1] = sum;
+}
+// pass 3: p = exp(s - max) / sum -> (hi, lo) cells in place order
+__global__ void softmax_cells_write_kernel(const float* __restrict__ s, long long t, long long rows_alloc, long long t_pad,
+                                           const float* __restrict__ stats, __nv_bfloat16* __restrict__ p_hi,
+                                           __nv_bfloat16* __restrict__ p_lo) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (jc, i), i fastest
+  if (idx >= (t_pad / 8) * t_pad) return;
+  const long long i = idx % t_pad, jc = idx / t_pad;
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (i < t && jc * 8 < t) {
+    const float mx = stats[i * 2], den = stats[i * 2 + 1];
+    const float* p = s + (jc * rows_alloc + i) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (jc * 8 + j < t) ? expf(x[j] - mx) / den : 0.f;
+  }
+  uint4 h, l;
+  split8(v, h, l);
+  *reinterpret_cast<uint4*>(p_hi + (size_t)idx * 8) = h;
+  if (p_lo) *reinterpret_cast<uint4*>(p_lo + (size_t)idx * 8) = l;
+}
+
 // ------------------------------------------------------------------------------------------------ bilinear base
 // ATen upsample_bilinear2d, align_corners=False, scale_factor given: src = (dst + 0.5) / scale - 0.5, clamped at 0
 __global__ void add_bilinear_base_kernel(const float* __restrict__ xc, int n, int h, int w, int scale, float* __restrict__ out) {
@@ -855,6 +916,29 @@ int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t
   dim3 grid((unsigned)((t_pad / 8 + 31) / 32), (unsigned)((t_pad + 31) / 32));
   softmax_write_kernel<<<grid, 1024, 0, st>>>(s, t, ld, t_pad, row_stats, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo);
   GPEMSR_LAUNCH_OK("softmax_write_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_softmax_cells_blocked(const float* s_cells, int64_t t, int64_t rows_alloc, int64_t t_pad, float* scratch, void* p_hi,
+                                 void* p_lo, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!s_cells || !scratch || !p_hi || t <= 0 || rows_alloc < t_pad || t_pad < t || t_pad % 8)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "softmax_cells_blocked: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long ncell = (t + 7) / 8;
+  const int parts = (int)std::max<long long>(1, std::min<long long>(16, ncell / 16));
+  const int cpp = (int)((ncell + parts - 1) / parts);
+  float* part = scratch + 2 * t;                   // scratch: [t][2] stats, then [parts][t][2] partials
+  softmax_cells_partial_kernel<<<dim3((unsigned)((t + 127) / 128), parts), 128, 0, st>>>(s_cells, t, rows_alloc, cpp, part);
+  GPEMSR_LAUNCH_OK("softmax_cells_partial_kernel");
+  softmax_cells_combine_kernel<<<(unsigned)((t + 127) / 128), 128, 0, st>>>(part, t, parts, scratch);
+  GPEMSR_LAUNCH_OK("softmax_cells_combine_kernel");
+  const long long total = (t_pad / 8) * t_pad;
+  softmax_cells_write_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s_cells, t, rows_alloc, t_pad, scratch,
+                                                                           (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo);
+  GPEMSR_LAUNCH_OK("softmax_cells_write_kernel");
   return GPEMSR_OK;
 }
 

@@ -193,8 +193,10 @@ class Decoder(nn.Module):
             vt = (torch.zeros(shape, dtype=torch.bfloat16, device=P.device),
                   torch.zeros(shape, dtype=torch.bfloat16, device=P.device) if P.split == 3 else None)
             P.bufs[name + '.vt'] = vt
-            P.bufs[name + '.s'] = torch.zeros(t_pad, t_pad, dtype=torch.float32, device=P.device)
-            P.bufs[name + '.stats'] = torch.zeros(t_pad, 2, dtype=torch.float32, device=P.device)
+            sg = G.Geom(1, g.h, g.w, padded=False, r_img=t_pad, m0=0)             # scores: rows = queries, cells = 8 keys
+            P.bufs[name + '.s'] = _View(None, None, sg)
+            P.bufs[name + '.s'].f32 = torch.zeros(t_pad // 8, sg.rows_alloc, 8, dtype=torch.float32, device=P.device)
+            P.bufs[name + '.stats'] = torch.zeros(2 * t_pad * 17, dtype=torch.float32, device=P.device)
             pshape = (t_pad // 8, t_pad, 8)
             P.bufs[name + '.p'] = (torch.zeros(pshape, dtype=torch.bfloat16, device=P.device),
                                    torch.zeros(pshape, dtype=torch.bfloat16, device=P.device) if P.split == 3 else None)
@@ -212,8 +214,8 @@ class Decoder(nn.Module):
             G.igemm(q, None, P.err, split=P.split, scale=float(int(c) ** (-0.5)), a_geom=cg.sample(i), n_cols=t,
                     b_hi=k.hi.data_ptr() + i * t_pad * row_bytes,
                     b_lo=(k.lo.data_ptr() + i * t_pad * row_bytes) if k.lo is not None else None,
-                    b_rows=cg.rows_alloc, k_pad=k.c_pad, out_rowmajor=s_buf, ld=t_pad)
-            G.softmax_rows_blocked(s_buf, t, t_pad, t_pad, stats, p_hi, p_lo)
+                    b_rows=cg.rows_alloc, k_pad=k.c_pad, out=s_buf, out_planes=False)
+            G.softmax_cells_blocked(s_buf.f32, t, s_buf.geom.rows_alloc, t_pad, stats, p_hi, p_lo)
             # o_i = P v_i^T
             pg = G.Geom(1, g.h, g.w, padded=False, r_img=t_pad, m0=0, rows_alloc=t_pad)
             pa = _View(p_hi, p_lo, pg)

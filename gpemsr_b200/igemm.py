@@ -289,6 +289,11 @@ def softmax_rows_blocked(s, t, ld, t_pad, stats, p_hi, p_lo):
                                                       _lib.ptr(p_lo), _lib.stream_ptr()))
 
 
+def softmax_cells_blocked(s_cells, t, rows_alloc, t_pad, scratch, p_hi, p_lo):
+    _lib.check(_lib.lib().gpemsr_softmax_cells_blocked(_lib.ptr(s_cells), t, rows_alloc, t_pad, _lib.ptr(scratch), _lib.ptr(p_hi),
+                                                       _lib.ptr(p_lo), _lib.stream_ptr()))
+
+
 def add_bilinear_base(x_center, scale, out):
     n, _, h, w = x_center.shape
     _lib.check(_lib.lib().gpemsr_add_bilinear_base(_lib.ptr(x_center.contiguous()), n, h, w, scale, _lib.ptr(out),

@@ -189,6 +189,11 @@ GPEMSR_API int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t*
 GPEMSR_API int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t_pad, float* row_stats /* [t,2] */,
                                 void* p_hi, void* p_lo, gpemsr_stream_t stream);
 
+/* same softmax on scores stored as K8-blocked fp32 cells [t_pad/8][rows_alloc][8] (the igemm out_f32 format with keys as
+ * "channels"): coalesced without a transpose.  scratch: 2*t*(1+16) floats. */
+GPEMSR_API int gpemsr_softmax_cells_blocked(const float* s_cells, int64_t t, int64_t rows_alloc, int64_t t_pad, float* scratch,
+                                 void* p_hi, void* p_lo, gpemsr_stream_t stream);
+
 /* Border ring of a 2x-upsampling, 4-phase, 3x3-tap linear map whose weights depend on the output position class (top /
  * interior / bottom) x (left / interior / right): wc [9][4][cout][cin][3][3], bias [9][cout].  Used by the decoder's final
  * stage, where ConvTranspose2d (model/blocks.py:35) and the output conv (model/decoder.py:33) are composed into one
