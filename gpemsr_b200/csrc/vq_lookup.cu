@@ -54,7 +54,7 @@ struct Workspace {
 
 Workspace carve(void* base, long long rows, int d, int k) {
   const long long rows_pad = round_up(std::max<long long>(rows, 1), gemm::BLOCK_M);
-  const long long d_pad = round_up(d, 64), k_pad = round_up(k, VQ_BLOCK_N);
+  const long long d_pad = round_up(d + 3, 64), k_pad = round_up(k, VQ_BLOCK_N);      // + 3: the folded constant's k slots
   uintptr_t p = (uintptr_t)base;
   auto take = [&](size_t n) { uintptr_t r = p; p += (uintptr_t)round_up((long long)n, 256); return (void*)r; };
   Workspace w;
@@ -73,36 +73,49 @@ Workspace carve(void* base, long long rows, int d, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// codes: one warp per code k.  c_k = |e_k|^2 (mode 0) or -bias_k (mode 1); B operand cells; max norm.
+// codes: one warp per code k.  c_k = |e_k|^2 (mode 0) or -bias_k (mode 1); B operand cells; max norms.
+// The per-code constant is FOLDED INTO THE GEMM: the three k slots after the real data hold t_k = c_k / alpha split into
+// three bf16 pieces (hi + lo + lo2 = t_k to 2^-24) and the A operand holds 1.0 there, so the accumulator is
+//   acc_k = bf16(z).bf16(e_k) + c_k / alpha,   score_k = alpha * acc_k,   arg-min score = arg-max acc   (alpha < 0)
+// and the epilogue needs no per-column constant load or FFMA at all.
 __global__ void vq_prep_codes(const float* __restrict__ e, const float* __restrict__ bias, int k, int d, int k_pad, int d_pad,
-                              int mode, __nv_bfloat16* __restrict__ b, float* __restrict__ c, float* __restrict__ emax) {
+                              int mode, float alpha, __nv_bfloat16* __restrict__ b, float* __restrict__ c, float* __restrict__ emax) {
   const int code = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (code >= k_pad) return;
+  const bool real = code < k;
   float ss = 0.f, sd = 0.f;                 // |e_k|^2 and |e_k - bf16(e_k)|^2
+  if (real)
+    for (int i = lane; i < d; i += 32) {
+      const float v = e[(size_t)code * d + i], r = v - sm100::bf16_round(v);
+      ss = fmaf(v, v, ss);
+      sd = fmaf(r, r, sd);
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
+  const float ck = real ? (mode == 0 ? ss : -bias[code]) : INFINITY;
+  const float t = ck / alpha;                                   // alpha is -2 or -1: exact
+  float t_hi = sm100::bf16_round(t), t_lo = 0.f, t_lo2 = 0.f;
+  if (real) { t_lo = sm100::bf16_round(t - t_hi); t_lo2 = sm100::bf16_round((t - t_hi) - t_lo); }
   for (int kc = lane; kc < d_pad / 8; kc += 32) {
     uint32_t h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int d0 = kc * 8 + 2 * j;
-      const float v0 = (code < k && d0 < d) ? e[(size_t)code * d + d0] : 0.f;
-      const float v1 = (code < k && d0 + 1 < d) ? e[(size_t)code * d + d0 + 1] : 0.f;
-      ss = fmaf(v0, v0, ss);
-      ss = fmaf(v1, v1, ss);
-      const float r0 = v0 - sm100::bf16_round(v0), r1 = v1 - sm100::bf16_round(v1);
-      sd = fmaf(r0, r0, sd);
-      sd = fmaf(r1, r1, sd);
-      h[j] = sm100::pack_bf16x2(v0, v1);
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int dd = kc * 8 + 2 * j + u;
+        v[u] = dd < d ? (real ? e[(size_t)code * d + dd] : 0.f) : (dd == d ? t_hi : dd == d + 1 ? t_lo : dd == d + 2 ? t_lo2 : 0.f);
+      }
+      h[j] = sm100::pack_bf16x2(v[0], v[1]);
     }
     // tiled layout [code tile][k-chunk of 64][k-cell][256 codes][8]: every GEMM stage is one contiguous 32 KB copy
     const size_t cell = (((size_t)(code / VQ_BLOCK_N) * (d_pad / 64) + kc / 8) * 8 + (kc & 7)) * VQ_BLOCK_N + (code % VQ_BLOCK_N);
     *reinterpret_cast<uint4*>(b + cell * 8) = make_uint4(h[0], h[1], h[2], h[3]);
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
   if (lane == 0) {
-    c[code] = (code >= k) ? INFINITY : (mode == 0 ? ss : -bias[code]);
-    if (code < k) {                                     // non-negative floats order like ints
+    c[code] = ck;
+    if (real) {                                         // non-negative floats order like ints
       atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(ss) * 1.0000002f));
       atomicMax(reinterpret_cast<int*>(emax) + 1, __float_as_int(sqrtf(sd) * 1.0000002f));
     }
@@ -139,6 +152,11 @@ __global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long l
       const float rj = v[j] - sm100::bf16_round(v[j]);
       sdz = fmaf(rj, rj, sdz);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                    // the three k slots that multiply the folded constant (see vq_prep_codes)
+      const int dd = kc * 8 + j;
+      if (dd >= d && dd < d + 3) v[j] = 1.0f;
+    }
     *reinterpret_cast<uint4*>(a + ((size_t)kc * rows_pad + r) * 8) =
         make_uint4(sm100::pack_bf16x2(v[0], v[1]), sm100::pack_bf16x2(v[2], v[3]), sm100::pack_bf16x2(v[4], v[5]),
                    sm100::pack_bf16x2(v[6], v[7]));
@@ -152,48 +170,44 @@ __global__ void vq_prep_rows(const float* __restrict__ z, long long rows, long l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GEMM epilogue: score_k = c_k + alpha * acc_k (minimised).  Per code tile: pass 1 lowers the row's running minimum,
-// pass 2 appends every code within `margin` of it straight to the row's candidate list in global memory (a predicated
-// store + counter bump: the lanes of a warp are different rows, so anything heavier would serialise).  The list is a
-// superset of the codes within `margin` of the FINAL minimum because the running minimum only decreases; vq_finalize
-// filters it against the final minimum.
+// GEMM epilogue.  The accumulator already contains the per-code constant (acc_k = dot_k + c_k / alpha), so with alpha < 0
+// the best code is the arg-MAX of the raw accumulators.  Per code tile: pass 1 raises the row's running maximum (one
+// FMNMX per column), pass 2 appends every code within margin / |alpha| of it straight to the row's candidate list in
+// global memory (a predicated store + counter bump: the lanes of a warp are different rows, so anything heavier would
+// serialise).  The list is a superset of the codes within `margin` of the FINAL optimum because the running maximum only
+// increases; vq_rescore filters it against the final value.  Scores are stored as alpha * acc ("smaller is better").
+// (A single-pass variant with a seeded running maximum was measured: no faster, and its longer lists slow vq_rescore.)
 struct EpiArgExtremum {
-  const float* c;
   const float* margin;
-  uint32_t* cand_cnt;      // [rows]
-  uint2* cand;             // [rows][CMAX] (code, score bits), ascending code order
-  float* runmin_out;       // [rows]
+  uint32_t* cand_cnt;      // [rows][2]
+  uint2* cand;             // [rows][2][CSUB] (code, score bits)
+  float* runmin_out;       // [rows][2]
   long long rows;
   float alpha;
 
   static constexpr int WARPS = 8;        // two warps per TMEM lane quarter: each row is scanned by two threads, one per
-                                         // half of the tile's columns, with its own running minimum and sub-list
+                                         // half of the tile's columns, with its own running maximum and sub-list
   struct State {
-    float runmin = INFINITY;
+    float runmax = -INFINITY;
     uint32_t cnt = 0;
   };
 
-  __device__ __forceinline__ float min32(const uint32_t (&r)[32], const float* __restrict__ cc, float mn) const {
+  __device__ __forceinline__ float max32(const uint32_t (&r)[32], float mx) const {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 ck = __ldg(reinterpret_cast<const float4*>(cc + j));
-      mn = fminf(mn, fminf(fminf(fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), fmaf(alpha, __uint_as_float(r[j + 1]), ck.y)),
-                           fminf(fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), fmaf(alpha, __uint_as_float(r[j + 3]), ck.w))));
-    }
-    return mn;
+    for (int j = 0; j < 32; j += 4)
+      mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))));
+    return mx;
   }
-  __device__ __forceinline__ void scan32(State& st, const uint32_t (&r)[32], const float* __restrict__ cc, uint32_t code0,
-                                         float thr, uint2* __restrict__ list) const {
+  __device__ __forceinline__ void scan32(State& st, const uint32_t (&r)[32], uint32_t code0, float thr, uint2* __restrict__ list) const {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 ck = __ldg(reinterpret_cast<const float4*>(cc + j));
-      const float v[4] = {fmaf(alpha, __uint_as_float(r[j + 0]), ck.x), fmaf(alpha, __uint_as_float(r[j + 1]), ck.y),
-                          fmaf(alpha, __uint_as_float(r[j + 2]), ck.z), fmaf(alpha, __uint_as_float(r[j + 3]), ck.w)};
-      if (fminf(fminf(v[0], v[1]), fminf(v[2], v[3])) <= thr) {
+      const float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]), v2 = __uint_as_float(r[j + 2]), v3 = __uint_as_float(r[j + 3]);
+      if (fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) >= thr) {
+        const float v[4] = {v0, v1, v2, v3};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (v[u] <= thr) {
-            if (st.cnt < CSUB) list[st.cnt] = make_uint2(code0 + j + u, __float_as_uint(v[u]));
+          if (v[u] >= thr) {
+            if (st.cnt < CSUB) list[st.cnt] = make_uint2(code0 + j + u, __float_as_uint(alpha * v[u]));
             ++st.cnt;
           }
         }
@@ -207,37 +221,36 @@ struct EpiArgExtremum {
     const long long gr = m_tile * gemm::BLOCK_M + row;
     const bool live = gr < rows;
     const int cbase = part * SPAN;
-    const float* cc = c + (size_t)n_tile * VQ_BLOCK_N + cbase;
-    const float mg = live ? __ldg(margin + gr) : 0.f;
+    const float mg = live ? __ldg(margin + gr) / fabsf(alpha) : 0.f;
     uint2* list = cand + ((size_t)(live ? gr : 0) * 2 + part) * CSUB;
     const uint32_t tm = tmem_acc + cbase;
     uint32_t ra[32], rb[32];
-    float mn = st.runmin;
+    float mx = st.runmax;
     sm100::tmem_ld_32x32(tm, ra);
 #pragma unroll 1
     for (int c0 = 0; c0 < SPAN; c0 += 64) {
       sm100::tmem_ld_wait();
       sm100::tmem_ld_32x32(tm + c0 + 32, rb);
-      mn = min32(ra, cc + c0, mn);
+      mx = max32(ra, mx);
       sm100::tmem_ld_wait();
       sm100::tmem_ld_32x32(tm + ((c0 + 64) & (SPAN - 1)), ra);       // wraps to the first column for pass 2
-      mn = min32(rb, cc + c0 + 32, mn);
+      mx = max32(rb, mx);
     }
-    st.runmin = mn;
-    const float thr = live ? mn + mg : -INFINITY;      // padding rows never append
+    st.runmax = mx;
+    const float thr = live ? mx - mg : INFINITY;       // padding rows never append
     const uint32_t code_base = (uint32_t)(n_tile * VQ_BLOCK_N + cbase);
 #pragma unroll 1
     for (int c0 = 0; c0 < SPAN; c0 += 64) {
       sm100::tmem_ld_wait();
       sm100::tmem_ld_32x32(tm + c0 + 32, rb);
-      scan32(st, ra, cc + c0, code_base + c0, thr, list);
+      scan32(st, ra, code_base + c0, thr, list);
       sm100::tmem_ld_wait();
       if (c0 + 64 < SPAN) sm100::tmem_ld_32x32(tm + c0 + 64, ra);
-      scan32(st, rb, cc + c0 + 32, code_base + c0 + 32, thr, list);
+      scan32(st, rb, code_base + c0 + 32, thr, list);
     }
     if (n_tile == n_tiles - 1 && live) {
       cand_cnt[gr * 2 + part] = st.cnt > CSUB ? OVERFLOW : st.cnt;
-      runmin_out[gr * 2 + part] = mn;
+      runmin_out[gr * 2 + part] = alpha * mx;
     }
   }
 };
@@ -496,11 +509,11 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
 
   Workspace W = carve(ws, rows, d, k);
   const long long rows_pad = round_up(rows, gemm::BLOCK_M);
-  const int d_pad = (int)round_up(d, 64), k_pad = (int)round_up(k, VQ_BLOCK_N), n_tiles = k_pad / VQ_BLOCK_N;
+  const int d_pad = (int)round_up(d + 3, 64), k_pad = (int)round_up(k, VQ_BLOCK_N), n_tiles = k_pad / VQ_BLOCK_N;
   const float alpha = mode == 0 ? -2.0f : -1.0f;
 
   GPEMSR_CUDA_OK(cudaMemsetAsync(W.emax, 0, 512, s));       // emax and err (adjacent 256-byte slots)
-  vq_prep_codes<<<(k_pad + 7) / 8, 256, 0, s>>>(w, bias, k, d, k_pad, d_pad, mode, W.b, W.c, W.emax);
+  vq_prep_codes<<<(k_pad + 7) / 8, 256, 0, s>>>(w, bias, k, d, k_pad, d_pad, mode, alpha, W.b, W.c, W.emax);
   GPEMSR_LAUNCH_OK("vq_prep_codes");
   vq_prep_rows<<<(unsigned)((rows_pad + 127) / 128), 128, 0, s>>>(z, rows, hw, d, d_pad, rows_pad, fabsf(alpha), W.emax, W.a,
                                                                 W.zz, W.margin);
@@ -510,7 +523,7 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
     op.a_hi = W.a; op.a_lo = nullptr; op.b_hi = W.b; op.b_lo = nullptr;
     op.a_rows = rows_pad; op.b_rows = k_pad; op.b_packed = 1; op.k = d_pad; op.taps = 1; op.a_row_off[0] = 0;
     op.m_tiles = rows_pad / gemm::BLOCK_M; op.n_tiles = n_tiles; op.a_row0 = 0; op.err_flag = W.err;
-    EpiArgExtremum epi{W.c, W.margin, W.cand_cnt, W.cand, W.runmin, rows, alpha};
+    EpiArgExtremum epi{W.margin, W.cand_cnt, W.cand, W.runmin, rows, alpha};
     using Cfg = gemm::Config<VQ_BLOCK_N, 64, 1, 4>;
     if (op.m_tiles >= 2 && use_clusters()) {       // CTA pairs share every codebook stage by multicast (halves L2 traffic)
       auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum, 2>;
