@@ -466,6 +466,217 @@ vq_gather(const float* __restrict__ table, const long long* __restrict__ idx, lo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// vq_finish: vq_rescore + vq_gather in ONE kernel for 16-byte friendly shapes (d % 4 == 0, dq % 4 == 0, aligned bases) --
+// the path every model shape takes.  Same decisions as vq_rescore, with a much leaner inner loop:
+//   * the block's whole fp32 z tile [32 rows][<= 512 channels] is staged ROW-major in shared memory (coalesced reads along
+//     hw, float4 stores; row stride 516 floats keeps every quarter-warp float4 access conflict-free), so a (row, code)
+//     pair costs 4 x (LDS.128 + LDG.128 + 4 FFMA) and ONE warp reduction instead of 16 scalar triples and 4 reductions;
+//   * the winners' code vectors are then transposed through the same buffer and stored along hw (NCHW), so the indices
+//     never round-trip through HBM and the tile's z (needed by the optional loss) is still in L2.
+constexpr int FZ_D = 512;                        // channels per staged tile
+constexpr int FZ_LD = FZ_D + 4;
+constexpr int FZ_SMEM = FIN_ROWS * FZ_LD * 4;
+
+__global__ void __launch_bounds__(FIN_THREADS, 3)
+vq_finish(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ table, long long hw,
+          int blocks_per_image, int d, int k, int dq, int mode, const float* __restrict__ c, const float* __restrict__ zz,
+          const float* __restrict__ margin, const float* __restrict__ runmin, const uint32_t* __restrict__ cand_cnt,
+          const uint2* __restrict__ cand, long long* __restrict__ idx_out, float* __restrict__ zq, float* __restrict__ sq_err) {
+  constexpr int NW = FIN_THREADS / 32;
+  static_assert(NW == 16 && FIN_ROWS == 32 && CSUB == 16, "thread mapping below");
+  extern __shared__ __align__(16) float zt[];                  // [FIN_ROWS][FZ_LD]; first used as the step-0 scratch
+  __shared__ int s_idx[FIN_ROWS];
+  __shared__ int s_first[FIN_ROWS + 1];
+  __shared__ uint32_t s_pair[FIN_MAXPAIRS];      // (row << 16) | code
+  __shared__ float s_score[FIN_MAXPAIRS];
+  __shared__ int s_over[FIN_ROWS];
+  __shared__ int s_cnt[FIN_ROWS];
+  __shared__ int s_nover, s_npairs;
+  __shared__ unsigned s_overmask;
+  uint16_t (*s_tmp)[2 * CSUB] = reinterpret_cast<uint16_t (*)[2 * CSUB]>(zt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bi = blockIdx.x / blocks_per_image;
+  const long long p0 = (long long)(blockIdx.x % blocks_per_image) * FIN_ROWS;
+  const int nrows = (int)min((long long)FIN_ROWS, hw - p0);
+  const long long row0 = bi * hw + p0;
+
+  if (threadIdx.x == 0) s_overmask = 0;
+  if (threadIdx.x < FIN_ROWS) s_idx[threadIdx.x] = 0;
+  __syncthreads();
+  for (int r = warp; r < FIN_ROWS; r += NW) {      // step 0: filter the candidate sub-lists against the final minimum
+    int cnt = 0;
+    if (r < nrows) {
+      const long long gr = row0 + r;
+      const uint32_t n0 = cand_cnt[gr * 2], n1 = cand_cnt[gr * 2 + 1];
+      if (n0 == OVERFLOW || n1 == OVERFLOW) {
+        if (lane == 0) atomicOr(&s_overmask, 1u << r);
+      } else {
+        const float thr = fminf(runmin[gr * 2], runmin[gr * 2 + 1]) + margin[gr];
+        const uint2 e = cand[(size_t)gr * 2 * CSUB + lane];
+        const bool keep = (uint32_t)(lane & (CSUB - 1)) < (lane < CSUB ? n0 : n1) && __uint_as_float(e.y) <= thr;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        cnt = __popc(m);
+        if (keep) s_tmp[r][__popc(m & ((1u << lane) - 1))] = (uint16_t)e.x;
+        if (cnt <= 1) {
+          const int only = __shfl_sync(0xffffffffu, (int)e.x, m ? __ffs(m) - 1 : 0);
+          if (lane == 0) s_idx[r] = cnt ? only : 0;
+        }
+      }
+    }
+    if (lane == 0) s_cnt[r] = cnt >= 2 ? cnt : 0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int np = s_cnt[lane];
+    int incl = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    s_first[lane] = incl - np;
+    if (lane == 31) { s_first[32] = incl; s_npairs = incl; }
+    const unsigned om = s_overmask;
+    if ((om >> lane) & 1u) s_over[__popc(om & ((1u << lane) - 1))] = lane;
+    if (lane == 0) s_nover = __popc(om);
+  }
+  __syncthreads();
+  for (int r = warp; r < FIN_ROWS; r += NW) {
+    const int np = s_cnt[r], f = s_first[r];
+    if (lane < np) s_pair[f + lane] = ((uint32_t)r << 16) | s_tmp[r][lane];
+  }
+  __syncthreads();
+  const int npairs = s_npairs, nover = s_nover;
+
+  if (npairs > 0) {
+    for (int d0 = 0; d0 < d; d0 += FZ_D) {
+      const int dn = min(FZ_D, d - d0);
+      const float* zb = z + (bi * d + d0) * hw + p0 + (lane < nrows ? lane : 0);
+      if (d0) __syncthreads();
+      // stage the tile: thread (lane = row, quad q) loads 4 channels along coalesced hw lines and stores one float4.
+      // (4-byte cp.async copies straight into a transposed tile were measured: 0.5 ms slower.)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int dd = 4 * (warp + NW * (u + 4 * half));
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (dd < dn) {
+            const float* q = zb + (long long)dd * hw;
+            v[u].x = __ldg(q); v[u].y = __ldg(q + hw); v[u].z = __ldg(q + 2 * hw); v[u].w = __ldg(q + 3 * hw);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<float4*>(zt + lane * FZ_LD + 4 * (warp + NW * (u + 4 * half))) = v[u];
+      }
+      __syncthreads();
+      for (int p = warp; p < npairs; p += NW) {
+        const uint32_t pr = s_pair[p];
+        const int r = (int)(pr >> 16), kk = (int)(pr & 0xFFFFu);
+        const float* wk = w + (size_t)kk * d + d0;
+        const float* zr = zt + r * FZ_LD;
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < FZ_D / 128; ++u) {
+          const int dd = 128 * u + 4 * lane;
+          if (dd < dn) {
+            const float4 a = *reinterpret_cast<const float4*>(zr + dd);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(wk + dd));
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_score[p] = d0 ? s_score[p] + acc : acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < nrows) {
+      const int f = s_first[threadIdx.x], l = s_first[threadIdx.x + 1];
+      if (l > f) {
+        const float zzr = zz[row0 + threadIdx.x];
+        float bs = INFINITY; int best = 0;
+        for (int p = f; p < l; ++p) {                                // lowest index wins ties (the two sub-lists interleave)
+          const int kk = (int)(s_pair[p] & 0xFFFFu);
+          const float sc = score_of(s_score[p], mode, zzr, c[kk]);
+          if (sc < bs || (sc == bs && kk < best)) { bs = sc; best = kk; }
+        }
+        s_idx[threadIdx.x] = best;
+      }
+    }
+  }
+  // rows whose sub-lists overflowed (many duplicated / near-tied codes; rare): exact scan of ALL codes, z read in place
+  for (int o = 0; o < nover; ++o) {
+    __shared__ float s_wbest[NW];
+    __shared__ int s_wbestk[NW];
+    const int r = s_over[o];
+    const float* zr = z + bi * d * hw + p0 + r;
+    const float zzr = zz[row0 + r];
+    float bs = INFINITY;
+    int bk = 0x7fffffff;
+    for (int kk = warp; kk < k; kk += NW) {
+      float acc = 0.f;
+      for (int i = lane; i < d; i += 32) acc = fmaf(__ldg(zr + (long long)i * hw), __ldg(w + (size_t)kk * d + i), acc);
+#pragma unroll
+      for (int of = 16; of; of >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, of);
+      const float sc = score_of(acc, mode, zzr, c[kk]);
+      if (sc < bs) { bs = sc; bk = kk; }
+    }
+    if (lane == 0) { s_wbest[warp] = bs; s_wbestk[warp] = bk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = INFINITY; int bkk = 0x7fffffff;
+      for (int wv = 0; wv < NW; ++wv)
+        if (s_wbest[wv] < b || (s_wbest[wv] == b && s_wbestk[wv] < bkk)) { b = s_wbest[wv]; bkk = s_wbestk[wv]; }
+      s_idx[r] = bkk == 0x7fffffff ? 0 : bkk;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x < nrows) idx_out[row0 + threadIdx.x] = s_idx[threadIdx.x];
+
+  // ---- gather: z_q[bi, :, p0 + r] = table[idx[r], :]
+  float err = 0.f;
+  for (int q0 = 0; q0 < dq; q0 += FZ_D) {
+    const int dn = min(FZ_D, dq - q0);
+    if (q0) __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < FIN_ROWS / NW; ++rr) {
+      const int r = warp + NW * rr;
+      const float* src = table + (size_t)s_idx[r] * dq + q0;
+#pragma unroll
+      for (int u = 0; u < FZ_D / 128; ++u) {
+        const int dd = 128 * u + 4 * lane;
+        if (dd < dn) *reinterpret_cast<float4*>(zt + r * FZ_LD + dd) = __ldg(reinterpret_cast<const float4*>(src + dd));
+      }
+    }
+    __syncthreads();
+    if (lane < nrows) {
+      float* qb = zq + (bi * dq + q0) * hw + p0 + lane;
+      const float* zb = sq_err ? z + (bi * dq + q0) * hw + p0 + lane : nullptr;
+#pragma unroll
+      for (int u = 0; u < FZ_D / (4 * NW); ++u) {
+        const int dd = 4 * (warp + NW * u);
+        if (dd < dn) {
+          const float4 t = *reinterpret_cast<const float4*>(zt + lane * FZ_LD + dd);
+          float* q = qb + (long long)dd * hw;
+          __stcs(q, t.x); __stcs(q + hw, t.y); __stcs(q + 2 * hw, t.z); __stcs(q + 3 * hw, t.w);
+          if (zb) {
+            const float* zs = zb + (long long)dd * hw;
+            const float e0 = t.x - __ldg(zs), e1 = t.y - __ldg(zs + hw), e2 = t.z - __ldg(zs + 2 * hw), e3 = t.w - __ldg(zs + 3 * hw);
+            err = fmaf(e0, e0, err); err = fmaf(e1, e1, err); err = fmaf(e2, e2, err); err = fmaf(e3, e3, err);
+          }
+        }
+      }
+    }
+  }
+  if (sq_err) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+    if (lane == 0 && err != 0.f) atomicAdd(sq_err, err);
+  }
+}
+
 // argmax over materialised logits + gather (Codebook.inference_lr on its own): one warp per row
 __global__ void argmax_gather_kernel(const float* __restrict__ p, const float* __restrict__ table, long long rows, long long hw,
                                      int k, int dq, float* __restrict__ zq, long long* __restrict__ idx_out) {
@@ -540,14 +751,23 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
   }
   {
     const int blocks_per_image = (int)((hw + FIN_ROWS - 1) / FIN_ROWS);
-    vq_rescore<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, 0, s>>>(
-        z, w, hw, blocks_per_image, d, k, mode, W.c, W.zz, W.margin, W.runmin, W.cand_cnt, W.cand, idx);
-    GPEMSR_LAUNCH_OK("vq_rescore");
     const bool want_err = mode == 0 && sq_err_sum != nullptr;
     if (want_err) GPEMSR_CUDA_OK(cudaMemsetAsync(sq_err_sum, 0, sizeof(float), s));
-    dim3 grid((unsigned)((long long)b * blocks_per_image), (unsigned)((dq + GA_DCH - 1) / GA_DCH));
-    vq_gather<<<grid, 256, 0, s>>>(table, idx, hw, blocks_per_image, dq, zq, want_err ? z : nullptr, want_err ? sq_err_sum : nullptr);
-    GPEMSR_LAUNCH_OK("vq_gather");
+    const bool vec_ok = d % 4 == 0 && dq % 4 == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(table)) & 15) == 0;
+    if (vec_ok) {
+      GPEMSR_CUDA_OK(cudaFuncSetAttribute(vq_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM));
+      vq_finish<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, FZ_SMEM, s>>>(
+          z, w, table, hw, blocks_per_image, d, k, dq, mode, W.c, W.zz, W.margin, W.runmin, W.cand_cnt, W.cand, idx, zq,
+          want_err ? sq_err_sum : nullptr);
+      GPEMSR_LAUNCH_OK("vq_finish");
+    } else {                                   // odd channel counts / unaligned tables: the scalar two-kernel form
+      vq_rescore<<<(unsigned)((long long)b * blocks_per_image), FIN_THREADS, 0, s>>>(
+          z, w, hw, blocks_per_image, d, k, mode, W.c, W.zz, W.margin, W.runmin, W.cand_cnt, W.cand, idx);
+      GPEMSR_LAUNCH_OK("vq_rescore");
+      dim3 grid((unsigned)((long long)b * blocks_per_image), (unsigned)((dq + GA_DCH - 1) / GA_DCH));
+      vq_gather<<<grid, 256, 0, s>>>(table, idx, hw, blocks_per_image, dq, zq, want_err ? z : nullptr, want_err ? sq_err_sum : nullptr);
+      GPEMSR_LAUNCH_OK("vq_gather");
+    }
   }
   return GPEMSR_OK;
 }
