@@ -7,7 +7,8 @@ A "step" is one pass of the hot path over one slice window of BASELINE.json conf
 (GPEMSR x16, N_frames = 5 per option/output_GPEMSR_x16.yml, 80x80 LR -> 1280x1280 HR; 78x78 cannot run through the
 reference):
 
-    a-2  Indexer head Linear(512->1024) + softmax/top-1 + codebook gather on the 5 x 512 x 80 x 80 latents
+    f-4  Indexer16 conv stack (model/indexer.py) on the 5 x 1 x 80 x 80 LR frames -> 5 x 512 x 80 x 80 features
+    a-2  Indexer head Linear(512->1024) + softmax/top-1 + codebook gather on those features
     a-3  Decoder.multi_scale_feat_calculate on the 5 quantised latents  (-> 5 x 1 x 1280 x 1280 reference images)
     a-5  the 60 flow_warp calls SpyNet makes per forward (5 frames x 2 calls x 6 pyramid levels, 3 x 10^2 .. 3 x 320^2)
     a-4  the SR tail on the fused 64 x 80 x 80 feature (-> 1 x 1 x 1280 x 1280)
@@ -37,6 +38,8 @@ if ROOT not in sys.path:
 SCALE, NFRAMES, LR = 16, 5, 80
 DEC_CFG = dict(channel_list=[512, 256, 128, 64, 64], im_channel=1, num_resblock_per_scale=1, num_input_resblck=3,
                latent_dim=512, use_non_local=True)
+IDX_CFG = dict(channel_list=[64, 64, 128, 256, 512], im_channel=1, num_resblock_per_scale=2, num_output_resblck=3,
+               latent_dim=512, use_non_local=True)                      # option/output_GPEMSR_x16.yml:30-36
 METRIC, UNIT = 'hr_megapixels_per_s', 'MP/s'
 
 
@@ -49,7 +52,7 @@ def warp_levels(lr):
 def make_inputs(lr, nframes, seed, pin=False):
     g = torch.Generator().manual_seed(seed)
     ins = {
-        'feat': torch.randn(nframes, 512, lr, lr, generator=g),            # Indexer output_layer result
+        'lr_frames': torch.rand(nframes, 1, lr, lr, generator=g),          # the LR slice window (EM intensities in [0, 1])
         'fea': torch.randn(1, 64, lr, lr, generator=g),                    # ThreeDA output
         'x_center': torch.rand(1, 1, lr, lr, generator=g),
     }
@@ -64,7 +67,7 @@ def make_inputs(lr, nframes, seed, pin=False):
 def make_weights(seed=1):
     from oracle import weights as W      # deterministic random-init parameters (no checkpoints offline)
     return dict(dec=W.fill(W.decoder_spec(), seed), emb=W.fill(W.codebook_spec(), seed + 1)['embedding.weight'],
-                head=W.fill(W.indexer_head_spec(), seed + 2), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
+                idx=W.fill(W.indexer_spec(16), seed + 2), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
 
 
 # ----------------------------------------------------------------------------------------------- native arm
@@ -78,11 +81,13 @@ class NativeHotPath:
         self.dec.load_state_dict(wts['dec'], strict=True)
         self.tail = gpemsr_b200.SRTail(64, 10, SCALE).to(device)
         self.tail.load_state_dict(wts['tail'], strict=True)
-        self.hw = wts['head']['embedding.weight'].to(device)
-        self.hb = wts['head']['embedding.bias'].to(device)
+        from gpemsr_b200.indexer import Indexer16
+        self.idx = Indexer16(IDX_CFG).to(device)
+        self.idx.load_state_dict(wts['idx'], strict=True)
 
     def step(self, d):
-        zq = self.cb.inference_from_feat(d['feat'], self.hw, self.hb)
+        feat = self.idx.features(d['lr_frames'])
+        zq = self.cb.inference_from_feat(feat, self.idx.embedding.weight.detach(), self.idx.embedding.bias.detach())
         feats = self.dec.multi_scale_feat_calculate(zq)
         nlev = len([k for k in d if k.startswith('warp_x')])
         for i in range(nlev):
@@ -98,7 +103,7 @@ def cpu_step(wts, ins):
     from oracle import ref_ops as R
     from oracle.flow_warp import flow_warp_torch
     with torch.no_grad():
-        feats, _ = R.ref_extract_from_feat(ins['feat'], wts['head'], wts['emb'], wts['dec'])
+        feats, _ = R.ref_extract(ins['lr_frames'], wts['idx'], wts['emb'], wts['dec'])
         i = 0
         while f'warp_x{i}' in ins:
             x, f = ins[f'warp_x{i}'], ins[f'warp_f{i}']
@@ -278,7 +283,7 @@ def run_reference(args, rank, world):
 
 
 def config_block(world):
-    return {'workload': f'GPEMSR x16 hot path (Indexer head + codebook lookup, VQ decoder multi-scale, 60 SpyNet flow_warp '
+    return {'workload': f'GPEMSR x16 hot path (Indexer16 conv stack + head + codebook lookup, VQ decoder multi-scale, 60 SpyNet flow_warp '
                         f'calls, SR tail), {NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
             'lr': LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
             'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '

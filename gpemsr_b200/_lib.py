@@ -39,6 +39,7 @@ SIGNATURES = {
     'gpemsr_igemm': (_i, [_p, _p]),
     'gpemsr_act_pack_nchw': (_i, [_p, _i, _p, _i, _p, _p, _p, _p]),
     'gpemsr_act_unpack_nchw': (_i, [_p, _i, _p, _i, _p, _p]),
+    'gpemsr_space_to_depth': (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
     'gpemsr_pack_weights': (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _p, _p, _p]),
     'gpemsr_igemm_plan': (_i, [_p, _p, _p]),
     'gpemsr_pack_weights_tiled_bytes': (_sz, [_i, _i, _i, _i, _i]),

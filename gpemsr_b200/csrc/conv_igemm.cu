@@ -382,6 +382,25 @@ __global__ void act_unpack_nchw_kernel(const float* __restrict__ f32, int c, Geo
   }
 }
 
+// space-to-depth of the bf16 operand planes (stride-2 convolutions, model/blocks.py:41-47 DownBlock): output pixel (y, x) of
+// channel block (p*2 + q) holds input pixel (2y + p, 2x + q); whole 16-byte cells move, pixels past an odd edge are zero.
+__global__ void space_to_depth_kernel(const uint4* __restrict__ in_hi, const uint4* __restrict__ in_lo, Geom gi, int cells,
+                                      uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, Geom go) {
+  const long long hw = (long long)go.h * go.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (img, phase, cell, pixel): pixel fastest
+  if (t >= (long long)go.n * 4 * cells * hw) return;
+  const long long px = t % hw;
+  const int cc = (int)((t / hw) % cells), ph = (int)((t / (hw * cells)) % 4), img = (int)(t / (hw * cells * 4));
+  const int y = (int)(px / go.w), x = (int)(px % go.w);
+  const int sy = 2 * y + (ph >> 1), sx = 2 * x + (ph & 1);
+  const bool in = sy < gi.h && sx < gi.w;
+  const size_t src = (size_t)cc * gi.rows_alloc + (in ? place_row(gi, img, sy, sx) : 0);
+  const size_t dst = (size_t)(ph * cells + cc) * go.rows_alloc + place_row(go, img, y, x);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  out_hi[dst] = in ? in_hi[src] : zero;
+  if (out_lo) out_lo[dst] = in ? in_lo[src] : zero;
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, int n, int k, long long n_stride, long long k_stride, int taps,
                                     const int* __restrict__ tap_src, int b_rows, int k_pad, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo) {
@@ -840,6 +859,23 @@ int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int 
   const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
   act_unpack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f32, c, to_geom(*g), c_off, x);
   GPEMSR_LAUNCH_OK("act_unpack_nchw_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_space_to_depth(const void* in_hi, const void* in_lo, const gpemsr_geom_t* gi, int c, void* out_hi, void* out_lo,
+                          const gpemsr_geom_t* go, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!in_hi || !out_hi || !gi || !go || c <= 0 || c % 8 || (out_lo && !in_lo))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "space_to_depth: bad arguments (channels must be a multiple of 8)");
+  if ((rc = check_geom(*gi, "space_to_depth(in)")) != GPEMSR_OK || (rc = check_geom(*go, "space_to_depth(out)")) != GPEMSR_OK) return rc;
+  if (go->n != gi->n || go->h != (gi->h + 1) / 2 || go->w != (gi->w + 1) / 2)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "space_to_depth: output geometry must be ceil(h/2) x ceil(w/2)");
+  const long long total = (long long)go->n * 4 * (c / 8) * go->h * go->w;
+  space_to_depth_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)in_hi, (const uint4*)in_lo, to_geom(*gi), c / 8, (uint4*)out_hi, (uint4*)out_lo, to_geom(*go));
+  GPEMSR_LAUNCH_OK("space_to_depth_kernel");
   return GPEMSR_OK;
 }
 

@@ -36,6 +36,12 @@ class UpBlock(nn.Module):                                     # model/blocks.py:
         self.upblock = nn.ConvTranspose2d(in_channels, out_channels, 3, 2, 1, 1)
 
 
+class DownBlock(nn.Module):                                   # model/blocks.py:41-47
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.downblock = nn.Conv2d(in_channels, out_channels, 3, 2, 1)
+
+
 class NonLocalBlock(nn.Module):                               # model/blocks.py:50-59
     def __init__(self, channels):
         super().__init__()
@@ -83,36 +89,30 @@ class _Plan:
         return s
 
 
-class Decoder(nn.Module):
-    """Drop-in for ``model.decoder.Decoder`` (same ``args`` dict)."""
+class _BlockNet(nn.Module):
+    """Runs the reference's building blocks (model/blocks.py) on the implicit-GEMM kernels; shared by Decoder and Indexer*."""
 
-    def __init__(self, args, precision='fp32', compose_final=True):
-        super().__init__()
-        self.args = args
-        self.compose_final = compose_final
-        self.channel_list = args['channel_list']
-        self.num_res_blocks = args['num_resblock_per_scale']
-        self.num_input_resblck = args['num_input_resblck']
-        self.latent_dim = args['latent_dim']
-        self.use_non_local = args['use_non_local']
+    def _init_runner(self, precision):
         assert precision in ('fp32', 'bf16')
         self.precision = precision
-
-        layers = [nn.Conv2d(self.latent_dim, self.channel_list[0], 1)]
-        for _ in range(self.num_input_resblck):
-            layers.append(ResidualBlock(self.channel_list[0], self.channel_list[0]))
-        self.input_layer = nn.Sequential(*layers)
-        layers = []
-        if self.use_non_local:
-            layers.append(NonLocalBlock(self.channel_list[0]))
-        for i in range(len(self.channel_list) - 1):
-            cin, cout = self.channel_list[i], self.channel_list[i + 1]
-            for _ in range(self.num_res_blocks):
-                layers.append(ResidualBlock(cin, cin))
-            layers.append(UpBlock(cin, cout))
-        self.feat_extract = nn.Sequential(*layers)
-        self.output_layer = nn.Conv2d(self.channel_list[-1], args['im_channel'], 3, 1, 1)
         self._plans = {}
+
+    def _plan_for(self, x):
+        if not x.is_cuda:
+            from ._lib import GpemsrError
+            raise GpemsrError(-3, f'{type(self).__name__} needs CUDA tensors: there is no CPU fallback')
+        n, _, h, w = x.shape
+        key = (n, h, w, x.device.index)
+        P = self._plans.get(key)
+        if P is None:
+            P = _Plan(self, n, h, w, x.device)
+            self._plans[key] = P
+        self._last_plan = P
+        return P
+
+    def check(self):
+        """Synchronise and raise if a GEMM pipeline timed out (tests / smoke)."""
+        G.check_pipeline(self._last_plan.err)
 
     # ------------------------------------------------------------------ building blocks
     def _conv(self, P, name, mod, x, out, **kw):
@@ -165,6 +165,22 @@ class Decoder(nn.Module):
                 wt = P.weights(f'{name}.p{py}{px}', ub.upblock.weight, 'convT', taps=G.convT_phase_taps(py, px))
                 G.igemm(x, wt, P.err, split=P.split, bias=ub.upblock.bias.detach(), out=y, up=2, py=py, px=px,
                         out_f32=need_f32)
+        return y
+
+    def _down_block(self, P, name, db, x):
+        """Conv2d(k3, s2, p1) (model/blocks.py:41-47) = space-to-depth + a 2x2-tap stride-1 GEMM over 4*cin channels."""
+        g = x.geom
+        conv = db.downblock
+        og = G.Geom(g.n, (g.h + 1) // 2, (g.w + 1) // 2, True)
+        s2d = P.act(name + '.s2d', og, 4 * conv.in_channels, f32=False)
+        G.space_to_depth(x, s2d)
+        wt = P.wts.get(name)
+        if wt is None:
+            m, taps = G.down_conv_weight(conv.weight.detach())
+            wt = G.Weights(m, 'conv', taps=taps, split=P.split)
+            P.wts[name] = wt
+        y = P.act(name + '.out', og, conv.out_channels, f32=True)
+        G.igemm(s2d, wt, P.err, split=P.split, bias=conv.bias.detach(), out=y)
         return y
 
     def _non_local(self, P, name, nl, x):
@@ -227,6 +243,36 @@ class Decoder(nn.Module):
                 bias=nl.proj_out.bias.detach(), residual=x.f32, out=y)
         return y
 
+
+class Decoder(_BlockNet):
+    """Drop-in for ``model.decoder.Decoder`` (same ``args`` dict)."""
+
+    def __init__(self, args, precision='fp32', compose_final=True):
+        super().__init__()
+        self.args = args
+        self.compose_final = compose_final
+        self.channel_list = args['channel_list']
+        self.num_res_blocks = args['num_resblock_per_scale']
+        self.num_input_resblck = args['num_input_resblck']
+        self.latent_dim = args['latent_dim']
+        self.use_non_local = args['use_non_local']
+        self._init_runner(precision)
+
+        layers = [nn.Conv2d(self.latent_dim, self.channel_list[0], 1)]
+        for _ in range(self.num_input_resblck):
+            layers.append(ResidualBlock(self.channel_list[0], self.channel_list[0]))
+        self.input_layer = nn.Sequential(*layers)
+        layers = []
+        if self.use_non_local:
+            layers.append(NonLocalBlock(self.channel_list[0]))
+        for i in range(len(self.channel_list) - 1):
+            cin, cout = self.channel_list[i], self.channel_list[i + 1]
+            for _ in range(self.num_res_blocks):
+                layers.append(ResidualBlock(cin, cin))
+            layers.append(UpBlock(cin, cout))
+        self.feat_extract = nn.Sequential(*layers)
+        self.output_layer = nn.Conv2d(self.channel_list[-1], args['im_channel'], 3, 1, 1)
+
     def _final_stage(self, P, ub, x, img):
         """Last UpBlock + output conv (model/decoder.py:31,33) composed into ONE 4-phase GEMM on the up-block's input
         grid: the 64 x 16h x 16w intermediate (the largest tensor of the decoder, which the reference never returns) is not
@@ -255,15 +301,8 @@ class Decoder(nn.Module):
         return self._run(x, want_feats=False)[1]
 
     def _run(self, x, want_feats):
-        if not x.is_cuda:
-            from ._lib import GpemsrError
-            raise GpemsrError(-3, 'Decoder needs CUDA tensors: there is no CPU fallback')
+        P = self._plan_for(x)
         n, c, h, w = x.shape
-        key = (n, h, w, x.device.index)
-        P = self._plans.get(key)
-        if P is None:
-            P = _Plan(self, n, h, w, x.device)
-            self._plans[key] = P
         g = G.Geom(n, h, w, True)
         xin = P.act('in', g, c, f32=False)
         G.pack_nchw(x.float(), xin)
@@ -290,19 +329,13 @@ class Decoder(nn.Module):
                     img = torch.empty(n, self.output_layer.out_channels, 2 * cur.geom.h, 2 * cur.geom.w, dtype=torch.float32,
                                       device=x.device)
                     self._final_stage(P, mod, cur, img)
-                    self._last_plan = P
                     return feats, img
                 cur = self._up_block(P, name, mod, cur, need_f32=not last)
         img = torch.empty(n, self.output_layer.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
         wt = P.weights('output_layer', self.output_layer.weight, 'conv')
         G.igemm(cur, wt, P.err, split=P.split, bias=self.output_layer.bias.detach(), out_nchw=img,
                 nchw_c=self.output_layer.out_channels)
-        self._last_plan = P
         return feats, img
-
-    def check(self):
-        """Synchronise and raise if a GEMM pipeline timed out (tests / smoke)."""
-        G.check_pipeline(self._last_plan.err)
 
 
 class _View:

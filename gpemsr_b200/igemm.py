@@ -260,6 +260,31 @@ def unpack_nchw(act, c=None, c_off=0):
     return out
 
 
+def space_to_depth(x, out):
+    """x: Act with c channels (c % 8 == 0) at h x w -> out: Act with 4*c channels at ceil(h/2) x ceil(w/2) (planes only)."""
+    gi, go = x.geom.c, out.geom.c
+    _lib.check(_lib.lib().gpemsr_space_to_depth(_lib.ptr(x.hi), _lib.ptr(x.lo), C.byref(gi), x.c, _lib.ptr(out.hi),
+                                                _lib.ptr(out.lo), C.byref(go), _lib.stream_ptr()))
+
+
+def down_conv_weight(w):
+    """Conv2d(k3, s2, p1) weight [co, ci, 3, 3] (model/blocks.py:44) -> [co, 4*ci, 2, 2] acting on the space-to-depth input:
+    input row 2y + dy (dy = ky - 1) is phase p = dy & 1 of s2d row y + (dy - p) / 2, i.e. s2d offset sy in {-1, 0}; the
+    (p = 0, sy = -1) combinations do not occur and stay zero.  Returns (weight, taps) for ``Weights(kind='conv')``."""
+    co, ci = w.shape[0], w.shape[1]
+    m = torch.zeros(co, 4 * ci, 2, 2, dtype=torch.float32, device=w.device)
+    for ky in range(3):
+        py = (ky - 1) & 1
+        sy = (ky - 1 - py) // 2
+        for kx in range(3):
+            px = (kx - 1) & 1
+            sx = (kx - 1 - px) // 2
+            ph = py * 2 + px
+            m[:, ph * ci:(ph + 1) * ci, sy + 1, sx + 1] = w[:, :, ky, kx]
+    taps = [(a * 2 + b, a - 1, b - 1) for a in range(2) for b in range(2)]
+    return m, taps
+
+
 class GroupNormScratch:
     def __init__(self, n, c, device):
         self.sums = torch.zeros(n, c, 2, dtype=torch.float64, device=device)

@@ -154,6 +154,12 @@ GPEMSR_API int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* 
                          float* f32, void* hi, void* lo, gpemsr_stream_t stream);
 GPEMSR_API int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int c_off, float* x,
                            gpemsr_stream_t stream);
+/* Space-to-depth of bf16 operand planes for stride-2 convolutions (DownBlock, model/blocks.py:41-47: Conv2d(k3, s2, p1)):
+ * channel block (p*2 + q) of output pixel (y, x) = input pixel (2y + p, 2x + q), zero past an odd edge; c % 8 == 0; the
+ * output holds 4*c channels on the ceil(h/2) x ceil(w/2) grid.  The stride-2 conv is then a 2x2-tap (offsets {-1,0}^2)
+ * stride-1 gpemsr_igemm() over it. */
+GPEMSR_API int gpemsr_space_to_depth(const void* in_hi, const void* in_lo, const gpemsr_geom_t* in_geom, int c,
+                          void* out_hi, void* out_lo, const gpemsr_geom_t* out_geom, gpemsr_stream_t stream);
 /* weights -> B operand planes.  src element (col n, k, tap t) = w[n * n_stride + k * k_stride + tap_src[t]].
  * Conv2d weight [co, ci, kh, kw]: n_stride = ci*kh*kw, k_stride = kh*kw ; ConvTranspose2d [ci, co, kh, kw]:
  * n_stride = kh*kw, k_stride = co*kh*kw ; Linear [n, k]: n_stride = k, k_stride = 1, one tap. */

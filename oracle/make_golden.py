@@ -176,6 +176,27 @@ def gen_flow_warp(ref):
     _save('flow_warp_small', **arrs)
 
 
+def gen_indexer(ref):
+    from model.indexer import Indexer16, Indexer8
+    out = {}
+    # small widths, every layer kind: channel-changing ResidualBlocks, NonLocalBlock, the DownBlock of Indexer8 (i == 3, on an
+    # odd-sized input) and the ResidualBlock + UpBlock tail Indexer16 appends for 4-entry channel lists
+    cases = [('i16', Indexer16, 16, [32, 32, 64, 64, 64], (2, 1, 6, 7), 61),
+             ('i8', Indexer8, 8, [32, 32, 64, 64, 64], (2, 1, 9, 7), 63),
+             ('i16up', Indexer16, 16, [32, 64, 64, 64], (1, 1, 5, 6), 65)]
+    for tag, cls, variant, cl, shape, seed in cases:
+        cfg = dict(channel_list=cl, im_channel=1, num_resblock_per_scale=2, num_output_resblck=1, latent_dim=64, use_non_local=True)
+        m = cls(cfg).eval()
+        _load_into(m, W.fill(W.indexer_spec(variant, cl, 1, 2, 1, 64, True), seed=seed))
+        g = torch.Generator().manual_seed(seed + 1)
+        x = torch.rand(shape, generator=g)                      # EM intensities are in [0, 1]
+        with torch.no_grad():
+            feat = m.output_layer(m.feat_extract(m.input_layer(x)))
+            logits = m(x)
+        out.update({f'{tag}_x': _np(x), f'{tag}_feat': _np(feat), f'{tag}_logits': _np(logits)})
+    _save('indexer_small', **out, seeds=np.array([61, 63, 65]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference/GPEMSR-CREMI/GPEMSR')
@@ -184,7 +205,7 @@ def main():
     sys.path.insert(0, a.ref)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gens = dict(codebook=gen_codebook, decoder=gen_decoder, blocks=gen_blocks, tail=gen_tail,
-                flow_warp=gen_flow_warp)
+                flow_warp=gen_flow_warp, indexer=gen_indexer)
     for n, fn in gens.items():
         if a.only and n not in a.only.split(','):
             continue

@@ -202,3 +202,48 @@ def ref_extract_from_feat(feat, sd_indexer_head, emb, sd_decoder, **dec_kw):
     logits = indexer_logits(feat, sd_indexer_head['embedding.weight'], sd_indexer_head['embedding.bias'])
     zq, idx = codebook_inference_lr(logits, emb)
     return decoder_multi_scale(zq, sd_decoder, **dec_kw), idx
+
+
+# --------------------------------------------------------------------------- #
+# the Indexer conv stack in front of a-2
+# --------------------------------------------------------------------------- #
+def down_block(x, sd):
+    """``DownBlock.forward`` -- model/blocks.py:41-47 (Conv2d k3, s2, p1)."""
+    return F.conv2d(x, sd['downblock.weight'], sd['downblock.bias'], 2, 1)
+
+
+def indexer_features(x, sd):
+    """``output_layer(feat_extract(input_layer(x)))`` of ``Indexer16`` / ``Indexer8`` -- model/indexer.py:51-52 / 98-99.
+
+    The layer kinds are read off the parameter names (the module lists of :21-37 / 72-86 in order), so one function
+    serves both variants and every channel list.  Returns feat f32[B, latent_dim, h, w].
+    """
+    h = F.relu(F.conv2d(x, sd['input_layer.0.weight'], sd['input_layer.0.bias'], 1, 1))      # :10-11
+    li = 0
+    while any(k.startswith(f'feat_extract.{li}.') for k in sd):
+        p = _sub(sd, f'feat_extract.{li}.')
+        if 'downblock.weight' in p:
+            h = down_block(h, p)
+        elif 'upblock.weight' in p:
+            h = up_block(h, p)
+        elif 'q.weight' in p:
+            h = non_local_block(h, p)
+        else:
+            h = residual_block(h, p)
+        li += 1
+    i = 0
+    while f'output_layer.{i}.block.0.weight' in sd:                                          # :40-43
+        h = residual_block(h, _sub(sd, f'output_layer.{i}.'))
+        i += 1
+    return F.conv2d(h, sd[f'output_layer.{i}.weight'], sd[f'output_layer.{i}.bias'])
+
+
+def indexer_forward(x, sd):
+    """``Indexer*.forward`` -- model/indexer.py:51-55 / 98-102: logits f32[B, h, w, 1024]."""
+    return indexer_logits(indexer_features(x, sd), sd['embedding.weight'], sd['embedding.bias'])
+
+
+def ref_extract(imgs, sd_indexer, emb, sd_decoder, **dec_kw):
+    """``lrGenerator{8,16}.ref_extract`` -- model/vqgan_indexer.py:44-48 / 87-91."""
+    zq, idx = codebook_inference_lr(indexer_forward(imgs, sd_indexer), emb)
+    return decoder_multi_scale(zq, sd_decoder, **dec_kw), idx

@@ -129,3 +129,39 @@ def codebook_spec(num_codes=1024, latent_dim=512):
 def indexer_head_spec(latent_dim=512, num_codes=1024):
     return OrderedDict([('embedding.weight', ('linear', (num_codes, latent_dim))),
                         ('embedding.bias', ('bias', (num_codes,)))])
+
+
+def indexer_spec(variant=16, channel_list=(64, 64, 128, 256, 512), im_channel=1, num_res_blocks=2, num_output_resblck=3,
+                 latent_dim=512, use_non_local=True, num_codes=1024):
+    """Parameter names/shapes of ``Indexer16`` / ``Indexer8`` -- model/indexer.py:6-47 / 58-96."""
+    spec = OrderedDict()
+    _conv(spec, 'input_layer.0', channel_list[0], im_channel, 3)
+    down_at = 4 if variant == 16 else 3
+    li = 0
+    for i in range(len(channel_list) - 1):
+        cin, cout = channel_list[i], channel_list[i + 1]
+        for _ in range(num_res_blocks - 1):
+            _resblock(spec, f'feat_extract.{li}', cin, cin)
+            li += 1
+        if i == down_at:
+            _conv(spec, f'feat_extract.{li}.downblock', cout, cin, 3)
+        else:
+            _resblock(spec, f'feat_extract.{li}', cin, cout)
+        li += 1
+    c = channel_list[-1]
+    if variant == 16 and len(channel_list) == 4:
+        for _ in range(num_res_blocks - 1):
+            _resblock(spec, f'feat_extract.{li}', c, c)
+            li += 1
+        spec[f'feat_extract.{li}.upblock.weight'] = ('convT', (c, c, 3, 3))
+        spec[f'feat_extract.{li}.upblock.bias'] = ('bias', (c,))
+        li += 1
+    if use_non_local:
+        _nonlocal(spec, f'feat_extract.{li}', c)
+        li += 1
+    for i in range(num_output_resblck):
+        _resblock(spec, f'output_layer.{i}', c, c)
+    _conv(spec, f'output_layer.{num_output_resblck}', latent_dim, c, 1)
+    spec['embedding.weight'] = ('linear', (num_codes, latent_dim))
+    spec['embedding.bias'] = ('bias', (num_codes,))
+    return spec

@@ -117,3 +117,16 @@ def test_flow_warp_kats():
     assert np.allclose(out_b, exp_b, atol=2e-6)
     exp_z = exp_b.copy(); exp_z[:, :, 0, :] = 0; exp_z[:, :, :, 7:] = 0
     assert np.allclose(out_z, exp_z, atol=2e-6)
+
+
+INDEXER_CASES = [('i16', 16, [32, 32, 64, 64, 64], 0), ('i8', 8, [32, 32, 64, 64, 64], 1), ('i16up', 16, [32, 64, 64, 64], 2)]
+
+
+def test_indexer_small_bitexact(golden):
+    """Indexer16 / Indexer8 conv stacks (model/indexer.py), incl. DownBlock on an odd-sized input and the UpBlock tail."""
+    g = golden('indexer_small')
+    for tag, variant, cl, si in INDEXER_CASES:
+        sd = W.fill(W.indexer_spec(variant, cl, 1, 2, 1, 64, True), seed=int(g['seeds'][si]))
+        feat = R.indexer_features(T(g[f'{tag}_x']), sd)
+        assert np.array_equal(feat.numpy(), g[f'{tag}_feat']), tag
+        assert np.array_equal(R.indexer_forward(T(g[f'{tag}_x']), sd).numpy(), g[f'{tag}_logits']), tag
