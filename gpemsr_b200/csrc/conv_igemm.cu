@@ -274,14 +274,30 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   const int sms = gpemsr::num_sms();
-  long long gx = std::min<long long>(op.m_tiles, sms);
-  long long gy = 1;
-  if (op.m_tiles < sms) gy = std::min<long long>(op.n_tiles, (sms + op.m_tiles - 1) / op.m_tiles);
-  if (BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters()) {
+  const bool clustered = BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters();
+  // grid: gx persistent row-tile walkers x gy column-tile splitters.  Model: one CTA per SM, CTAs run in waves, a CTA's
+  // time = its (row tile, column tile) count.  Take the cheapest shape (e.g. 50 row tiles x 25 column tiles: 50 x 5 CTAs
+  // = 2 waves x 5 units, not 50 x 3 = 150 CTAs whose 2 stragglers double the time); ties go to fewer column splits
+  // (every split re-reads the A tiles).
+  long long gx = std::min<long long>(op.m_tiles, sms), gy = 1;
+  {
+    // fixed cost of a CTA (launch, TMEM allocation, pipeline fill, un-overlapped last epilogue) ~ 3 us, in tile units
+    const double tile_us = (double)op.taps * (op.k / 16) * SPLIT * (BLOCK_N / 2) / 1900.0;
+    const double overhead = 3.0 / std::max(tile_us, 0.05);
+    double best = -1.0;
+    const long long gx_max = std::min<long long>(op.m_tiles, sms);
+    for (long long y = 1; y <= op.n_tiles; ++y)
+      for (long long x = clustered ? 2 : 1; x <= (clustered ? (gx_max + 1) / 2 * 2 : gx_max); x += clustered ? 2 : 1) {
+        const long long waves = (x * y + sms - 1) / sms;
+        const long long per = ((op.m_tiles + x - 1) / x) * ((op.n_tiles + y - 1) / y);
+        const double cost = (double)waves * ((double)per + overhead);
+        if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && (y < gy || (y == gy && x > gx)))) { best = cost; gx = x; gy = y; }
+      }
+  }
+  if (clustered) {
     // wide tiles are bound by operand traffic out of L2: pairs of CTAs share every B stage by multicast
     auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, Epi, 2>;
     GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    gx = (gx + 1) / 2 * 2;
     GPEMSR_CUDA_OK(gpemsr::launch_cluster(kern, dim3((unsigned)gx, (unsigned)gy), dim3(gemm::num_threads<Epi>()), Cfg::SMEM_BYTES, s, 2, op, e));
     gpemsr::count_launch();
     return GPEMSR_OK;

@@ -45,6 +45,8 @@ struct Operands {
   int n_tiles;                 // number of BLOCK_N column tiles
   long long a_row0;            // row of A that tile 0 / row 0 maps to (so shifts may be negative)
   int* err_flag;               // device int, set non-zero on a pipeline time-out
+  long long b_batch_elems;     // batched (block-diagonal) GEMM: row tile m uses B + (m / batch_tiles) * b_batch_elems (bf16
+  int batch_tiles;             //   elements, both planes); batch_tiles == 0: one B for every row tile.  Streaming kernel only.
   // ---- tap-fused mode (gemm_tapfuse_kernel): B resident in smem, A fetched once per k-slab as <= 3 row segments
   int n_seg;                   // distinct tap dy values
   int seg_row_off[3];          // first A row of segment s relative to the tile's first row (dy * wp + dx_min)
@@ -148,10 +150,11 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     for (long long i = 0; i < n_iter && ok; ++i) {
       const long long m_tile = min(blockIdx.x + i * gridDim.x, op.m_tiles - 1);
       const __nv_bfloat16* a_tile = (plane ? op.a_lo : op.a_hi) + ((long long)kc * op.a_rows + op.a_row0 + m_tile * BLOCK_M) * 8;
+      const long long b_batch = op.batch_tiles ? (m_tile / op.batch_tiles) * op.b_batch_elems : 0;
       for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
         const __nv_bfloat16* b_src;
         if (op.b_packed) b_src = op.b_hi + (long long)n_tile * op.taps * kiters_per_tap * b_kstep + crank * (b_part / 2);
-        else b_src = (plane ? op.b_lo : op.b_hi) + ((long long)kc * op.b_rows + (long long)n_tile * BLOCK_N) * 8;
+        else b_src = (plane ? op.b_lo : op.b_hi) + ((long long)kc * op.b_rows + (long long)n_tile * BLOCK_N) * 8 + b_batch;
         for (int tap = 0; tap < op.taps && ok; ++tap) {
           const __nv_bfloat16* a_src = a_tile + (long long)op.a_row_off[tap] * 8;
           for (int kci = 0; kci < kiters_per_tap; ++kci) {
