@@ -75,6 +75,9 @@ struct EpiConv {
   long long ld;
   double* gn_sums;
   int gn_cpg;
+  const float* patch_other;   // fp32 cells in the output geometry: the tensor the stored values are correlated with
+  float* patch_sums;          // [n][h / patch][w / patch][3] = (sum v*o, sum v*v, sum o*o) per patch x patch block of pixels
+  int patch_size;
 
   static constexpr int WARPS = BLOCK_N >= 64 ? 8 : 4;
   struct State {
@@ -83,6 +86,7 @@ struct EpiConv {
     float row_bias = 0.f;
     long long orow = 0;        // output row of (up*y + py, up*x + px) in the blocked outputs
     long long nchw0 = 0;       // offset of (img, channel 0, Y, X) in out_nchw
+    float p_ab = 0.f, p_aa = 0.f, p_bb = 0.f;      // patch-correlation partial sums of this row (patch_sums)
   };
 
   // one cell = 8 consecutive output channels of one output pixel; (dy, dx) only differ from 0 under PixelShuffle
@@ -147,7 +151,7 @@ struct EpiConv {
   }
 
   template <int CHUNK>
-  __device__ __forceinline__ void chunk(const State& st, const uint32_t (&r)[CHUNK], int col0, long long rel) const {
+  __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], int col0, long long rel) const {
     float f[CHUNK];
     const bool full = col0 + CHUNK <= n_cols;
     // v = scale * acc + bias  (flag tests are hoisted out of the column loops: they are uniform for the launch)
@@ -185,6 +189,21 @@ struct EpiConv {
       group_stats<CHUNK>(st, f, col0);
     }
     if (!st.valid) return;
+    if (patch_sums) {
+#pragma unroll
+      for (int g = 0; g < CHUNK / 8; ++g) {
+        if (col0 + 8 * g >= n_cols) break;
+        const size_t cell = ((size_t)((c_off + col0 + 8 * g) >> 3) * og.rows_alloc + st.orow) * 8;
+        const float4 o0 = __ldg(reinterpret_cast<const float4*>(patch_other + cell));
+        const float4 o1 = __ldg(reinterpret_cast<const float4*>(patch_other + cell + 4));
+        const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = f[8 * g + j];
+          st.p_ab = fmaf(a, o[j], st.p_ab); st.p_aa = fmaf(a, a, st.p_aa); st.p_bb = fmaf(o[j], o[j], st.p_bb);
+        }
+      }
+    }
     if (out_rowmajor) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 4)
@@ -259,6 +278,29 @@ struct EpiConv {
       const int col0 = n_tile * BLOCK_N + c0;
       if ((st.valid || gn_sums) && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
     }
+    if (patch_sums) flush_patch(st);
+  }
+
+  // The 32 lanes of a warp are 32 consecutive flat rows: pixels of the same patch row form contiguous runs.  A segmented
+  // shuffle reduction leaves each run's total in its first lane, which adds it to the patch's three accumulators.
+  __device__ __forceinline__ void flush_patch(State& st) const {
+    const int lane = threadIdx.x & 31;
+    const int ppr = ag.w / patch_size;
+    const int run = st.valid ? (st.img * ag.h + st.y) * ppr + st.x / patch_size : -1;     // unique per (image row, patch column)
+    float ab = st.p_ab, aa = st.p_aa, bb = st.p_bb;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int ro = __shfl_down_sync(0xffffffffu, run, off);
+      const float t0 = __shfl_down_sync(0xffffffffu, ab, off), t1 = __shfl_down_sync(0xffffffffu, aa, off),
+                  t2 = __shfl_down_sync(0xffffffffu, bb, off);
+      if (lane + off < 32 && ro == run) { ab += t0; aa += t1; bb += t2; }
+    }
+    const int rprev = __shfl_up_sync(0xffffffffu, run, 1);
+    if (run >= 0 && (lane == 0 || rprev != run)) {
+      float* dst = patch_sums + ((size_t)(st.img * (ag.h / patch_size) + st.y / patch_size) * ppr + st.x / patch_size) * 3;
+      atomicAdd(dst, ab); atomicAdd(dst + 1, aa); atomicAdd(dst + 2, bb);
+    }
+    st.p_ab = st.p_aa = st.p_bb = 0.f;
   }
 };
 
@@ -273,6 +315,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
+  e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   const int sms = gpemsr::num_sms();
   const bool clustered = BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters();
   // grid: gx persistent row-tile walkers x gy column-tile splitters.  Model: one CTA per SM, CTAs run in waves, a CTA's
@@ -319,6 +362,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
+  e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
@@ -396,6 +440,54 @@ __global__ void act_unpack_nchw_kernel(const float* __restrict__ f32, int c, Geo
     const int ch = cc * 8 + j;
     if (ch < c) x[((long long)img * c + ch) * hw + p] = v[j];
   }
+}
+
+// ---- VGG19 conv1_1 on a one-channel image (the three input channels of the reference are copies of each other, so their
+// weights are summed on the host): thread = pixel, 9 loads shared by all output channels, one 16-byte (hi, lo) cell pair per 8
+// channels.  Weights / bias are broadcast reads from shared memory.
+__global__ void __launch_bounds__(256)
+conv3x3_c1_relu_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ bias, int co, Geom g,
+                       uint4* __restrict__ out_hi, uint4* __restrict__ out_lo) {
+  __shared__ float sw[64 * 9 + 64];
+  for (int i = threadIdx.x; i < co * 9; i += blockDim.x) sw[i] = w1[i];
+  for (int i = threadIdx.x; i < co; i += blockDim.x) sw[64 * 9 + i] = bias[i];
+  __syncthreads();
+  const long long hw = (long long)g.h * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)g.n * hw) return;
+  const int img = (int)(t / hw), y = (int)((t % hw) / g.w), xx = (int)(t % g.w);
+  const float* p = x + (long long)img * hw;
+  float v[9];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int yy = y + dy, xc = xx + dx;
+      v[(dy + 1) * 3 + dx + 1] = (yy >= 0 && yy < g.h && xc >= 0 && xc < g.w) ? __ldg(p + (long long)yy * g.w + xc) : 0.f;
+    }
+  const long long row = place_row(g, img, y, xx);
+  for (int cc = 0; cc < co / 8; ++cc) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wj = sw + (cc * 8 + j) * 9;
+      float a = sw[64 * 9 + cc * 8 + j];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(v[k], wj[k], a);
+      o[j] = fmaxf(a, 0.f);
+    }
+    uint4 hi, lo;
+    split8(o, hi, lo);
+    out_hi[(size_t)cc * g.rows_alloc + row] = hi;
+    if (out_lo) out_lo[(size_t)cc * g.rows_alloc + row] = lo;
+  }
+}
+
+__global__ void patch_cosine_kernel(const float* __restrict__ s, long long n, float eps, float* __restrict__ mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ab = s[3 * i], na = fmaxf(sqrtf(s[3 * i + 1]), eps), nb = fmaxf(sqrtf(s[3 * i + 2]), eps);
+  mask[i] = ab / (na * nb);
 }
 
 // space-to-depth of the bf16 operand planes (stride-2 convolutions, model/blocks.py:41-47 DownBlock): output pixel (y, x) of
@@ -774,6 +866,15 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
     GPEMSR_CUDA_OK(cudaMemsetAsync(d.gn_sums, 0, (size_t)d.a_geom.n * (d.n_cols / g) * 2 * sizeof(double), (cudaStream_t)stream));
   }
 
+  if (d.patch_sums) {
+    const int ps = d.patch_size;
+    if (!d.patch_other || ps <= 0 || d.a_geom.h % ps || d.a_geom.w % ps || d.up != 1 || d.pixel_shuffle || d.phase_cols)
+      return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: patch_sums needs patch_other, a same-resolution output and h, w divisible by patch_size");
+    if ((rc = check_geom(d.o_geom, "igemm(patch)")) != GPEMSR_OK) return rc;
+    GPEMSR_CUDA_OK(cudaMemsetAsync(d.patch_sums, 0, (size_t)d.a_geom.n * (d.a_geom.h / ps) * (d.a_geom.w / ps) * 3 * sizeof(float),
+                                   (cudaStream_t)stream));
+  }
+
   const int block_n = pick_block_n(d);
   gemm::Operands op{};
   op.a_hi = (const __nv_bfloat16*)d.a_hi; op.a_lo = (const __nv_bfloat16*)d.a_lo;
@@ -875,6 +976,32 @@ int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int 
   const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
   act_unpack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f32, c, to_geom(*g), c_off, x);
   GPEMSR_LAUNCH_OK("act_unpack_nchw_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_conv3x3_c1_relu(const float* x, const float* w1, const float* bias, int co, const gpemsr_geom_t* g, void* out_hi,
+                           void* out_lo, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x || !w1 || !bias || !g || !out_hi || co <= 0 || co % 8 || co > 64)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "conv3x3_c1_relu: bad arguments (co must be a multiple of 8, <= 64)");
+  if ((rc = check_geom(*g, "conv3x3_c1_relu")) != GPEMSR_OK) return rc;
+  const long long total = (long long)g->n * g->h * g->w;
+  conv3x3_c1_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w1, bias, co, to_geom(*g),
+                                                                                          (uint4*)out_hi, (uint4*)out_lo);
+  GPEMSR_LAUNCH_OK("conv3x3_c1_relu_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_patch_cosine(const float* patch_sums, int64_t n, float eps, float* mask, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (n == 0) return GPEMSR_OK;
+  if (!patch_sums || !mask || n < 0) return set_error(GPEMSR_ERR_BAD_SHAPE, "patch_cosine: bad arguments");
+  patch_cosine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(patch_sums, n, eps, mask);
+  GPEMSR_LAUNCH_OK("patch_cosine_kernel");
   return GPEMSR_OK;
 }
 

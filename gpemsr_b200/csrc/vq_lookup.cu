@@ -546,7 +546,11 @@ vq_finish(const float* __restrict__ z, const float* __restrict__ w, const float*
   __syncthreads();
   const int npairs = s_npairs, nover = s_nover;
 
-  if (npairs > 0) {
+  // rows whose sub-lists overflowed (many near-tied codes: the tail of the append-count distribution) are scanned against
+  // ALL codes; their partial dot products live in s_ovdot and are accumulated tile by tile like the pair scores
+  __shared__ float s_ovbest[NW];
+  __shared__ int s_ovbestk[NW];
+  if (npairs > 0 || nover > 0) {
     for (int d0 = 0; d0 < d; d0 += FZ_D) {
       const int dn = min(FZ_D, d - d0);
       const float* zb = z + (bi * d + d0) * hw + p0 + (lane < nrows ? lane : 0);
@@ -589,6 +593,41 @@ vq_finish(const float* __restrict__ z, const float* __restrict__ w, const float*
         for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) s_score[p] = d0 ? s_score[p] + acc : acc;
       }
+      if (d <= FZ_D) {                      // single tile (every model shape): overflow rows scan all codes from the staged tile
+        for (int o = 0; o < nover; ++o) {
+          const int r = s_over[o];
+          const float zzr = zz[row0 + r];
+          const float* zr = zt + r * FZ_LD;
+          float bs = INFINITY;
+          int bk = 0x7fffffff;
+          for (int kk = warp; kk < k; kk += NW) {          // ascending per warp: the first minimum is the lowest index
+            const float* wk = w + (size_t)kk * d;
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < FZ_D / 128; ++u) {
+              const int dd = 128 * u + 4 * lane;
+              if (dd < dn) {
+                const float4 a4 = *reinterpret_cast<const float4*>(zr + dd);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(wk + dd));
+                acc = fmaf(a4.x, b4.x, acc); acc = fmaf(a4.y, b4.y, acc); acc = fmaf(a4.z, b4.z, acc); acc = fmaf(a4.w, b4.w, acc);
+              }
+            }
+#pragma unroll
+            for (int of = 16; of; of >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, of);
+            const float sc = score_of(acc, mode, zzr, c[kk]);
+            if (sc < bs) { bs = sc; bk = kk; }
+          }
+          if (lane == 0) { s_ovbest[warp] = bs; s_ovbestk[warp] = bk; }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            float b = INFINITY; int bkk = 0x7fffffff;
+            for (int wv = 0; wv < NW; ++wv)
+              if (s_ovbest[wv] < b || (s_ovbest[wv] == b && s_ovbestk[wv] < bkk)) { b = s_ovbest[wv]; bkk = s_ovbestk[wv]; }
+            s_idx[r] = bkk == 0x7fffffff ? 0 : bkk;
+          }
+          __syncthreads();
+        }
+      }
     }
     __syncthreads();
     if (threadIdx.x < nrows) {
@@ -605,8 +644,8 @@ vq_finish(const float* __restrict__ z, const float* __restrict__ w, const float*
       }
     }
   }
-  // rows whose sub-lists overflowed (many duplicated / near-tied codes; rare): exact scan of ALL codes, z read in place
-  for (int o = 0; o < nover; ++o) {
+  // multi-tile channel counts (d > FZ_D; no model shape): overflow rows read z in place
+  for (int o = 0; o < (d > FZ_D ? nover : 0); ++o) {
     __shared__ float s_wbest[NW];
     __shared__ int s_wbestk[NW];
     const int r = s_over[o];

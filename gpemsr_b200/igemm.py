@@ -34,6 +34,7 @@ class IgemmDesc(C.Structure):
                 ('out_nchw', C.c_void_p), ('nchw_c', C.c_int32),
                 ('out_rowmajor', C.c_void_p), ('ld', C.c_int64),
                 ('gn_sums', C.c_void_p), ('gn_cpg', C.c_int32),
+                ('patch_other', C.c_void_p), ('patch_sums', C.c_void_p), ('patch_size', C.c_int32),
                 ('err_flag', C.c_void_p)]
 
 
@@ -208,7 +209,8 @@ def _p(t):
 def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row=False, act=ACT_NONE, slope=0.0,
           residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, phase_cols=0, c_off=0,
           out_f32=True, out_planes=True, out_nchw=None, nchw_c=0, out_rowmajor=None, ld=0,
-          b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None, gn_sums=None, gn_cpg=0):
+          b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None, gn_sums=None, gn_cpg=0,
+          patch_other=None, patch_sums=None, patch_size=0):
     """One fused implicit-GEMM launch.  `a`: Act (A operand); `w`: Weights or None when b_* are given explicitly;
     `out`: Act receiving fp32 master / planes (whichever it owns and the flags allow)."""
     d = IgemmDesc()
@@ -240,6 +242,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
     d.out_nchw, d.nchw_c = _p(out_nchw), nchw_c
     d.out_rowmajor, d.ld = _p(out_rowmajor), ld
     d.gn_sums, d.gn_cpg = _p(gn_sums), gn_cpg
+    d.patch_other, d.patch_sums, d.patch_size = _p(patch_other), _p(patch_sums), patch_size
     d.err_flag = _p(err)
     _lib.check(_lib.lib().gpemsr_igemm(C.byref(d), _lib.stream_ptr()))
 

@@ -144,6 +144,12 @@ typedef struct gpemsr_igemm_desc {
   double* gn_sums; int32_t gn_cpg;          /* optional fused GroupNorm statistics of the stored values: [n][n_cols/gn_cpg][2]
                                                doubles (sum, sum of squares per image and group of gn_cpg channels), zeroed by
                                                the call; gn_cpg in {1,2,4,8,16,32} */
+  const float* patch_other; float* patch_sums; int32_t patch_size;
+                                            /* optional fused patch correlation (the VGG relu1_2 similarity mask,
+                                               model/GPEMSR.py:345-353): patch_other = fp32 cells of a second tensor in the
+                                               output geometry; patch_sums [n][h/ps][w/ps][3] receives, per ps x ps pixel block
+                                               and over all n_cols channels, (sum v*o, sum v*v, sum o*o) of the stored values v;
+                                               zeroed by the call; needs up == 1 and h, w divisible by patch_size */
   int32_t* err_flag;                        /* device int: set when the pipeline times out (never hangs) */
 } gpemsr_igemm_desc_t;
 
@@ -154,6 +160,15 @@ GPEMSR_API int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* 
                          float* f32, void* hi, void* lo, gpemsr_stream_t stream);
 GPEMSR_API int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int c_off, float* x,
                            gpemsr_stream_t stream);
+/* First VGG19 layer on a one-channel image (model/VGG.py:21 slice1.0 applied to `img.expand(-1, 3, -1, -1)`,
+ * model/GPEMSR.py:345,349): y = relu(conv3x3(x, w1) + bias) with w1[co][ky][kx] = sum over the 3 identical input channels
+ * of the reference weight, zero padding 1.  x fp32 [n, 1, h, w] (reference layout); output = bf16 (hi, lo) operand planes
+ * with `co` channels (multiple of 8, <= 64) in geometry g (padded).  CUDA cores: 9 MACs per output, HBM bound. */
+GPEMSR_API int gpemsr_conv3x3_c1_relu(const float* x, const float* w1 /*[co][9]*/, const float* bias /*[co]*/, int co,
+                           const gpemsr_geom_t* g, void* out_hi, void* out_lo, gpemsr_stream_t stream);
+/* mask[i] = s0 / (max(sqrt(s1), eps) * max(sqrt(s2), eps)) over the n triples of a patch_sums buffer: the cosine similarity of
+ * F.normalize()d patch vectors (model/GPEMSR.py:346-351). */
+GPEMSR_API int gpemsr_patch_cosine(const float* patch_sums, int64_t n, float eps, float* mask, gpemsr_stream_t stream);
 /* Space-to-depth of bf16 operand planes for stride-2 convolutions (DownBlock, model/blocks.py:41-47: Conv2d(k3, s2, p1)):
  * channel block (p*2 + q) of output pixel (y, x) = input pixel (2y + p, 2x + q), zero past an odd edge; c % 8 == 0; the
  * output holds 4*c channels on the ceil(h/2) x ceil(w/2) grid.  The stride-2 conv is then a 2x2-tap (offsets {-1,0}^2)

@@ -197,6 +197,31 @@ def gen_indexer(ref):
     _save('indexer_small', **out, seeds=np.array([61, 63, 65]))
 
 
+def gen_vgg_mask(ref):
+    """The mask lines of the reference forward (model/GPEMSR.py:344-353) executed with the reference's own ``VGG19``
+    (model/VGG.py, random-init through the shim that neutralises its checkpoint load) and ``extract_image_patches``."""
+    import torch.nn.functional as F
+    M = basicsr_shim.install(ref)
+    from model.VGG import VGG19
+    vgg = VGG19().eval()
+    M._oracle_restore()
+    sd = W.fill(W.vgg_slice1_spec(), seed=81)
+    own = vgg.slice1.state_dict()
+    assert list(own.keys()) == ['0.weight', '0.bias', '2.weight', '2.bias']
+    vgg.slice1.load_state_dict({k[len('slice1.'):]: v for k, v in sd.items()}, strict=True)
+    g = torch.Generator().manual_seed(82)
+    x = torch.rand(3, 1, 4, 6, generator=g)                                # LR frames
+    ref_img = torch.rand(3, 1, 64, 96, generator=g)                        # the decoder's x16 image
+    with torch.no_grad():
+        up_lr = F.interpolate(x, scale_factor=16, mode='bilinear', align_corners=False)                    # :344
+        r12 = getattr(vgg(ref_img.expand(-1, 3, -1, -1)), 'relu1_2')                                       # :345
+        a = F.normalize(M.extract_image_patches(r12, ksizes=[16, 16], strides=[16, 16], rates=[1, 1], padding='same'), dim=1)
+        lr12 = getattr(vgg(up_lr.expand(-1, 3, -1, -1)), 'relu1_2')                                        # :349
+        b = F.normalize(M.extract_image_patches(lr12, ksizes=[16, 16], strides=[16, 16], rates=[1, 1], padding='same'), dim=1)
+        mask = torch.sum(a.contiguous() * b.contiguous(), dim=1, keepdim=True).view(3, 1, 4, 6)           # :352-353
+    _save('vgg_mask_small', x=_np(x), ref_img=_np(ref_img), relu1_2=_np(r12[:1, :, :16, :16]), mask=_np(mask), seed=np.array([81]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference/GPEMSR-CREMI/GPEMSR')
@@ -205,7 +230,7 @@ def main():
     sys.path.insert(0, a.ref)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gens = dict(codebook=gen_codebook, decoder=gen_decoder, blocks=gen_blocks, tail=gen_tail,
-                flow_warp=gen_flow_warp, indexer=gen_indexer)
+                flow_warp=gen_flow_warp, indexer=gen_indexer, vgg_mask=gen_vgg_mask)
     for n, fn in gens.items():
         if a.only and n not in a.only.split(','):
             continue

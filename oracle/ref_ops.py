@@ -247,3 +247,34 @@ def ref_extract(imgs, sd_indexer, emb, sd_decoder, **dec_kw):
     """``lrGenerator{8,16}.ref_extract`` -- model/vqgan_indexer.py:44-48 / 87-91."""
     zq, idx = codebook_inference_lr(indexer_forward(imgs, sd_indexer), emb)
     return decoder_multi_scale(zq, sd_decoder, **dec_kw), idx
+
+
+# --------------------------------------------------------------------------- #
+# SURVEY.md 8(f)-1: VGG19 relu1_2 patch-similarity mask
+# --------------------------------------------------------------------------- #
+def vgg_relu1_2(x3, sd):
+    """``VGG19.forward(X).relu1_2`` -- model/VGG.py:21-22, 39-40 (slice1 = conv, ReLU, conv, ReLU)."""
+    h = F.relu(F.conv2d(x3, sd['slice1.0.weight'], sd['slice1.0.bias'], 1, 1))
+    return F.relu(F.conv2d(h, sd['slice1.2.weight'], sd['slice1.2.bias'], 1, 1))
+
+
+def image_patches(x, k):
+    """``extract_image_patches(x, [k, k], [k, k], [1, 1], 'same')`` for sizes divisible by k (no padding is added then) --
+    model/GPEMSR.py:14-60: [N, C*k*k, L]."""
+    assert x.shape[2] % k == 0 and x.shape[3] % k == 0
+    return F.unfold(x, kernel_size=k, dilation=1, padding=0, stride=k)
+
+
+def patch_similarity(ref_img, other_img, sd, k=16):
+    """model/GPEMSR.py:345-353: relu1_2 of both (expanded to 3 channels), 16x16 patches, normalize, dot -> [N, 1, h/k, w/k]."""
+    n, _, h, w = ref_img.shape
+    a = F.normalize(image_patches(vgg_relu1_2(ref_img.expand(-1, 3, -1, -1), sd), k), dim=1)
+    b = F.normalize(image_patches(vgg_relu1_2(other_img.expand(-1, 3, -1, -1), sd), k), dim=1)
+    mask = torch.sum(a.contiguous() * b.contiguous(), dim=1, keepdim=True)
+    return mask.view(n, 1, h // k, w // k)
+
+
+def similarity_mask(ref_img, x_lr, sd, scale, k=16):
+    """model/GPEMSR.py:344-353 (16to1) / 395-403 (8to1): up_lr = bilinear x`scale` of the LR frames, then the patch similarity."""
+    up_lr = F.interpolate(x_lr, scale_factor=scale, mode='bilinear', align_corners=False)
+    return patch_similarity(ref_img, up_lr, sd, k)

@@ -165,3 +165,11 @@ def indexer_spec(variant=16, channel_list=(64, 64, 128, 256, 512), im_channel=1,
     spec['embedding.weight'] = ('linear', (num_codes, latent_dim))
     spec['embedding.bias'] = ('bias', (num_codes,))
     return spec
+
+
+def vgg_slice1_spec():
+    """``VGG19.slice1`` = torchvision vgg19.features[0:4] -- model/VGG.py:21-22."""
+    spec = OrderedDict()
+    _conv(spec, 'slice1.0', 64, 3, 3)
+    _conv(spec, 'slice1.2', 64, 64, 3)
+    return spec

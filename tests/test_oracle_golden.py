@@ -130,3 +130,13 @@ def test_indexer_small_bitexact(golden):
         feat = R.indexer_features(T(g[f'{tag}_x']), sd)
         assert np.array_equal(feat.numpy(), g[f'{tag}_feat']), tag
         assert np.array_equal(R.indexer_forward(T(g[f'{tag}_x']), sd).numpy(), g[f'{tag}_logits']), tag
+
+
+def test_vgg_mask_bitexact(golden):
+    """relu1_2 patch-similarity mask (model/GPEMSR.py:344-353 with the reference's VGG19 + extract_image_patches)."""
+    g = golden('vgg_mask_small')
+    sd = W.fill(W.vgg_slice1_spec(), seed=int(g['seed'][0]))
+    r12 = R.vgg_relu1_2(T(g['ref_img']).expand(-1, 3, -1, -1), sd)
+    assert np.array_equal(r12[:1, :, :16, :16].numpy(), g['relu1_2'])
+    mask = R.similarity_mask(T(g['ref_img']), T(g['x']), sd, 16)
+    assert np.array_equal(mask.numpy(), g['mask'])
