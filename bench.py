@@ -10,6 +10,8 @@ reference):
     f-4  Indexer16 conv stack (model/indexer.py) on the 5 x 1 x 80 x 80 LR frames -> 5 x 512 x 80 x 80 features
     a-2  Indexer head Linear(512->1024) + softmax/top-1 + codebook gather on those features
     a-3  Decoder.multi_scale_feat_calculate on the 5 quantised latents  (-> 5 x 1 x 1280 x 1280 reference images)
+    f-1  VGG19 relu1_2 patch-similarity mask of the reference images vs the bilinearly upsampled LR frames
+         (model/GPEMSR.py:344-353: 2 x (conv 3->64, conv 64->64) on 5 x 1280 x 1280, 16 x 16 patch cosine -> 5 x 1 x 80 x 80)
     a-5  the 60 flow_warp calls SpyNet makes per forward (5 frames x 2 calls x 6 pyramid levels, 3 x 10^2 .. 3 x 320^2)
     a-4  the SR tail on the fused 64 x 80 x 80 feature (-> 1 x 1 x 1280 x 1280)
 
@@ -67,7 +69,7 @@ def make_inputs(lr, nframes, seed, pin=False):
 def make_weights(seed=1):
     from oracle import weights as W      # deterministic random-init parameters (no checkpoints offline)
     return dict(dec=W.fill(W.decoder_spec(), seed), emb=W.fill(W.codebook_spec(), seed + 1)['embedding.weight'],
-                idx=W.fill(W.indexer_spec(16), seed + 2), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
+                idx=W.fill(W.indexer_spec(16), seed + 2), vgg=W.fill(W.vgg_slice1_spec(), seed + 4), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
 
 
 # ----------------------------------------------------------------------------------------------- native arm
@@ -84,18 +86,22 @@ class NativeHotPath:
         from gpemsr_b200.indexer import Indexer16
         self.idx = Indexer16(IDX_CFG).to(device)
         self.idx.load_state_dict(wts['idx'], strict=True)
+        from gpemsr_b200.vgg import VGG19Slice1
+        self.vgg = VGG19Slice1().to(device)
+        self.vgg.load_reference_state_dict(wts['vgg'])
 
     def step(self, d):
         feat = self.idx.features(d['lr_frames'])
         zq = self.cb.inference_from_feat(feat, self.idx.embedding.weight.detach(), self.idx.embedding.bias.detach())
         feats = self.dec.multi_scale_feat_calculate(zq)
+        mask = self.vgg.similarity_mask(feats[-1], d['lr_frames'], SCALE)
         nlev = len([k for k in d if k.startswith('warp_x')])
         for i in range(nlev):
             x, f = d[f'warp_x{i}'], d[f'warp_f{i}']
             for j in range(x.shape[0]):                 # the reference issues these one SpyNet level at a time
                 self.g.flow_warp(x[j:j + 1], f[j:j + 1], 'bilinear', 'border')
         out = self.tail(d['fea'], d['x_center'])
-        return out, feats
+        return out, feats + [mask]
 
 
 # ----------------------------------------------------------------------------------------------- reference (CPU) arm
@@ -104,6 +110,7 @@ def cpu_step(wts, ins):
     from oracle.flow_warp import flow_warp_torch
     with torch.no_grad():
         feats, _ = R.ref_extract(ins['lr_frames'], wts['idx'], wts['emb'], wts['dec'])
+        feats = feats + [R.similarity_mask(feats[-1], ins['lr_frames'], wts['vgg'], SCALE)]
         i = 0
         while f'warp_x{i}' in ins:
             x, f = ins[f'warp_x{i}'], ins[f'warp_f{i}']
@@ -283,7 +290,7 @@ def run_reference(args, rank, world):
 
 
 def config_block(world):
-    return {'workload': f'GPEMSR x16 hot path (Indexer16 conv stack + head + codebook lookup, VQ decoder multi-scale, 60 SpyNet flow_warp '
+    return {'workload': f'GPEMSR x16 hot path (Indexer16 conv stack + head + codebook lookup, VQ decoder multi-scale, VGG relu1_2 similarity mask, 60 SpyNet flow_warp '
                         f'calls, SR tail), {NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
             'lr': LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
             'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '
