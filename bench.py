@@ -218,7 +218,7 @@ def instrumented_step(hp, dev_in):
         s.record()
         orig(a, w, err, **kw)
         e.record()
-        rec.append((f'gemm_kernel<{bn},split{kw.get("split", 3)}>', 2.0 * rows * n * k * taps, s, e))
+        rec.append((f'gemm_kernel<{bn},split{kw.get("split", 3)}>', 2.0 * rows * n * k * taps, s, e, (rows, n, k, taps)))
 
     G.igemm = wrapped
     import gpemsr_b200.decoder as D
@@ -229,9 +229,16 @@ def instrumented_step(hp, dev_in):
     finally:
         G.igemm = orig
     agg = {}
-    for name, fl, s, e in rec:
+    dump = os.environ.get('GPEMSR_BENCH_DUMP_LAUNCHES')
+    rows_out = []
+    for name, fl, s, e, shape in rec:
         a = agg.setdefault(name, [0.0, 0.0, 0])
         a[0] += fl; a[1] += s.elapsed_time(e); a[2] += 1
+        rows_out.append(dict(kernel=name, rows=shape[0], n=shape[1], k=shape[2], taps=shape[3], ms=s.elapsed_time(e),
+                             tflops=fl / max(s.elapsed_time(e), 1e-6) / 1e9))
+    if dump:
+        with open(dump, 'w') as f:
+            json.dump(rows_out, f, indent=0)
     return agg
 
 

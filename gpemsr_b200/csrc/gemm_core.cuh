@@ -180,6 +180,8 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
     uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
     bool ok = true;
+    const uint64_t a_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages), BLOCK_M * 16, 128);
+    const uint64_t b_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages) + Cfg::PLANES * Cfg::A_PLANE_BYTES, BLOCK_N * 16, 128);
     for (long long i = 0; i < n_iter && ok; ++i) {
       for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
         ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
@@ -191,17 +193,19 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
           if (!ok) break;
           sm100::tc_fence_after();
           if (sm100::elect_one()) {
-            const uint32_t sa = sm100::smem_u32(stages + stage * Cfg::STAGE_BYTES);
-            const uint32_t sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+            // descriptors = base descriptor + offset in the 14-bit start-address field (address >> 4): the issuing warp
+            // is close to the critical path, so nothing is rebuilt per trip
+            const uint64_t sa = a_desc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+            const uint64_t sb = b_desc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
             for (int k16 = 0; k16 < BLOCK_K / 16; ++k16) {
               // one UMMA consumes two 16-byte k-cells: advance the start address by 2 cell columns per step
-              const uint64_t a_hi = sm100::smem_desc_kmajor_noswz(sa + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
-              const uint64_t b_hi = sm100::smem_desc_kmajor_noswz(sb + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+              const uint64_t a_hi = sa + k16 * ((2 * BLOCK_M * 16) >> 4);
+              const uint64_t b_hi = sb + k16 * ((2 * BLOCK_N * 16) >> 4);
               sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | k16) != 0);
               if constexpr (SPLIT == 3) {
-                const uint64_t a_lo = sm100::smem_desc_kmajor_noswz(sa + Cfg::A_PLANE_BYTES + k16 * 2 * (BLOCK_M * 16), BLOCK_M * 16, 128);
-                const uint64_t b_lo = sm100::smem_desc_kmajor_noswz(sb + Cfg::B_PLANE_BYTES + k16 * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+                const uint64_t a_lo = a_hi + (Cfg::A_PLANE_BYTES >> 4);
+                const uint64_t b_lo = b_hi + (Cfg::B_PLANE_BYTES >> 4);
                 sm100::umma_bf16(tmem_acc, a_lo, b_hi, idesc, true);
                 sm100::umma_bf16(tmem_acc, a_hi, b_lo, idesc, true);
               }
@@ -246,6 +250,178 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
   if (warp == 1) {
     sm100::tc_fence_after();
     sm100::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A-resident variant (single bf16 pass, one tap, tiled B): the whole [128 x K] A tile of a row tile lives in shared memory
+// and is fetched ONCE, while the B tiles of all column tiles stream through the stage ring.  The streaming kernel re-reads A
+// for every column tile; for the VQ lookup (4 code tiles) that is 4 x 147 KB of the 1.2 MB a row tile pulls out of L2, and
+// L2 -> SM operand bandwidth is what bounds that kernel.  There is no room for a second A tile (K = 544: 136 KB), so the
+// tile is recycled chunk by chunk: when the MMAs of the LAST column tile have consumed k-chunk c (tcgen05.commit on
+// a_empty[c]) a dedicated A-producer warp refills it with the next row tile's chunk c -- about one column tile of MMA
+// time before the next row tile needs it.
+// Roles: warp 0 = B producer, warp 1 = MMA issuer, warp 2 = A producer, warps 3.. = epilogue.
+constexpr int ARES_MAX_CHUNKS = 24;
+struct BarriersAres {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t a_full[ARES_MAX_CHUNKS];
+  uint64_t a_empty[ARES_MAX_CHUNKS];
+  uint32_t tmem_base;
+};
+template <class Epi> constexpr int num_threads_ares() { return 96 + 32 * Epi::WARPS; }
+template <int BLOCK_N, int BLOCK_K, int NSTAGE>
+constexpr int ares_smem_bytes(int k) { return k * BLOCK_M * 2 + NSTAGE * BLOCK_N * BLOCK_K * 2 + 1024; }
+
+template <int BLOCK_N, int BLOCK_K, int NSTAGE, class Epi, int CLUSTER = 1>
+__global__ void __launch_bounds__(96 + 32 * Epi::WARPS, 1)
+gemm_ares_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
+  constexpr int KCH = BLOCK_K / 8;                              // 16-byte k-cells per chunk
+  constexpr int A_CHUNK_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(sizeof(BarriersAres) <= 1024, "barrier block");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nch = op.k / BLOCK_K;                               // A chunks (<= ARES_MAX_CHUNKS, checked by the host)
+  uint8_t* a_res = smem;
+  uint8_t* stages = smem + nch * A_CHUNK_BYTES;
+  BarriersAres* bars = reinterpret_cast<BarriersAres*>(stages + NSTAGE * B_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = CLUSTER > 1 ? sm100::cluster_ctarank() : 0;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CLUSTER) - 1);
+  const long long n_iter = (op.m_tiles + gridDim.x - 1) / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], CLUSTER); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
+    for (int c = 0; c < nch; ++c) { sm100::mbar_init(&bars->a_full[c], 1); sm100::mbar_init(&bars->a_empty[c], 1); }
+    sm100::fence_mbar_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  sm100::tc_fence_before();
+  if constexpr (CLUSTER > 1) sm100::cluster_sync_all(); else __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== B producer: one contiguous (half-)stage copy per k-chunk =====================
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    constexpr uint32_t b_part = B_STAGE_BYTES / CLUSTER;
+    const long long b_kstep = B_STAGE_BYTES / 2;                // elements per k-chunk of the tiled B
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        const __nv_bfloat16* b_src = op.b_hi + (long long)n_tile * nch * b_kstep + crank * (b_part / 2);
+        for (int kci = 0; kci < nch; ++kci) {
+          ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+          if (!ok) break;
+          if (lane == 0) {
+            sm100::mbar_arrive_expect_tx(&bars->full[stage], B_STAGE_BYTES);
+            uint8_t* dst = stages + stage * B_STAGE_BYTES + crank * b_part;
+            if constexpr (CLUSTER > 1) sm100::bulk_g2s_multicast(dst, b_src, b_part, &bars->full[stage], kAllCtas);
+            else sm100::bulk_g2s(dst, b_src, b_part, &bars->full[stage]);
+          }
+          __syncwarp();
+          b_src += b_kstep;
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== A producer: refill chunk c as soon as the previous row tile has released it ==============
+    bool ok = true;
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      const long long m_tile = min(blockIdx.x + i * gridDim.x, op.m_tiles - 1);
+      const __nv_bfloat16* a_tile = op.a_hi + (op.a_row0 + m_tile * BLOCK_M) * 8;
+      const uint32_t par = (uint32_t)(i & 1);
+      for (int c = 0; c < nch && ok; ++c) {
+        ok = sm100::mbar_wait(&bars->a_empty[c], par ^ 1, op.err_flag, 5);
+        if (!ok) break;
+        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->a_full[c], A_CHUNK_BYTES);
+        __syncwarp();
+        if (lane < KCH)
+          sm100::bulk_g2s(a_res + c * A_CHUNK_BYTES + lane * (BLOCK_M * 16),
+                          a_tile + (long long)(c * KCH + lane) * op.a_rows * 8, BLOCK_M * 16, &bars->a_full[c]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    // the column tiles this CTA sweeps: first / last decide when A chunks are awaited / released
+    const int n_first = blockIdx.y;
+    const int n_last = n_first + ((op.n_tiles - 1 - n_first) / (int)gridDim.y) * (int)gridDim.y;
+    const uint64_t a_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(a_res), BLOCK_M * 16, 128);
+    const uint64_t b_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages), BLOCK_N * 16, 128);
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      const uint32_t par = (uint32_t)(i & 1);
+      for (int n_tile = n_first; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+        // The single issuing warp is itself close to the critical path here (2 MMAs = 256 tensor cycles per trip): the trip
+        // is kept lean -- descriptors are a base plus a 14-bit start-address offset, no per-trip descriptor rebuild.
+        // (Issuing two chunks per trip was measured slower: it holds two of the five B stages twice as long.)
+        for (int c = 0; c < nch && ok; ++c) {
+          if (n_tile == n_first) {
+            ok = sm100::mbar_wait(&bars->a_full[c], par, op.err_flag, 6);
+            if (!ok) break;
+          }
+          ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+          if (!ok) break;
+          sm100::tc_fence_after();
+          if (sm100::elect_one()) {
+            const uint64_t da = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
+            const uint64_t db = b_desc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k16 = 0; k16 < BLOCK_K / 16; ++k16)
+              sm100::umma_bf16(tmem_acc, da + k16 * ((2 * BLOCK_M * 16) >> 4), db + k16 * ((2 * BLOCK_N * 16) >> 4), idesc, (c | k16) != 0);
+            if constexpr (CLUSTER > 1) sm100::umma_commit_multicast(&bars->empty[stage], kAllCtas);
+            else sm100::umma_commit(&bars->empty[stage]);
+            if (n_tile == n_last) sm100::umma_commit(&bars->a_empty[c]);       // chunk c may be refilled for the next row tile
+            if (c == nch - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
+          }
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      const long long m_tile = blockIdx.x + i * gridDim.x;
+      const bool live = m_tile < op.m_tiles;
+      typename Epi::State st{};
+      for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+        if (live) epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, (warp - 3) >> 2);
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+        if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  sm100::tc_fence_before();
+  if constexpr (CLUSTER > 1) sm100::cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 

@@ -25,6 +25,7 @@
 #include "gemm_core.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -32,6 +33,8 @@ constexpr int CMAX = 32;             // candidate-list slots per row (two sub-li
                                      // row); more appends -> exact scan of every code for that row
 constexpr int CSUB = CMAX / 2;
 constexpr int VQ_BLOCK_N = 256;
+constexpr int VQ_BLOCK_K = 32;       // k-chunk of the GEMM stages; the operands are padded to a multiple of it
+constexpr int VQ_STAGES = 5;
 constexpr uint32_t OVERFLOW = 0xFFFFFFFFu;
 constexpr int FIN_ROWS = 32;         // rows per finalize block
 constexpr int FIN_THREADS = 512;
@@ -40,7 +43,7 @@ inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m
 
 struct Workspace {
   __nv_bfloat16* a;       // [d_pad/8][rows_pad][8]
-  __nv_bfloat16* b;       // [k_pad/256][d_pad/64][8][256][8] (tiled: one contiguous block per GEMM stage)
+  __nv_bfloat16* b;       // [k_pad/256][d_pad/8][256][8] (tiled: one contiguous block per GEMM stage)
   float* c;               // [k_pad]   |e_k|^2 (or -bias_k); +inf for padding codes
   float* zz;              // [rows_pad]
   float* margin;          // [rows_pad]
@@ -54,7 +57,7 @@ struct Workspace {
 
 Workspace carve(void* base, long long rows, int d, int k) {
   const long long rows_pad = round_up(std::max<long long>(rows, 1), gemm::BLOCK_M);
-  const long long d_pad = round_up(d + 3, 64), k_pad = round_up(k, VQ_BLOCK_N);      // + 3: the folded constant's k slots
+  const long long d_pad = round_up(d + 3, VQ_BLOCK_K), k_pad = round_up(k, VQ_BLOCK_N);      // + 3: the folded constant's k slots
   uintptr_t p = (uintptr_t)base;
   auto take = [&](size_t n) { uintptr_t r = p; p += (uintptr_t)round_up((long long)n, 256); return (void*)r; };
   Workspace w;
@@ -109,8 +112,8 @@ __global__ void vq_prep_codes(const float* __restrict__ e, const float* __restri
       }
       h[j] = sm100::pack_bf16x2(v[0], v[1]);
     }
-    // tiled layout [code tile][k-chunk of 64][k-cell][256 codes][8]: every GEMM stage is one contiguous 32 KB copy
-    const size_t cell = (((size_t)(code / VQ_BLOCK_N) * (d_pad / 64) + kc / 8) * 8 + (kc & 7)) * VQ_BLOCK_N + (code % VQ_BLOCK_N);
+    // tiled layout [code tile][k-cell][256 codes][8]: every GEMM stage (VQ_BLOCK_K / 8 consecutive cells) is one contiguous copy
+    const size_t cell = ((size_t)(code / VQ_BLOCK_N) * (d_pad / 8) + kc) * VQ_BLOCK_N + (code % VQ_BLOCK_N);
     *reinterpret_cast<uint4*>(b + cell * 8) = make_uint4(h[0], h[1], h[2], h[3]);
   }
   if (lane == 0) {
@@ -759,7 +762,7 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
 
   Workspace W = carve(ws, rows, d, k);
   const long long rows_pad = round_up(rows, gemm::BLOCK_M);
-  const int d_pad = (int)round_up(d + 3, 64), k_pad = (int)round_up(k, VQ_BLOCK_N), n_tiles = k_pad / VQ_BLOCK_N;
+  const int d_pad = (int)round_up(d + 3, VQ_BLOCK_K), k_pad = (int)round_up(k, VQ_BLOCK_N), n_tiles = k_pad / VQ_BLOCK_N;
   const float alpha = mode == 0 ? -2.0f : -1.0f;
 
   GPEMSR_CUDA_OK(cudaMemsetAsync(W.emax, 0, 512, s));       // emax and err (adjacent 256-byte slots)
@@ -774,14 +777,28 @@ int run_lookup(const float* z, const float* w, const float* bias, const float* t
     op.a_rows = rows_pad; op.b_rows = k_pad; op.b_packed = 1; op.k = d_pad; op.taps = 1; op.a_row_off[0] = 0;
     op.m_tiles = rows_pad / gemm::BLOCK_M; op.n_tiles = n_tiles; op.a_row0 = 0; op.err_flag = W.err;
     EpiArgExtremum epi{W.margin, W.cand_cnt, W.cand, W.runmin, rows, alpha};
-    using Cfg = gemm::Config<VQ_BLOCK_N, 64, 1, 4>;
-    if (op.m_tiles >= 2 && use_clusters()) {       // CTA pairs share every codebook stage by multicast (halves L2 traffic)
-      auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum, 2>;
+    using Cfg = gemm::Config<VQ_BLOCK_N, VQ_BLOCK_K, 1, 6>;
+    const bool pair = op.m_tiles >= 2 && use_clusters();   // CTA pairs share every codebook stage by multicast (halves L2 traffic)
+    const int ares_smem = gemm::ares_smem_bytes<VQ_BLOCK_N, VQ_BLOCK_K, VQ_STAGES>(d_pad);
+    const bool a_resident = ares_smem <= 227 * 1024 && d_pad / VQ_BLOCK_K <= gemm::ARES_MAX_CHUNKS && !getenv("GPEMSR_VQ_STREAM_A");
+    if (a_resident && pair) {
+      // the [128 x d_pad] A tile stays in shared memory for all code tiles (gemm_ares_kernel): A leaves L2 once, not 4 times
+      auto kern = gemm::gemm_ares_kernel<VQ_BLOCK_N, VQ_BLOCK_K, VQ_STAGES, EpiArgExtremum, 2>;
+      GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ares_smem));
+      const int grid = (int)((std::min<long long>(op.m_tiles, num_sms()) + 1) / 2 * 2);
+      GPEMSR_CUDA_OK(launch_cluster(kern, dim3(grid), dim3(gemm::num_threads_ares<EpiArgExtremum>()), ares_smem, s, 2, op, epi));
+    } else if (a_resident) {
+      auto kern = gemm::gemm_ares_kernel<VQ_BLOCK_N, VQ_BLOCK_K, VQ_STAGES, EpiArgExtremum, 1>;
+      GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ares_smem));
+      const int grid = (int)std::min<long long>(op.m_tiles, num_sms());
+      kern<<<grid, gemm::num_threads_ares<EpiArgExtremum>(), ares_smem, s>>>(op, epi);
+    } else if (pair) {
+      auto kern = gemm::gemm_kernel<VQ_BLOCK_N, VQ_BLOCK_K, 1, 6, EpiArgExtremum, 2>;
       GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
       const int grid = (int)((std::min<long long>(op.m_tiles, num_sms()) + 1) / 2 * 2);
       GPEMSR_CUDA_OK(launch_cluster(kern, dim3(grid), dim3(gemm::num_threads<EpiArgExtremum>()), Cfg::SMEM_BYTES, s, 2, op, epi));
     } else {
-      auto kern = gemm::gemm_kernel<VQ_BLOCK_N, 64, 1, 4, EpiArgExtremum>;
+      auto kern = gemm::gemm_kernel<VQ_BLOCK_N, VQ_BLOCK_K, 1, 6, EpiArgExtremum>;
       GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
       const int grid = (int)std::min<long long>(op.m_tiles, num_sms());
       kern<<<grid, gemm::num_threads<EpiArgExtremum>(), Cfg::SMEM_BYTES, s>>>(op, epi);
