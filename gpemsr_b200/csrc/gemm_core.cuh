@@ -176,7 +176,8 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer: ONE elected thread runs the whole loop (no per-trip elect / reconvergence) =====
+    if (sm100::elect_one()) {
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
     uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
     bool ok = true;
@@ -192,7 +193,7 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
           ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
           if (!ok) break;
           sm100::tc_fence_after();
-          if (sm100::elect_one()) {
+          {
             // descriptors = base descriptor + offset in the 14-bit start-address field (address >> 4): the issuing warp
             // is close to the critical path, so nothing is rebuilt per trip
             const uint64_t sa = a_desc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
@@ -215,12 +216,13 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
             else sm100::umma_commit(&bars->empty[stage]);
             if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);   // accumulator complete
           }
-          __syncwarp();
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
       }
     }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
@@ -349,7 +351,8 @@ gemm_ares_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer: ONE elected thread runs the whole loop (no per-trip elect / reconvergence) =====
+    if (sm100::elect_one()) {
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
     uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
     bool ok = true;
@@ -376,7 +379,7 @@ gemm_ares_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
           ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
           if (!ok) break;
           sm100::tc_fence_after();
-          if (sm100::elect_one()) {
+          {
             const uint64_t da = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
             const uint64_t db = b_desc0 + (uint64_t)(stage * (B_STAGE_BYTES >> 4));
 #pragma unroll
@@ -387,12 +390,13 @@ gemm_ares_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
             if (n_tile == n_last) sm100::umma_commit(&bars->a_empty[c]);       // chunk c may be refilled for the next row tile
             if (c == nch - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
           }
-          __syncwarp();
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
       }
     }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;
