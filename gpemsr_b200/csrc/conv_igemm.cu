@@ -16,7 +16,7 @@ namespace {
 struct Geom {
   int n, h, w, padded;
   long long r_img, m0, rows_alloc;
-  __host__ __device__ int wp() const { return padded ? w + 2 : w; }
+  __host__ __device__ int wp() const { return w + 2 * padded; }       // `padded` is the zero-ring width (0 = compact)
 };
 Geom to_geom(const gpemsr_geom_t& g) { return Geom{g.n, g.h, g.w, g.padded, g.r_img, g.m0, g.rows_alloc}; }
 
@@ -45,16 +45,16 @@ __device__ __forceinline__ bool decode_row(const Geom& g, long long rel, int& im
   img = (int)(rel / g.r_img);
   const long long q = rel - (long long)img * g.r_img;
   if (g.padded) {
-    const int wp = g.w + 2;
+    const int wp = g.w + 2 * g.padded;
     const int yp = (int)(q / wp), xp = (int)(q - (long long)yp * wp);
-    y = yp - 1; x = xp - 1;
-    return img < g.n && yp >= 1 && yp <= g.h && xp >= 1 && xp <= g.w;
+    y = yp - g.padded; x = xp - g.padded;
+    return img < g.n && y >= 0 && y < g.h && x >= 0 && x < g.w;
   }
   y = (int)(q / g.w); x = (int)(q - (long long)y * g.w);
   return img < g.n && q < (long long)g.h * g.w;
 }
 __device__ __forceinline__ long long place_row(const Geom& g, int img, int y, int x) {
-  return g.m0 + (long long)img * g.r_img + (g.padded ? (long long)(y + 1) * (g.w + 2) + (x + 1) : (long long)y * g.w + x);
+  return g.m0 + (long long)img * g.r_img + (long long)(y + g.padded) * (g.w + 2 * g.padded) + (x + g.padded);
 }
 
 template <int BLOCK_N>
@@ -92,7 +92,7 @@ struct EpiConv {
   // one cell = 8 consecutive output channels of one output pixel; (dy, dx) only differ from 0 under PixelShuffle
   __device__ __forceinline__ void store_cell(const State& st, float (&v)[8], int ch0, int dy, int dx) const {
     if (out_f32 || out_hi || residual) {
-      const long long orow = st.orow + (long long)dy * (og.padded ? og.w + 2 : og.w) + dx;
+      const long long orow = st.orow + (long long)dy * (og.w + 2 * og.padded) + dx;
       const size_t cell = ((size_t)(ch0 >> 3) * og.rows_alloc + orow) * 8;
       if (residual) {
         const float4 r0 = *reinterpret_cast<const float4*>(residual + cell), r1 = *reinterpret_cast<const float4*>(residual + cell + 4);
@@ -440,6 +440,74 @@ __global__ void act_unpack_nchw_kernel(const float* __restrict__ f32, int c, Geo
     const int ch = cc * 8 + j;
     if (ch < c) x[((long long)img * c + ch) * hw + p] = v[j];
   }
+}
+
+// ------------------------------------------------------------------------------------------------ SpyNet helpers
+// ATen upsample_bilinear2d (the arithmetic of F.interpolate(mode='bilinear')) with the source index computed the way ATen
+// does: align_corners ? dst * (in-1)/(out-1) : max((dst + 0.5) * (in/out or 1/scale_factor) - 0.5, 0).
+//   out[n, co, y, x] (=|+=) mul[co] * (bilinear(x[n, ci(co), ...]) - sub[co]) / div[co]
+// ci(co) = co % c_in (a one-channel frame broadcast to three channels), sub/div/mul NULL = identity.  rep_h / rep_w > 0:
+// output rows / columns >= rep_h / rep_w repeat the last natural one (F.pad(..., mode='replicate') after the upsampling,
+// SpyNet's odd-size case).  rh / rw are the host-computed fp32 scales (ATen's area_pixel_compute_scale).
+__global__ void resize_bilinear_kernel(const float* __restrict__ x, int n, int c_in, int h, int w, int c_out, int ho, int wo,
+                                       int align_corners, float rh, float rw, int rep_h, int rep_w,
+                                       const float* __restrict__ sub, const float* __restrict__ div,
+                                       const float* __restrict__ mul, int accumulate, float* __restrict__ out,
+                                       float* __restrict__ out_nhwc) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * c_out * ho * wo) return;
+  const int ox0 = (int)(t % wo), oy0 = (int)((t / wo) % ho), co = (int)((t / ((long long)wo * ho)) % c_out);
+  const int img = (int)(t / ((long long)wo * ho * c_out));
+  const int oy = rep_h > 0 ? min(oy0, rep_h - 1) : oy0, ox = rep_w > 0 ? min(ox0, rep_w - 1) : ox0;
+  float sy, sx;
+  if (align_corners) { sy = rh * (float)oy; sx = rw * (float)ox; }
+  else { sy = fmaxf(rh * ((float)oy + 0.5f) - 0.5f, 0.f); sx = fmaxf(rw * ((float)ox + 0.5f) - 0.5f, 0.f); }
+  const int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* p = x + ((long long)img * c_in + co % c_in) * h * w;
+  float v = hy * (hx * __ldg(p + (long long)y0 * w + x0) + lx * __ldg(p + (long long)y0 * w + x1)) +
+            ly * (hx * __ldg(p + (long long)y1 * w + x0) + lx * __ldg(p + (long long)y1 * w + x1));
+  if (sub) v = v - sub[co];
+  if (div) v = v / div[co];
+  if (mul) v = v * mul[co];
+  if (out) { if (accumulate) out[t] += v; else out[t] = v; }
+  if (out_nhwc) out_nhwc[(((long long)img * ho + oy0) * wo + ox0) * c_out + co] = v;
+}
+
+// F.avg_pool2d(x, 2, 2, count_include_pad=False) on even sizes: the mean of each 2 x 2 block, ATen's order of additions
+__global__ void avg_pool2_kernel(const float* __restrict__ x, long long planes, int h, int w, float* __restrict__ out) {
+  const int ho = h / 2, wo = w / 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= planes * ho * wo) return;
+  const int ox = (int)(t % wo), oy = (int)((t / wo) % ho);
+  const float* p = x + (t / ((long long)wo * ho)) * h * w + (long long)(2 * oy) * w + 2 * ox;
+  out[t] = (((__ldg(p) + __ldg(p + 1)) + __ldg(p + w)) + __ldg(p + w + 1)) / 4.0f;
+}
+
+// channel concatenation of up to three NCHW fp32 tensors straight into one 8-channel cell column (hi, lo planes):
+// SpyNet's torch.cat([ref, warped, flow], 1) (3 + 3 + 2 channels) fused with the operand packing.
+__global__ void pack_concat3_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                                    const float* __restrict__ c, int cc, Geom g, uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const long long hw = (long long)g.h * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)g.n * hw) return;
+  const int img = (int)(t / hw);
+  const long long p = t % hw;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float val = 0.f;
+    if (j < ca) val = __ldg(a + ((long long)img * ca + j) * hw + p);
+    else if (j < ca + cb) val = __ldg(b + ((long long)img * cb + (j - ca)) * hw + p);
+    else if (j < ca + cb + cc) val = __ldg(c + ((long long)img * cc + (j - ca - cb)) * hw + p);
+    v[j] = val;
+  }
+  uint4 h4, l4;
+  split8(v, h4, l4);
+  const size_t cell = (size_t)place_row(g, img, (int)(p / g.w), (int)(p % g.w));
+  hi[cell] = h4;
+  if (lo) lo[cell] = l4;
 }
 
 // ---- VGG19 conv1_1 on a one-channel image (the three input channels of the reference are copies of each other, so their
@@ -827,8 +895,9 @@ int check_geom(const gpemsr_geom_t& g, const char* what) {
   using namespace gpemsr;
   if (g.n <= 0 || g.h <= 0 || g.w <= 0 || g.r_img <= 0 || (g.r_img % gemm::BLOCK_M) != 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: bad geometry n=%d h=%d w=%d r_img=%lld", what, g.n, g.h, g.w, (long long)g.r_img);
-  const long long need = g.padded ? (long long)(g.h + 2) * (g.w + 2) : (long long)g.h * g.w;
-  const long long margin = g.padded ? g.w + 3 : 0;
+  if (g.padded < 0 || g.padded > 3) return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: ring width %d (0..3 supported)", what, g.padded);
+  const long long need = (long long)(g.h + 2 * g.padded) * (g.w + 2 * g.padded);
+  const long long margin = g.padded ? (long long)g.padded * (g.w + 2 * g.padded) + g.padded : 0;     // largest tap shift
   if (g.r_img < need || g.m0 < margin || g.rows_alloc < g.m0 + (long long)g.n * g.r_img + margin)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: geometry does not leave room for the zero ring / tap shifts", what);
   return GPEMSR_OK;
@@ -880,10 +949,11 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   op.a_hi = (const __nv_bfloat16*)d.a_hi; op.a_lo = (const __nv_bfloat16*)d.a_lo;
   op.b_hi = (const __nv_bfloat16*)d.b_hi; op.b_lo = (const __nv_bfloat16*)d.b_lo;
   op.a_rows = d.a_geom.rows_alloc; op.b_rows = d.b_rows; op.b_packed = d.b_packed; op.k = d.k_pad; op.taps = d.taps;
-  const int wp = d.a_geom.padded ? d.a_geom.w + 2 : d.a_geom.w;
+  const int wp = d.a_geom.w + 2 * d.a_geom.padded;
   for (int t = 0; t < d.taps; ++t) {
-    if (!d.a_geom.padded && (d.tap_dy[t] || d.tap_dx[t])) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: shifted taps need a padded geometry");
-    if (abs(d.tap_dy[t]) > 1 || abs(d.tap_dx[t]) > 1) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: taps beyond +-1 need a wider ring");
+    if (abs(d.tap_dy[t]) > d.a_geom.padded || abs(d.tap_dx[t]) > d.a_geom.padded)
+      return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: tap (%d, %d) needs a zero ring of that width (geometry has %d)", d.tap_dy[t],
+                       d.tap_dx[t], d.a_geom.padded);
     op.a_row_off[t] = d.tap_dy[t] * wp + d.tap_dx[t];
   }
   op.m_tiles = (long long)d.a_geom.n * d.a_geom.r_img / gemm::BLOCK_M;
@@ -976,6 +1046,48 @@ int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int 
   const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
   act_unpack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f32, c, to_geom(*g), c_off, x);
   GPEMSR_LAUNCH_OK("act_unpack_nchw_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_resize_bilinear(const float* x, int n, int c_in, int h, int w, int c_out, int ho, int wo, int align_corners,
+                           float rh, float rw, int rep_h, int rep_w, const float* sub, const float* div, const float* mul,
+                           int accumulate, float* out, float* out_nhwc, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x || (!out && !out_nhwc) || n <= 0 || c_in <= 0 || c_out <= 0 || h <= 0 || w <= 0 || ho <= 0 || wo <= 0)
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "resize_bilinear: bad arguments");
+  const long long total = (long long)n * c_out * ho * wo;
+  resize_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, n, c_in, h, w, c_out, ho, wo, align_corners, rh, rw, rep_h, rep_w, sub, div, mul, accumulate, out, out_nhwc);
+  GPEMSR_LAUNCH_OK("resize_bilinear_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_avg_pool2(const float* x, int64_t planes, int h, int w, float* out, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x || !out || planes <= 0 || h < 2 || w < 2 || (h & 1) || (w & 1))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "avg_pool2: needs even h, w");
+  const long long total = planes * (h / 2) * (w / 2);
+  avg_pool2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, planes, h, w, out);
+  GPEMSR_LAUNCH_OK("avg_pool2_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_pack_concat3(const float* a, int ca, const float* b, int cb, const float* c, int cc, const gpemsr_geom_t* g,
+                        void* out_hi, void* out_lo, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!a || !g || !out_hi || ca <= 0 || cb < 0 || cc < 0 || ca + cb + cc > 8 || (cb && !b) || (cc && !c))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "pack_concat3: at most 8 channels in total");
+  if ((rc = check_geom(*g, "pack_concat3")) != GPEMSR_OK) return rc;
+  const long long total = (long long)g->n * g->h * g->w;
+  pack_concat3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, ca, b, cb, c, cc, to_geom(*g),
+                                                                                       (uint4*)out_hi, (uint4*)out_lo);
+  GPEMSR_LAUNCH_OK("pack_concat3_kernel");
   return GPEMSR_OK;
 }
 

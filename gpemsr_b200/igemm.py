@@ -46,10 +46,12 @@ class Geom:
     """Row geometry of a flattened image batch (mirrors gpemsr_geom_t)."""
 
     def __init__(self, n, h, w, padded=True, m0=None, rows_alloc=None, r_img=None):
-        self.n, self.h, self.w, self.padded = int(n), int(h), int(w), bool(padded)
-        per = (h + 2) * (w + 2) if padded else h * w
+        """padded: zero-ring width (True = 1: 3x3 taps; 3: 7x7 taps; False / 0: compact rows)."""
+        self.n, self.h, self.w, self.padded = int(n), int(h), int(w), int(padded)
+        P = self.padded
+        per = (h + 2 * P) * (w + 2 * P)
         self.r_img = _round_up(per, 128) if r_img is None else int(r_img)
-        margin = _round_up(w + 3, 128) if padded else 0
+        margin = _round_up(P * (w + 2 * P) + P, 128) if P else 0
         self.m0 = margin if m0 is None else int(m0)
         # tail: room for the +1-row tap shifts (padded) / for a last column tile read as B operand (compact)
         tail = margin if padded else 256

@@ -105,9 +105,9 @@ GPEMSR_API int gpemsr_argmax_gather(const float* p, const float* emb, int b, int
  * are zeroed once by the caller).  "Compact" tensors (attention tokens) use row(i, y, x) = i * r_img + y * w + x. */
 typedef struct gpemsr_geom {
   int32_t n, h, w;         /* images, height, width */
-  int32_t padded;          /* 1: zero ring (wp = w + 2), 0: compact */
+  int32_t padded;          /* zero-ring width P: 0 = compact rows, 1 = 3x3 taps, 3 = 7x7 taps (wp = w + 2P) */
   int64_t r_img;           /* rows reserved per image (multiple of 128) */
-  int64_t m0;              /* first row of image 0 (>= w + 3 when padded) */
+  int64_t m0;              /* first row of image 0 (>= P * wp + P: the largest negative tap shift) */
   int64_t rows_alloc;      /* rows allocated per 8-channel plane */
 } gpemsr_geom_t;
 
@@ -160,6 +160,21 @@ GPEMSR_API int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* 
                          float* f32, void* hi, void* lo, gpemsr_stream_t stream);
 GPEMSR_API int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int c_off, float* x,
                            gpemsr_stream_t stream);
+/* ---- SpyNet helpers (basicsr SpyNet.process / forward; reached from model/GPEMSR.py:99-100) ----
+ * gpemsr_resize_bilinear: F.interpolate(mode='bilinear') with ATen's source-index arithmetic (rh / rw = ATen's
+ *   area_pixel_compute_scale, computed by the host in fp32), plus the elementwise work SpyNet wraps around it:
+ *   out[n, co, y, x] (=|+=) mul[co] * (bilinear(x[n, co % c_in]) - sub[co]) / div[co]  (NULL = identity); rep_h / rep_w > 0
+ *   repeat the last natural row / column (F.pad replicate after an upsampling).  NCHW fp32 in; NCHW and / or NHWC (the
+ *   layout flow_warp takes its flow in) out.
+ * gpemsr_avg_pool2: F.avg_pool2d(x, 2, 2) on `planes` images of even size.
+ * gpemsr_pack_concat3: torch.cat of up to three NCHW tensors (<= 8 channels in total) written as one operand cell column. */
+GPEMSR_API int gpemsr_resize_bilinear(const float* x, int n, int c_in, int h, int w, int c_out, int ho, int wo, int align_corners,
+                           float rh, float rw, int rep_h, int rep_w, const float* sub, const float* div, const float* mul,
+                           int accumulate, float* out /*NCHW, nullable*/, float* out_nhwc /*[n, ho, wo, c_out], nullable*/,
+                           gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_avg_pool2(const float* x, int64_t planes, int h, int w, float* out, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_pack_concat3(const float* a, int ca, const float* b, int cb, const float* c, int cc, const gpemsr_geom_t* g,
+                        void* out_hi, void* out_lo, gpemsr_stream_t stream);
 /* First VGG19 layer on a one-channel image (model/VGG.py:21 slice1.0 applied to `img.expand(-1, 3, -1, -1)`,
  * model/GPEMSR.py:345,349): y = relu(conv3x3(x, w1) + bias) with w1[co][ky][kx] = sum over the 3 identical input channels
  * of the reference weight, zero padding 1.  x fp32 [n, 1, h, w] (reference layout); output = bf16 (hi, lo) operand planes
