@@ -69,7 +69,8 @@ def make_inputs(lr, nframes, seed, pin=False):
 def make_weights(seed=1):
     from oracle import weights as W      # deterministic random-init parameters (no checkpoints offline)
     return dict(dec=W.fill(W.decoder_spec(), seed), emb=W.fill(W.codebook_spec(), seed + 1)['embedding.weight'],
-                idx=W.fill(W.indexer_spec(16), seed + 2), vgg=W.fill(W.vgg_slice1_spec(), seed + 4), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
+                idx=W.fill(W.indexer_spec(16), seed + 2), vgg=W.fill(W.vgg_slice1_spec(), seed + 4),
+                spy=W.fill(W.spynet_spec(), seed + 5, gain=2.0), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
 
 
 # ----------------------------------------------------------------------------------------------- native arm
@@ -275,6 +276,24 @@ def micro_rooflines(peaks):
     by = 8.0 * c * s * s + 8.0 * s * s
     out['flow_warp'] = {'bound': 'hbm', 'shape': f'{c} x {s}^2', 'ms': ms, 'achieved': by / ms / 1e6, 'peak': peaks['hbm'],
                         'unit': 'GB/s', 'frac': by / ms / 1e6 / peaks['hbm']}
+    # SpyNet on the window's 10 (neighbour, centre) pairs at 320^2: built and parity-tested, reported here
+    # and NOT yet part of the step -- its 7x7 convs still re-read the activations once per tap
+    try:
+        from gpemsr_b200.spynet import SpyNet, resize_bilinear
+        from oracle import weights as W
+        spy = SpyNet().cuda()
+        spy.load_state_dict({**W.fill(W.spynet_spec(), 6, gain=2.0), 'mean': spy.mean, 'std': spy.std}, strict=True)
+        fr = torch.rand(NFRAMES, 1, LR, LR, device='cuda')
+        x4 = resize_bilinear(fr, 4 * LR, 4 * LR, False, scale=4)
+        idx = torch.arange(NFRAMES, device='cuda').repeat(2)
+        ref, supp = x4.index_select(0, idx), x4[NFRAMES // 2:NFRAMES // 2 + 1].expand(2 * NFRAMES, -1, -1, -1).contiguous()
+        ms = med(lambda: spy(ref, supp), iters=3, warm=2)
+        fl = 2.0 * 49 * (8 * 32 + 32 * 64 + 64 * 32 + 32 * 16 + 16 * 2) * ref.shape[0] * (4 * LR) ** 2 * (4.0 / 3.0)
+        out['spynet'] = {'bound': 'tensor', 'shape': f'{ref.shape[0]} pairs x {4 * LR}^2, 6 levels', 'ms': ms, 'achieved': fl / ms / 1e9,
+                         'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': fl / ms / 1e9 / peaks['tf'],
+                         'note': 'not part of the step yet; 49-tap streaming GEMMs are L2-operand bound'}
+    except Exception as e:                                # a diagnostic extra must never take the bench line down
+        out['spynet'] = {'error': repr(e)[:200]}
     return out
 
 

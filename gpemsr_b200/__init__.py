@@ -7,6 +7,8 @@ meaning and error behaviour) over the C ABI in ``include/gpemsr_b200.h``:
   * ``Codebook`` (``forward`` / ``inference_lr``)   -- model/codebook.py
   * ``Decoder`` (``forward`` / ``multi_scale_feat_calculate``) -- model/decoder.py
   * ``SRTail``                          -- model/GPEMSR.py:441-455
+  * ``SpyNet``                          -- basicsr/archs/spynet_arch.py (7x7 convs + flow_warp, coarse to fine)
+  * ``VGG19Slice1``                     -- model/VGG.py slice1 + the patch-similarity mask of model/GPEMSR.py:344-353
   * ``Indexer16`` / ``Indexer8`` / ``lrGenerator16`` / ``lrGenerator8`` (inference methods) -- model/indexer.py, model/vqgan_indexer.py
 
 The CUDA library is mandatory: nothing here falls back to PyTorch or the CPU.
@@ -17,5 +19,7 @@ from .codebook import Codebook, argmax_gather, logits_argmax_gather, vq_lookup  
 from .decoder import Decoder  # noqa: F401
 from .sr_tail import SRTail  # noqa: F401
 from .indexer import Indexer8, Indexer16, lrGenerator8, lrGenerator16  # noqa: F401
+from .spynet import SpyNet  # noqa: F401
+from .vgg import VGG19Slice1  # noqa: F401
 
-__all__ = ['flow_warp', 'Decoder', 'SRTail', 'Indexer16', 'Indexer8', 'lrGenerator16', 'lrGenerator8', 'Codebook', 'vq_lookup', 'logits_argmax_gather', 'argmax_gather', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']
+__all__ = ['flow_warp', 'Decoder', 'SRTail', 'Indexer16', 'Indexer8', 'lrGenerator16', 'lrGenerator8', 'SpyNet', 'VGG19Slice1', 'Codebook', 'vq_lookup', 'logits_argmax_gather', 'argmax_gather', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']

@@ -915,7 +915,7 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (rc != GPEMSR_OK) return rc;
   if ((rc = check_geom(d.a_geom, "igemm(a)")) != GPEMSR_OK) return rc;
   if ((d.out_f32 || d.out_hi || d.residual) && (rc = check_geom(d.o_geom, "igemm(out)")) != GPEMSR_OK) return rc;
-  if (d.taps < 1 || d.taps > gemm::MAX_TAPS || d.k_pad <= 0 || d.k_pad % 64 || d.n_cols <= 0)
+  if (d.taps < 1 || d.taps > gemm::MAX_TAPS || d.k_pad <= 0 || d.k_pad % (d.split == 3 ? 32 : 64) || d.n_cols <= 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: taps=%d k_pad=%d n_cols=%d", d.taps, d.k_pad, d.n_cols);
   if (d.split != 1 && d.split != 3) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: split must be 1 or 3");
   if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || (!d.b_lo && !d.b_packed)))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
@@ -989,7 +989,7 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
 int gpemsr_igemm_plan(const gpemsr_igemm_desc_t* dp, int32_t* block_n, int32_t* tapfused) {
   using namespace gpemsr;
   if (!dp || !block_n || !tapfused) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm_plan: null argument");
-  if (dp->taps < 1 || dp->taps > gemm::MAX_TAPS || dp->k_pad <= 0 || dp->k_pad % 64 || dp->n_cols <= 0)
+  if (dp->taps < 1 || dp->taps > gemm::MAX_TAPS || dp->k_pad <= 0 || dp->k_pad % (dp->split == 3 ? 32 : 64) || dp->n_cols <= 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm_plan: taps=%d k_pad=%d n_cols=%d", dp->taps, dp->k_pad, dp->n_cols);
   const int bn = pick_block_n(*dp);
   *block_n = bn;

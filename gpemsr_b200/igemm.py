@@ -107,7 +107,7 @@ class Weights:
         else:
             raise ValueError(kind)
         self.n, self.k = n, k
-        self.k_pad = _round_up(k, 64)
+        self.k_pad = _round_up(k, 32 if split == 3 else 64)      # one k-chunk of the streaming kernel (narrow inputs: less padding)
         self.b_rows = _round_up(n, 16) if n <= 16 else _round_up(n, 64) if n <= 64 else _round_up(n, 128) if n <= 128 \
             else _round_up(n, block_rows)
         self.b_rows = max(self.b_rows, min_rows)

@@ -116,7 +116,7 @@ typedef struct gpemsr_igemm_desc {
   const void* a_hi; const void* a_lo;       /* [k_pad/8][a_geom.rows_alloc][8] */
   const void* b_hi; const void* b_lo;       /* [taps][k_pad/8][b_rows][8] */
   gpemsr_geom_t a_geom;                     /* rows computed = n * r_img starting at m0 */
-  int32_t k_pad;                            /* reduction length per tap (multiple of 64) */
+  int32_t k_pad;                            /* reduction length per tap (multiple of 32 for split 3, of 64 for split 1) */
   int32_t taps;                             /* 1..49 */
   int32_t tap_dy[49], tap_dx[49];           /* A row shift of tap t = dy * (w + 2) + dx */
   int32_t b_rows;                           /* allocated B rows per tap (multiple of block_n) */

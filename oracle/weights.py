@@ -173,3 +173,13 @@ def vgg_slice1_spec():
     _conv(spec, 'slice1.0', 64, 3, 3)
     _conv(spec, 'slice1.2', 64, 64, 3)
     return spec
+
+
+def spynet_spec():
+    """Parameters of BasicSR ``SpyNet`` (spynet_arch.py): six BasicModules of five 7x7 convolutions 8-32-64-32-16-2."""
+    spec = OrderedDict()
+    chans = [8, 32, 64, 32, 16, 2]
+    for lv in range(6):
+        for i in range(5):
+            _conv(spec, f'basic_module.{lv}.basic_module.{2 * i}', chans[i + 1], chans[i], 7)
+    return spec
