@@ -347,6 +347,7 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep NCCL's version banner off stdout: ONE JSON line there
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     import gpemsr_b200
     wts = make_weights()
