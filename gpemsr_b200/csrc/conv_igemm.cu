@@ -371,6 +371,47 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   return GPEMSR_OK;
 }
 
+// dy-fused plan (b_packed == 2): the taps must be a full n_dy x n_dx grid in dy-major order with contiguous offsets.
+// Returns the dynamic smem size or 0 when the shape does not qualify.
+size_t plan_dyfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n, int wp) {
+  const int planes = d.split == 3 ? 2 : 1;
+  if (d.taps < 2) return 0;
+  int n_dx = 1;
+  while (n_dx < d.taps && d.tap_dy[n_dx] == d.tap_dy[0]) ++n_dx;
+  if (d.taps % n_dx) return 0;
+  const int n_dy = d.taps / n_dx;
+  if (n_dy > 8) return 0;
+  for (int t = 0; t < d.taps; ++t)
+    if (d.tap_dy[t] != d.tap_dy[0] + t / n_dx || d.tap_dx[t] != d.tap_dx[0] + t % n_dx) return 0;
+  op.n_dy = n_dy; op.n_dx = n_dx;
+  op.seg_len = gemm::BLOCK_M + n_dx - 1;
+  for (int i = 0; i < n_dy; ++i) op.dy_row_off[i] = (d.tap_dy[0] + i) * wp + d.tap_dx[0];
+  const size_t stage_bytes = (size_t)planes * (2 * (size_t)op.seg_len * 16 + (size_t)n_dx * 2 * block_n * 16);
+  const size_t budget = 227 * 1024 - 1024;
+  if (3 * stage_bytes > budget) return 0;
+  op.nstage = (int)std::min<size_t>(8, budget / stage_bytes);
+  return (size_t)op.nstage * stage_bytes + 1024;
+}
+
+template <int BLOCK_N, int SPLIT>
+int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
+  using Epi = EpiConv<BLOCK_N>;
+  Epi e;
+  e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
+  e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
+  e.residual = d.residual; e.up = d.up; e.py = d.py; e.px = d.px; e.pixel_shuffle = d.pixel_shuffle; e.phase_cols = d.phase_cols; e.c_off = d.c_off;
+  e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
+  e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
+  e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
+  e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  auto kern = gemm::gemm_dyfuse_kernel<BLOCK_N, SPLIT, Epi>;
+  GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
+  kern<<<(unsigned)gx, gemm::num_threads<Epi>(), smem_bytes, s>>>(op, e);
+  GPEMSR_LAUNCH_OK("gemm_dyfuse_kernel<EpiConv>");
+  return GPEMSR_OK;
+}
+
 // Tap-fused plan: segments = distinct tap dy, each covering the dx range of all taps.  Returns the dynamic smem size, or 0
 // when the resident B plus >= 3 A stages do not fit.
 size_t plan_tapfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n, int wp) {
@@ -915,7 +956,7 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (rc != GPEMSR_OK) return rc;
   if ((rc = check_geom(d.a_geom, "igemm(a)")) != GPEMSR_OK) return rc;
   if ((d.out_f32 || d.out_hi || d.residual) && (rc = check_geom(d.o_geom, "igemm(out)")) != GPEMSR_OK) return rc;
-  if (d.taps < 1 || d.taps > gemm::MAX_TAPS || d.k_pad <= 0 || d.k_pad % (d.split == 3 ? 32 : 64) || d.n_cols <= 0)
+  if (d.taps < 1 || d.taps > gemm::MAX_TAPS || d.k_pad <= 0 || d.k_pad % (d.b_packed == 2 ? 16 : d.split == 3 ? 32 : 64) || d.n_cols <= 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: taps=%d k_pad=%d n_cols=%d", d.taps, d.k_pad, d.n_cols);
   if (d.split != 1 && d.split != 3) return set_error(GPEMSR_ERR_UNSUPPORTED, "igemm: split must be 1 or 3");
   if (!d.a_hi || !d.b_hi || (d.split == 3 && (!d.a_lo || (!d.b_lo && !d.b_packed)))) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: null operand");
@@ -961,6 +1002,15 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
   if (!d.b_packed && d.b_rows < op.n_tiles * block_n) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: b_rows=%d < %d", d.b_rows, op.n_tiles * block_n);
   op.a_row0 = d.a_geom.m0; op.err_flag = d.err_flag;
   cudaStream_t s = (cudaStream_t)stream;
+  if (d.b_packed == 2) {                           // large tap grids on narrow layers: weights streamed per (k-slab, dy)
+    const int bn = d.n_cols <= 16 ? 16 : d.n_cols <= 32 ? 32 : 64;
+    if (d.n_cols > 64 || d.pixel_shuffle || d.phase_cols) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: dy-fused weights need n_cols <= 64 and a plain output");
+    const size_t smem = plan_dyfuse(op, d, bn, wp);
+    if (!smem) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: dy-fused weights need a full dy-major tap grid that fits shared memory");
+    if (d.b_rows != bn) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: dy-fused weights were packed for %d columns, this launch uses %d", d.b_rows, bn);
+    if (d.split == 3) return bn == 16 ? launch_dyfuse<16, 3>(op, d, smem, s) : bn == 32 ? launch_dyfuse<32, 3>(op, d, smem, s) : launch_dyfuse<64, 3>(op, d, smem, s);
+    return bn == 16 ? launch_dyfuse<16, 1>(op, d, smem, s) : bn == 32 ? launch_dyfuse<32, 1>(op, d, smem, s) : launch_dyfuse<64, 1>(op, d, smem, s);
+  }
   if (block_n <= 64 && op.n_tiles == 1) {          // narrow outputs: B resident in smem, taps share one A fetch
     const size_t smem = plan_tapfuse(op, d, block_n, wp);
     if (smem && d.b_packed) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: this shape runs the tap-fused kernel, which needs "

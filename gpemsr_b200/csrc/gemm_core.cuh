@@ -54,6 +54,9 @@ struct Operands {
   int tap_seg[MAX_TAPS];       // segment of tap t
   int tap_dx[MAX_TAPS];        // row offset of tap t inside its segment (dx - dx_min)
   int nstage;                  // smem stages that fit next to the resident B
+  // ---- dy-fused mode (gemm_dyfuse_kernel): large tap grids (7x7), weights streamed per (k-slab, dy)
+  int n_dy, n_dx;              // taps = n_dy * n_dx, ordered dy-major
+  int dy_row_off[8];           // first A row of the dy-th segment relative to the tile's first row (dy * wp + dx_min)
 };
 
 template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE>
@@ -555,6 +558,136 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
       }
       if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
     }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      typename Epi::State st{};
+      ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+      if (!ok) break;
+      sm100::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+      if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+    }
+  }
+
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dy-fused variant for LARGE tap grids on narrow layers (SpyNet's 7x7 convolutions, 8..64 channels).  The streaming kernel
+// fetches the A tile once per tap (49x) and the tap-fused kernel needs every tap's weights resident (401 KB for 64x32x49 in
+// (hi, lo) planes: impossible).  Here a pipeline stage is one (16-wide k-slab, tap row dy): ONE A segment of 128 + 2P rows --
+// the n_dx taps of that row are 16-byte start-address shifts inside it -- plus the n_dx weight blocks of that (slab, dy),
+// which arrive as one contiguous copy from a [slab][dy][plane][dx][cell][BLOCK_N][8] packing.  A is read n_dy times instead
+// of n_dy * n_dx times; a stage carries n_dx * SPLIT MMAs.
+template <int BLOCK_N, int SPLIT, class Epi>
+__global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
+gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
+  constexpr int PLANES = SPLIT == 3 ? 2 : 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t seg_bytes = (uint32_t)op.seg_len * 16;                       // one 16-byte k-cell column of the segment
+  const uint32_t a_plane_bytes = 2 * seg_bytes;
+  const uint32_t a_bytes = PLANES * a_plane_bytes;
+  const uint32_t b_tap_bytes = 2 * BLOCK_N * 16;                              // one tap, one plane, one k-slab
+  const uint32_t b_plane_bytes = (uint32_t)op.n_dx * b_tap_bytes;
+  const uint32_t b_bytes = PLANES * b_plane_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* stages = smem;
+  Barriers* bars = reinterpret_cast<Barriers*>(stages + (size_t)op.nstage * stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kiters = (op.k / 16) * op.n_dy;
+  const int nstage = op.nstage;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
+    sm100::fence_mbar_init();
+  }
+  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : 256;
+  if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer: lanes 0 .. 2*PLANES-1 copy the A cell columns, the next lane the weight block ======
+    bool ok = true;
+    uint32_t stage = 0, phase = 0;
+    const bool is_a = lane < 2 * PLANES, is_b = lane == 2 * PLANES;
+    const int plane = lane >> 1, cell = lane & 1;
+    const long long a_slab = 2LL * op.a_rows * 8;                               // elements per k-slab advance of A
+    const __nv_bfloat16* a_base = is_a ? (plane ? op.a_lo : op.a_hi) + ((long long)cell * op.a_rows + op.a_row0) * 8 : nullptr;
+    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+      const __nv_bfloat16* b_src = op.b_hi;
+      int slab = 0, dyi = 0;
+      for (int it = 0; it < kiters && ok; ++it) {
+        ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+        if (!ok) break;
+        uint8_t* st = stages + (size_t)stage * stage_bytes;
+        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
+        __syncwarp();
+        if (is_a)
+          sm100::bulk_g2s(st + (uint32_t)lane * seg_bytes, a_base + slab * a_slab + (m_tile * BLOCK_M + op.dy_row_off[dyi]) * 8,
+                          seg_bytes, &bars->full[stage]);
+        else if (is_b)
+          sm100::bulk_g2s(st + a_bytes, b_src, b_bytes, &bars->full[stage]);
+        b_src += b_bytes / 2;
+        if (++dyi == op.n_dy) { dyi = 0; ++slab; }
+        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (sm100::elect_one()) {
+      constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
+      bool ok = true;
+      // base descriptors: A cells are seg_bytes apart (LBO), B cells BLOCK_N * 16 apart; offsets go into the address field
+      const uint64_t a_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages), seg_bytes, 128);
+      const uint64_t b_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages) + a_bytes, BLOCK_N * 16, 128);
+      for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+        ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+        for (int it = 0; it < kiters && ok; ++it) {
+          ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+          if (!ok) break;
+          sm100::tc_fence_after();
+          const uint64_t sa = a_desc0 + (uint64_t)(stage * (stage_bytes >> 4));
+          const uint64_t sb = b_desc0 + (uint64_t)(stage * (stage_bytes >> 4));
+          for (int dx = 0; dx < op.n_dx; ++dx) {
+            const uint64_t a_hi = sa + (uint64_t)dx;                               // one row = one 16-byte unit
+            const uint64_t b_hi = sb + (uint64_t)(dx * (b_tap_bytes >> 4));
+            sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | dx) != 0);
+            if constexpr (SPLIT == 3) {
+              sm100::umma_bf16(tmem_acc, a_hi + (a_plane_bytes >> 4), b_hi, idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi, b_hi + (b_plane_bytes >> 4), idesc, true);
+            }
+          }
+          sm100::umma_commit(&bars->empty[stage]);
+          if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
+          if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+        }
+        if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;

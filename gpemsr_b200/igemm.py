@@ -107,13 +107,31 @@ class Weights:
         else:
             raise ValueError(kind)
         self.n, self.k = n, k
+        self.taps = [(dy, dx) for _, dy, dx in taps]
+        src = torch.tensor([t[0] for t in taps], dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        if kind == 'conv' and len(taps) > 9 and n <= 64 and not plain and self._full_grid():
+            # large tap grids on narrow layers (SpyNet's 7x7): weights streamed per (16-wide k slab, tap row) -- the layout
+            # [slab][dy][plane][dx][cell][block_n][8] makes every pipeline stage's weights one contiguous copy
+            bn = 16 if n <= 16 else 32 if n <= 32 else 64
+            k16 = _round_up(k, 16)
+            n_dx = sum(1 for dy, _ in self.taps if dy == self.taps[0][0])
+            n_dy = len(taps) // n_dx
+            planes = []
+            for _ in range(2 if split == 3 else 1):
+                planes.append(torch.empty(len(taps), k16 // 8, bn, 8, dtype=torch.bfloat16, device=dev))
+            _lib.check(L.gpemsr_pack_weights(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src), bn, k16,
+                                             _lib.ptr(planes[0]), _lib.ptr(planes[1]) if split == 3 else None, _lib.stream_ptr()))
+            st = torch.stack([p.view(n_dy, n_dx, k16 // 16, 2, bn, 8) for p in planes])      # [plane, dy, dx, slab, cell, bn, 8]
+            self.hi = st.permute(3, 1, 0, 2, 4, 5, 6).contiguous()                              # [slab, dy, plane, dx, cell, bn, 8]
+            self.lo = None
+            self.packed, self.b_rows, self.k_pad = 2, bn, k16
+            self._keep = (w, src)
+            return
         self.k_pad = _round_up(k, 32 if split == 3 else 64)      # one k-chunk of the streaming kernel (narrow inputs: less padding)
         self.b_rows = _round_up(n, 16) if n <= 16 else _round_up(n, 64) if n <= 64 else _round_up(n, 128) if n <= 128 \
             else _round_up(n, block_rows)
         self.b_rows = max(self.b_rows, min_rows)
-        self.taps = [(dy, dx) for _, dy, dx in taps]
-        src = torch.tensor([t[0] for t in taps], dtype=torch.int32, device=dev)
-        L = _lib.lib()
         # ask the library which kernel variant this shape runs: the streaming kernel wants the tiled single-copy layout
         d = IgemmDesc()
         d.n_cols, d.k_pad, d.taps, d.split, d.pixel_shuffle = n, self.k_pad, len(taps), split, int(pixel_shuffle)
@@ -121,7 +139,7 @@ class Weights:
             d.tap_dy[i], d.tap_dx[i] = dy, dx
         bn, fused = C.c_int32(), C.c_int32()
         _lib.check(L.gpemsr_igemm_plan(C.byref(d), C.byref(bn), C.byref(fused)))
-        self.packed = (not fused.value) and min_rows == 0 and not plain
+        self.packed = int((not fused.value) and min_rows == 0 and not plain)
         if self.packed:
             nbytes = L.gpemsr_pack_weights_tiled_bytes(n, self.k_pad, len(taps), bn.value, split)
             self.hi = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
@@ -135,6 +153,17 @@ class Weights:
             _lib.check(L.gpemsr_pack_weights(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src),
                                              self.b_rows, self.k_pad, _lib.ptr(self.hi), _lib.ptr(self.lo), _lib.stream_ptr()))
         self._keep = (w, src)
+
+
+def _is_full_grid(taps):
+    """taps: list of (dy, dx) -- a full rectangular grid in dy-major order with unit steps?"""
+    n_dx = sum(1 for dy, _ in taps if dy == taps[0][0])
+    if len(taps) % n_dx:
+        return False
+    return all(t == (taps[0][0] + i // n_dx, taps[0][1] + i % n_dx) for i, t in enumerate(taps))
+
+
+Weights._full_grid = lambda self: _is_full_grid(self.taps)
 
 
 def convT_phase_taps(py, px):
