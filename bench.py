@@ -12,7 +12,9 @@ reference):
     a-3  Decoder.multi_scale_feat_calculate on the 5 quantised latents  (-> 5 x 1 x 1280 x 1280 reference images)
     f-1  VGG19 relu1_2 patch-similarity mask of the reference images vs the bilinearly upsampled LR frames
          (model/GPEMSR.py:344-353: 2 x (conv 3->64, conv 64->64) on 5 x 1280 x 1280, 16 x 16 patch cosine -> 5 x 1 x 80 x 80)
-    a-5  the 60 flow_warp calls SpyNet makes per forward (5 frames x 2 calls x 6 pyramid levels, 3 x 10^2 .. 3 x 320^2)
+    f-3  SpyNet on the 10 (neighbour, centre) frame pairs of the window (model/GPEMSR.py:99-100: 5 frames x 2 identical
+         calls, frames upsampled x4 to 320 x 320), 6 pyramid levels of five 7x7 convs each, and inside it
+    a-5  the 60 flow_warp calls (10 pairs x 6 levels, 3 x 10^2 .. 3 x 320^2)
     a-4  the SR tail on the fused 64 x 80 x 80 feature (-> 1 x 1 x 1280 x 1280)
 
 `value` times the step with inputs resident in HBM; `e2e` re-times it through the same public API with every step
@@ -45,12 +47,6 @@ IDX_CFG = dict(channel_list=[64, 64, 128, 256, 512], im_channel=1, num_resblock_
 METRIC, UNIT = 'hr_megapixels_per_s', 'MP/s'
 
 
-def warp_levels(lr):
-    """SpyNet pyramid sizes for frames upsampled x4 (model/GPEMSR.py:99) and resized to a multiple of 32."""
-    s = -(-(4 * lr) // 32) * 32
-    return [s >> k for k in range(5, -1, -1)]
-
-
 def make_inputs(lr, nframes, seed, pin=False):
     g = torch.Generator().manual_seed(seed)
     ins = {
@@ -58,12 +54,17 @@ def make_inputs(lr, nframes, seed, pin=False):
         'fea': torch.randn(1, 64, lr, lr, generator=g),                    # ThreeDA output
         'x_center': torch.rand(1, 1, lr, lr, generator=g),
     }
-    for i, s in enumerate(warp_levels(lr)):
-        ins[f'warp_x{i}'] = torch.randn(2 * nframes, 3, s, s, generator=g)       # one batch row per SpyNet call
-        ins[f'warp_f{i}'] = 1.5 * torch.randn(2 * nframes, s, s, 2, generator=g)
     if pin:
         ins = {k: v.pin_memory() for k, v in ins.items()}
     return ins
+
+
+def spynet_pairs(frames_x4, nframes):
+    """The (ref, supp) batches of model/GPEMSR.py:99-100: for every frame i, spynet(frame_i, centre) -- issued twice."""
+    idx = torch.arange(nframes, device=frames_x4.device).repeat(2)
+    ref = frames_x4.index_select(0, idx)
+    supp = frames_x4[nframes // 2:nframes // 2 + 1].expand(2 * nframes, -1, -1, -1).contiguous()
+    return ref, supp
 
 
 def make_weights(seed=1):
@@ -90,34 +91,42 @@ class NativeHotPath:
         from gpemsr_b200.vgg import VGG19Slice1
         self.vgg = VGG19Slice1().to(device)
         self.vgg.load_reference_state_dict(wts['vgg'])
+        from gpemsr_b200.spynet import SpyNet
+        self.spy = SpyNet().to(device)
+        self.spy.load_state_dict({**wts['spy'], 'mean': self.spy.mean, 'std': self.spy.std}, strict=True)
 
     def step(self, d):
         feat = self.idx.features(d['lr_frames'])
         zq = self.cb.inference_from_feat(feat, self.idx.embedding.weight.detach(), self.idx.embedding.bias.detach())
         feats = self.dec.multi_scale_feat_calculate(zq)
         mask = self.vgg.similarity_mask(feats[-1], d['lr_frames'], SCALE)
-        nlev = len([k for k in d if k.startswith('warp_x')])
-        for i in range(nlev):
-            x, f = d[f'warp_x{i}'], d[f'warp_f{i}']
-            for j in range(x.shape[0]):                 # the reference issues these one SpyNet level at a time
-                self.g.flow_warp(x[j:j + 1], f[j:j + 1], 'bilinear', 'border')
+        from gpemsr_b200.spynet import resize_bilinear
+        x4 = resize_bilinear(d['lr_frames'], 4 * d['lr_frames'].shape[2], 4 * d['lr_frames'].shape[3], False, scale=4)
+        flows = self.spy(*spynet_pairs(x4, x4.shape[0]))
         out = self.tail(d['fea'], d['x_center'])
-        return out, feats + [mask]
+        return out, feats + [mask, flows]
 
 
 # ----------------------------------------------------------------------------------------------- reference (CPU) arm
+_CPU_SPY = []
+
+
+def _cpu_spynet(wts):
+    if not _CPU_SPY:
+        from oracle.basicsr_shim import SpyNet
+        m = SpyNet().eval()
+        m.load_state_dict({**wts['spy'], 'mean': m.mean, 'std': m.std}, strict=True)
+        _CPU_SPY.append(m)
+    return _CPU_SPY[0]
+
+
 def cpu_step(wts, ins):
     from oracle import ref_ops as R
-    from oracle.flow_warp import flow_warp_torch
     with torch.no_grad():
         feats, _ = R.ref_extract(ins['lr_frames'], wts['idx'], wts['emb'], wts['dec'])
         feats = feats + [R.similarity_mask(feats[-1], ins['lr_frames'], wts['vgg'], SCALE)]
-        i = 0
-        while f'warp_x{i}' in ins:
-            x, f = ins[f'warp_x{i}'], ins[f'warp_f{i}']
-            for j in range(x.shape[0]):
-                flow_warp_torch(x[j:j + 1], f[j:j + 1], 'bilinear', 'border')
-            i += 1
+        x4 = torch.nn.functional.interpolate(ins['lr_frames'], scale_factor=4, mode='bilinear', align_corners=False)
+        feats = feats + [_cpu_spynet(wts)(*spynet_pairs(x4, x4.shape[0]))]
         out = R.sr_tail(ins['fea'], ins['x_center'], wts['tail'], SCALE)
     return out, feats
 
@@ -276,8 +285,7 @@ def micro_rooflines(peaks):
     by = 8.0 * c * s * s + 8.0 * s * s
     out['flow_warp'] = {'bound': 'hbm', 'shape': f'{c} x {s}^2', 'ms': ms, 'achieved': by / ms / 1e6, 'peak': peaks['hbm'],
                         'unit': 'GB/s', 'frac': by / ms / 1e6 / peaks['hbm']}
-    # SpyNet on the window's 10 (neighbour, centre) pairs at 320^2: built and parity-tested, reported here
-    # and NOT yet part of the step -- its 7x7 convs still re-read the activations once per tap
+    # SpyNet alone, on the window's 10 (neighbour, centre) pairs at 320^2
     try:
         from gpemsr_b200.spynet import SpyNet, resize_bilinear
         from oracle import weights as W
@@ -291,7 +299,7 @@ def micro_rooflines(peaks):
         fl = 2.0 * 49 * (8 * 32 + 32 * 64 + 64 * 32 + 32 * 16 + 16 * 2) * ref.shape[0] * (4 * LR) ** 2 * (4.0 / 3.0)
         out['spynet'] = {'bound': 'tensor', 'shape': f'{ref.shape[0]} pairs x {4 * LR}^2, 6 levels', 'ms': ms, 'achieved': fl / ms / 1e9,
                          'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': fl / ms / 1e9 / peaks['tf'],
-                         'note': 'not part of the step yet; 49-tap streaming GEMMs are L2-operand bound'}
+                         'note': 'dy-fused 49-tap GEMMs + resize / pool / pack / flow_warp helpers, 6 levels'}
     except Exception as e:                                # a diagnostic extra must never take the bench line down
         out['spynet'] = {'error': repr(e)[:200]}
     return out
@@ -316,8 +324,8 @@ def run_reference(args, rank, world):
 
 
 def config_block(world):
-    return {'workload': f'GPEMSR x16 hot path (Indexer16 conv stack + head + codebook lookup, VQ decoder multi-scale, VGG relu1_2 similarity mask, 60 SpyNet flow_warp '
-                        f'calls, SR tail), {NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
+    return {'workload': f'GPEMSR x16 hot path (Indexer16 conv stack + head + codebook lookup, VQ decoder multi-scale, VGG relu1_2 similarity mask, '
+                        f'SpyNet on the 10 frame pairs incl. its 60 flow_warp calls, SR tail), {NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
             'lr': LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
             'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '
             'exceeds the 126 MB L2; no explicit flush', 'precision': 'bf16 x3 split (fp32-faithful) on tcgen05'}
