@@ -14,7 +14,7 @@ reference):
          (model/GPEMSR.py:344-353: 2 x (conv 3->64, conv 64->64) on 5 x 1280 x 1280, 16 x 16 patch cosine -> 5 x 1 x 80 x 80)
     f-3  SpyNet on the 10 (neighbour, centre) frame pairs of the window (model/GPEMSR.py:99-100: 5 frames x 2 identical
          calls, frames upsampled x4 to 320 x 320), 6 pyramid levels of five 7x7 convs each, and inside it
-    a-5  the 60 flow_warp calls (10 pairs x 6 levels, 3 x 10^2 .. 3 x 320^2)
+    a-5  its 60 warps (10 pairs x 6 levels, 3 x 10^2 .. 3 x 320^2; batched: 6 flow_warp launches)
     a-4  the SR tail on the fused 64 x 80 x 80 feature (-> 1 x 1 x 1280 x 1280)
 
 `value` times the step with inputs resident in HBM; `e2e` re-times it through the same public API with every step
