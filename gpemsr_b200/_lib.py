@@ -39,6 +39,7 @@ SIGNATURES = {
     'gpemsr_igemm': (_i, [_p, _p]),
     'gpemsr_act_pack_nchw': (_i, [_p, _i, _p, _i, _p, _p, _p, _p]),
     'gpemsr_act_unpack_nchw': (_i, [_p, _i, _p, _i, _p, _p]),
+    'gpemsr_deform_im2col': (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
     'gpemsr_resize_bilinear': (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
     'gpemsr_avg_pool2': (_i, [_p, _i64, _i, _i, _p, _p]),
     'gpemsr_pack_concat3': (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p]),

@@ -483,6 +483,53 @@ __global__ void act_unpack_nchw_kernel(const float* __restrict__ f32, int c, Geo
   }
 }
 
+// ------------------------------------------------------------------------------------------------ DCNv2 (deformable im2col)
+// torchvision.ops.deform_conv2d (modulated, 3x3, stride 1, pad 1, dilation 1) as a gather + a plain GEMM.  One thread = one
+// (pixel, tap k, deformable group g): the group's 8 channels are ONE 32-byte fp32 cell of the input, sampled bilinearly at
+// (y - 1 + ky + off_y, x - 1 + kx + off_x) with torchvision's border rule (a sample outside (-1, H) x (-1, W) is 0; corners
+// outside the image contribute 0), multiplied by sigmoid(mask) and written as operand cell (k * groups + g) of the
+// [pixels x 9 * C] im2col matrix (hi, lo planes).  The weights then act as a 1x1 convolution over those 9 * C channels.
+// `om` is the conv_offset output in NCHW fp32 [n, 3 * groups * 9, h, w]: offset pair (y, x) of (g, k) = channels
+// 2 * (g * 9 + k), + 1 ; mask logit of (g, k) = channel 2 * groups * 9 + g * 9 + k  (BasicSR DCNv2Pack: cat(o1, o2), mask).
+__global__ void deform_im2col_kernel(const float* __restrict__ xf32, Geom gx, int groups, const float* __restrict__ om,
+                                     uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, Geom go) {
+  const long long hw = (long long)gx.h * gx.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (img, k, g, pixel): pixel fastest
+  if (t >= (long long)gx.n * 9 * groups * hw) return;
+  const long long p = t % hw;
+  const int g = (int)((t / hw) % groups), k = (int)((t / (hw * groups)) % 9), img = (int)(t / (hw * groups * 9));
+  const int y = (int)(p / gx.w), x = (int)(p % gx.w);
+  const float* o = om + (long long)img * 3 * groups * 9 * hw + p;
+  const int gk = g * 9 + k;
+  const float off_y = __ldg(o + (long long)(2 * gk) * hw), off_x = __ldg(o + (long long)(2 * gk + 1) * hw);
+  const float ml = __ldg(o + (long long)(2 * groups * 9 + gk) * hw);
+  const float mask = 1.0f / (1.0f + expf(-ml));
+  const float sy = (float)(y - 1 + k / 3) + off_y, sx = (float)(x - 1 + k % 3) + off_x;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (sy > -1.f && sx > -1.f && sy < (float)gx.h && sx < (float)gx.w) {
+    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float w4[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int yy = y0 + (c >> 1), xx = x0 + (c & 1);
+      if (yy >= 0 && yy < gx.h && xx >= 0 && xx < gx.w) {
+        const float* cell = xf32 + ((size_t)g * gx.rows_alloc + place_row(gx, img, yy, xx)) * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(cell)), b = __ldg(reinterpret_cast<const float4*>(cell + 4));
+        v[0] = fmaf(w4[c], a.x, v[0]); v[1] = fmaf(w4[c], a.y, v[1]); v[2] = fmaf(w4[c], a.z, v[2]); v[3] = fmaf(w4[c], a.w, v[3]);
+        v[4] = fmaf(w4[c], b.x, v[4]); v[5] = fmaf(w4[c], b.y, v[5]); v[6] = fmaf(w4[c], b.z, v[6]); v[7] = fmaf(w4[c], b.w, v[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= mask;
+  }
+  uint4 h4, l4;
+  split8(v, h4, l4);
+  const size_t dst = (size_t)(k * groups + g) * go.rows_alloc + place_row(go, img, y, x);
+  out_hi[dst] = h4;
+  if (out_lo) out_lo[dst] = l4;
+}
+
 // ------------------------------------------------------------------------------------------------ SpyNet helpers
 // ATen upsample_bilinear2d (the arithmetic of F.interpolate(mode='bilinear')) with the source index computed the way ATen
 // does: align_corners ? dst * (in-1)/(out-1) : max((dst + 0.5) * (in/out or 1/scale_factor) - 0.5, 0).
@@ -1096,6 +1143,23 @@ int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int 
   const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
   act_unpack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f32, c, to_geom(*g), c_off, x);
   GPEMSR_LAUNCH_OK("act_unpack_nchw_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_deform_im2col(const float* x_f32, const gpemsr_geom_t* gx, int channels, int deform_groups, const float* offset_mask,
+                         void* out_hi, void* out_lo, const gpemsr_geom_t* go, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!x_f32 || !gx || !go || !offset_mask || !out_hi || deform_groups <= 0 || channels != 8 * deform_groups)
+    return set_error(GPEMSR_ERR_UNSUPPORTED, "deform_im2col: built for channels == 8 * deformable_groups (one cell per group; "
+                     "GPEMSR: 64 channels, 8 groups), 3x3, stride 1, padding 1");
+  if ((rc = check_geom(*gx, "deform_im2col(x)")) != GPEMSR_OK || (rc = check_geom(*go, "deform_im2col(out)")) != GPEMSR_OK) return rc;
+  if (go->n != gx->n || go->h != gx->h || go->w != gx->w) return set_error(GPEMSR_ERR_BAD_SHAPE, "deform_im2col: geometries differ");
+  const long long total = (long long)gx->n * 9 * deform_groups * gx->h * gx->w;
+  deform_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x_f32, to_geom(*gx), deform_groups, offset_mask, (uint4*)out_hi, (uint4*)out_lo, to_geom(*go));
+  GPEMSR_LAUNCH_OK("deform_im2col_kernel");
   return GPEMSR_OK;
 }
 

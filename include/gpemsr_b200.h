@@ -160,6 +160,14 @@ GPEMSR_API int gpemsr_act_pack_nchw(const float* x, int c, const gpemsr_geom_t* 
                          float* f32, void* hi, void* lo, gpemsr_stream_t stream);
 GPEMSR_API int gpemsr_act_unpack_nchw(const float* f32, int c, const gpemsr_geom_t* g, int c_off, float* x,
                            gpemsr_stream_t stream);
+/* ---- DCNv2 (BasicSR DCNv2Pack -> torchvision.ops.deform_conv2d; model/GPEMSR.py:79-94, 123-150) ----
+ * Deformable im2col for the modulated 3x3 / stride 1 / padding 1 case with channels == 8 * deformable_groups: x_f32 = fp32
+ * master cells of the input in geometry gx; offset_mask = the conv_offset output, NCHW fp32 [n, 3 * groups * 9, h, w]
+ * (channels 2(g*9+k), +1 = the (y, x) offset of group g, tap k; channel 2*groups*9 + g*9 + k = its mask logit); the result
+ * is the [pixels x 9 * channels] operand (cell k * groups + g) in geometry `go`, ready for a one-tap gpemsr_igemm() with the
+ * weight reordered to [co][k * channels + ci].  Samples follow torchvision's border rule (zero outside (-1, H) x (-1, W)). */
+GPEMSR_API int gpemsr_deform_im2col(const float* x_f32, const gpemsr_geom_t* gx, int channels, int deform_groups,
+                         const float* offset_mask, void* out_hi, void* out_lo, const gpemsr_geom_t* go, gpemsr_stream_t stream);
 /* ---- SpyNet helpers (basicsr SpyNet.process / forward; reached from model/GPEMSR.py:99-100) ----
  * gpemsr_resize_bilinear: F.interpolate(mode='bilinear') with ATen's source-index arithmetic (rh / rw = ATen's
  *   area_pixel_compute_scale, computed by the host in fp32), plus the elementwise work SpyNet wraps around it:
