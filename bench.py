@@ -68,7 +68,7 @@ def spynet_pairs(frames_x4, nframes):
 
 
 def make_weights(seed=1):
-    from oracle import weights as W      # deterministic random-init parameters (no checkpoints offline)
+    from gpemsr_b200 import synth_weights as W      # deterministic random-init parameters (no checkpoints offline)
     return dict(dec=W.fill(W.decoder_spec(), seed), emb=W.fill(W.codebook_spec(), seed + 1)['embedding.weight'],
                 idx=W.fill(W.indexer_spec(16), seed + 2), vgg=W.fill(W.vgg_slice1_spec(), seed + 4),
                 spy=W.fill(W.spynet_spec(), seed + 5, gain=2.0), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
@@ -288,7 +288,7 @@ def micro_rooflines(peaks):
     # SpyNet alone, on the window's 10 (neighbour, centre) pairs at 320^2
     try:
         from gpemsr_b200.spynet import SpyNet, resize_bilinear
-        from oracle import weights as W
+        from gpemsr_b200 import synth_weights as W
         spy = SpyNet().cuda()
         spy.load_state_dict({**W.fill(W.spynet_spec(), 6, gain=2.0), 'mean': spy.mean, 'std': spy.std}, strict=True)
         fr = torch.rand(NFRAMES, 1, LR, LR, device='cuda')

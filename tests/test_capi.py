@@ -62,3 +62,21 @@ def test_sass_is_blackwell_native():
     for mnem in ('UTCHMMA', 'LDTM', 'UBLKCP'):
         assert mnem in sass.stdout, mnem
     assert 'HGMMA' not in sass.stdout
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: importing the whole product package (every host mirror) must not pull it in, and no
+    product source may name it in an import."""
+    import glob
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ('import sys; import gpemsr_b200; import gpemsr_b200.indexer, gpemsr_b200.vgg, gpemsr_b200.spynet, gpemsr_b200.dcn, '
+            'gpemsr_b200.volume, gpemsr_b200.graph, gpemsr_b200.synth_weights; '
+            'assert not [m for m in sys.modules if m == "oracle" or m.startswith("oracle.")], "oracle imported"')
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    for f in glob.glob(os.path.join(root, 'gpemsr_b200', '*.py')):
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', open(f).read(), re.M), f
