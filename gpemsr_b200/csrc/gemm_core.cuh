@@ -657,9 +657,14 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
       constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
       uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
       bool ok = true;
-      // base descriptors: A cells are seg_bytes apart (LBO), B cells BLOCK_N * 16 apart; offsets go into the address field
-      const uint64_t a_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages), seg_bytes, 128);
-      const uint64_t b_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages) + a_bytes, BLOCK_N * 16, 128);
+      // descriptors differ only in their low word (LBO << 16 | start address >> 4); the high word (SBO = 128 B, version 1) is
+      // a constant, so the issuing thread does 32-bit adds only.  Measured: every M = 128, K = 16 MMA costs >= ~60 cycles
+      // whatever N <= 64 is (the 4 KB A operand fetch from shared memory), so these narrow layers run at ~N/128 of the tensor
+      // rate; keeping the (small) weight sets resident instead of streaming them was measured and changes nothing.
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_base = (((seg_bytes >> 4) & 0x3FFFu) << 16) | (sm100::smem_u32(stages) >> 4);
+      const uint32_t b_lo_base = ((((uint32_t)BLOCK_N * 16 >> 4) & 0x3FFFu) << 16) | ((sm100::smem_u32(stages) + a_bytes) >> 4);
+      const uint32_t a_pl = a_plane_bytes >> 4, b_pl = b_plane_bytes >> 4, b_tap = b_tap_bytes >> 4;
       for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
         ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
         if (!ok) break;
@@ -669,15 +674,14 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
           ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
           if (!ok) break;
           sm100::tc_fence_after();
-          const uint64_t sa = a_desc0 + (uint64_t)(stage * (stage_bytes >> 4));
-          const uint64_t sb = b_desc0 + (uint64_t)(stage * (stage_bytes >> 4));
-          for (int dx = 0; dx < op.n_dx; ++dx) {
-            const uint64_t a_hi = sa + (uint64_t)dx;                               // one row = one 16-byte unit
-            const uint64_t b_hi = sb + (uint64_t)(dx * (b_tap_bytes >> 4));
+          uint32_t a = a_lo_base + stage * (stage_bytes >> 4);
+          uint32_t b = b_lo_base + stage * (stage_bytes >> 4);
+          for (int dx = 0; dx < op.n_dx; ++dx, ++a, b += b_tap) {                   // one row = one 16-byte unit
+            const uint64_t a_hi = ((uint64_t)kDescHi << 32) | a, b_hi = ((uint64_t)kDescHi << 32) | b;
             sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | dx) != 0);
             if constexpr (SPLIT == 3) {
-              sm100::umma_bf16(tmem_acc, a_hi + (a_plane_bytes >> 4), b_hi, idesc, true);
-              sm100::umma_bf16(tmem_acc, a_hi, b_hi + (b_plane_bytes >> 4), idesc, true);
+              sm100::umma_bf16(tmem_acc, ((uint64_t)kDescHi << 32) | (a + a_pl), b_hi, idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi, ((uint64_t)kDescHi << 32) | (b + b_pl), idesc, true);
             }
           }
           sm100::umma_commit(&bars->empty[stage]);
