@@ -71,3 +71,46 @@ def test_dcnv2pack_lr_resolution(cuda_dev):
     got = m(x.cuda(), feat.cuda())
     m.check()
     assert (got.cpu() - want).abs().max().item() <= 5e-5 * max(1.0, want.abs().max().item())
+
+
+def test_x8_config1_chain_vs_oracle(cuda_dev):
+    """BASELINE configs[0] (x8, 32 x 32 LR -> 256 x 256, option/output_GPEMSR_x8.yml) through the x8 variants of every stage:
+    lrGenerator8.ref_extract (Indexer8 with its DownBlock -> fused lookup -> decoder on the 16 x 16 latents) and the VGG
+    mask at scale 8 (mask on the H/2 grid, model/GPEMSR.py:395-403), against the CPU oracle on the same weights."""
+    from gpemsr_b200.indexer import lrGenerator8
+    from gpemsr_b200.vgg import VGG19Slice1
+    icfg = dict(channel_list=[64, 64, 128, 256, 512], im_channel=1, num_resblock_per_scale=2, num_output_resblck=3, latent_dim=512,
+                use_non_local=True)
+    dcfg = dict(channel_list=[512, 256, 128, 64, 64], im_channel=1, num_resblock_per_scale=1, num_input_resblck=3, latent_dim=512,
+                use_non_local=True)
+    args = dict(Indexer8=icfg, Decoder=dcfg, Codebook=dict(num_codebook_vectors=1024, latent_dim=512, beta=1))
+    sd_i = W.fill(W.indexer_spec(8), seed=211)
+    sd_d = W.fill(W.decoder_spec(), seed=212)
+    emb = W.fill(W.codebook_spec(), seed=213, gain=300.0)['embedding.weight']
+    gen = lrGenerator8(args).cuda()
+    gen.indexer.load_state_dict(sd_i, strict=True)
+    gen.decoder.load_state_dict(sd_d, strict=True)
+    gen.codebook.embedding.weight.data.copy_(emb)
+    x = torch.rand(3, 1, 32, 32, generator=torch.Generator().manual_seed(214))          # BASELINE: 3-slice 32 x 32 stack
+    feat = gen.indexer.features(x.cuda())
+    gen.indexer.check()
+    want_feat = R.indexer_features(x, sd_i)
+    assert tuple(feat.shape) == (3, 512, 16, 16)
+    assert (feat.cpu() - want_feat).abs().max().item() <= 1e-4 * max(1.0, want_feat.abs().max().item())
+    # downstream of the (discrete) lookup: decode the ORACLE's indices' neighbourhood by feeding the GPU's own features to the
+    # oracle tail, so a near-tied logit cannot make the comparison flaky
+    head = {'embedding.weight': sd_i['embedding.weight'], 'embedding.bias': sd_i['embedding.bias']}
+    want, _ = R.ref_extract_from_feat(feat.cpu(), head, emb, sd_d)
+    got = gen.ref_extract(x.cuda())
+    gen.decoder.check()
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
+    assert tuple(got[-1].shape) == (3, 1, 256, 256)
+    for a, b in zip(got, want):
+        assert (a.cpu() - b).abs().max().item() <= 1e-3 * max(1.0, b.abs().max().item())
+    sd_v = W.fill(W.vgg_slice1_spec(), seed=215)
+    vgg = VGG19Slice1().cuda()
+    vgg.load_reference_state_dict(sd_v)
+    mask = vgg.similarity_mask(got[-1], x.cuda(), 8)
+    vgg.check()
+    assert tuple(mask.shape) == (3, 1, 16, 16)                       # view(B*N, 1, H//2, W//2), model/GPEMSR.py:403
+    assert (mask.cpu() - R.similarity_mask(got[-1].cpu(), x, sd_v, 8)).abs().max().item() <= 1e-5
