@@ -809,59 +809,6 @@ __global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, co
 }
 
 // ------------------------------------------------------------------------------------------------ softmax
-__global__ void softmax_stats_kernel(const float* __restrict__ s, long long t, long long ld, float* __restrict__ stats) {
-  const long long row = blockIdx.x;
-  const float* p = s + row * ld;
-  float mx = -INFINITY;
-  for (long long j = threadIdx.x; j < t; j += blockDim.x) mx = fmaxf(mx, p[j]);
-  __shared__ float red[32];
-#pragma unroll
-  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  mx = red[0];
-  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
-  __syncthreads();
-  float sum = 0.f;
-  for (long long j = threadIdx.x; j < t; j += blockDim.x) sum += expf(p[j] - mx);
-#pragma unroll
-  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
-    stats[row * 2] = mx;
-    stats[row * 2 + 1] = tot;
-  }
-}
-
-// p = exp(s - max) / sum -> (hi, lo) cells, transposed at 16-byte-cell granularity through shared memory:
-// reads are coalesced along j (a warp reads 32 consecutive 32-byte score groups of one row), writes along i.
-__global__ void softmax_write_kernel(const float* __restrict__ s, long long t, long long ld, long long t_pad,
-                                     const float* __restrict__ stats, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
-  __shared__ uint4 th[32][33], tl[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 32 threads
-  const long long i = (long long)blockIdx.y * 32 + ty, jc = (long long)blockIdx.x * 32 + tx;
-  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (i < t && jc * 8 < t) {
-    const float mx = stats[i * 2], inv_den = stats[i * 2 + 1];
-    const float4 a = *reinterpret_cast<const float4*>(s + i * ld + jc * 8), b = *reinterpret_cast<const float4*>(s + i * ld + jc * 8 + 4);
-    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (jc * 8 + j < t) ? expf(x[j] - mx) / inv_den : 0.f;
-  }
-  uint4 h, l;
-  split8(v, h, l);
-  th[ty][tx] = h; tl[ty][tx] = l;
-  __syncthreads();
-  const long long oi = (long long)blockIdx.y * 32 + tx, ojc = (long long)blockIdx.x * 32 + ty;   // lanes along i
-  if (oi < t_pad && ojc < t_pad / 8) {
-    *reinterpret_cast<uint4*>(p_hi + ((size_t)ojc * t_pad + oi) * 8) = th[tx][ty];
-    if (p_lo) *reinterpret_cast<uint4*>(p_lo + ((size_t)ojc * t_pad + oi) * 8) = tl[tx][ty];
-  }
-}
-
 // ---- softmax over scores stored as K8-blocked fp32 cells [t_pad/8][rows_alloc][8] (row i = query, cell = 8 consecutive keys).
 // Lanes <-> consecutive rows, so every cell access of a warp is one contiguous 1 KB run; no transpose is needed because the
 // probabilities are written back in the same cell order (that is the A-operand layout of the P v^T GEMM).
@@ -1305,22 +1252,6 @@ int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const f
       x_f32, c, to_geom(*g), scale_shift, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
       out_nchw);
   GPEMSR_LAUNCH_OK("affine_act_kernel");
-  return GPEMSR_OK;
-}
-
-int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t_pad, float* row_stats, void* p_hi, void* p_lo,
-                                gpemsr_stream_t stream) {
-  using namespace gpemsr;
-  int rc = check_device_current();
-  if (rc != GPEMSR_OK) return rc;
-  if (!s || !row_stats || !p_hi || t <= 0 || ld < t || ld % 8 || t_pad < t || t_pad % 8)
-    return set_error(GPEMSR_ERR_BAD_SHAPE, "softmax_rows_blocked: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  softmax_stats_kernel<<<(unsigned)t, 256, 0, st>>>(s, t, ld, row_stats);
-  GPEMSR_LAUNCH_OK("softmax_stats_kernel");
-  dim3 grid((unsigned)((t_pad / 8 + 31) / 32), (unsigned)((t_pad + 31) / 32));
-  softmax_write_kernel<<<grid, 1024, 0, st>>>(s, t, ld, t_pad, row_stats, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo);
-  GPEMSR_LAUNCH_OK("softmax_write_kernel");
   return GPEMSR_OK;
 }
 

@@ -343,11 +343,6 @@ def group_norm_act(x, gamma, beta, scratch, out, act=ACT_NONE, slope=0.0, residu
                                    _lib.ptr(out_nchw), st))
 
 
-def softmax_rows_blocked(s, t, ld, t_pad, stats, p_hi, p_lo):
-    _lib.check(_lib.lib().gpemsr_softmax_rows_blocked(_lib.ptr(s), t, ld, t_pad, _lib.ptr(stats), _lib.ptr(p_hi),
-                                                      _lib.ptr(p_lo), _lib.stream_ptr()))
-
-
 def softmax_cells_blocked(s_cells, t, rows_alloc, t_pad, scratch, p_hi, p_lo):
     _lib.check(_lib.lib().gpemsr_softmax_cells_blocked(_lib.ptr(s_cells), t, rows_alloc, t_pad, _lib.ptr(scratch), _lib.ptr(p_hi),
                                                        _lib.ptr(p_lo), _lib.stream_ptr()))

@@ -228,13 +228,9 @@ GPEMSR_API int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t*
                       float* out_f32, void* out_hi, void* out_lo, float* out_nchw /* [n,c,h,w] or NULL */,
                       gpemsr_stream_t stream);
 
-/* softmax over the last dim of fp32 scores s [t, ld] (first t columns valid; model/blocks.py:76) ->
- * probabilities as K8-blocked bf16 A operand planes [t_pad/8][t_pad][8] (hi, lo). */
-GPEMSR_API int gpemsr_softmax_rows_blocked(const float* s, int64_t t, int64_t ld, int64_t t_pad, float* row_stats /* [t,2] */,
-                                void* p_hi, void* p_lo, gpemsr_stream_t stream);
-
-/* same softmax on scores stored as K8-blocked fp32 cells [t_pad/8][rows_alloc][8] (the igemm out_f32 format with keys as
- * "channels"): coalesced without a transpose.  scratch: 2*t*(1+16) floats. */
+/* softmax over the keys of attention scores (model/blocks.py:76) stored as K8-blocked fp32 cells [t_pad/8][rows_alloc][8] (the
+ * igemm out_f32 format with keys as "channels"): coalesced without a transpose; probabilities come out as K8-blocked bf16 A
+ * operand planes [t_pad/8][t_pad][8] (hi, lo).  scratch: 2*t*(1+16) floats. */
 GPEMSR_API int gpemsr_softmax_cells_blocked(const float* s_cells, int64_t t, int64_t rows_alloc, int64_t t_pad, float* scratch,
                                  void* p_hi, void* p_lo, gpemsr_stream_t stream);
 
