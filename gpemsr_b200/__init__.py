@@ -9,6 +9,7 @@ meaning and error behaviour) over the C ABI in ``include/gpemsr_b200.h``:
   * ``SRTail``                          -- model/GPEMSR.py:441-455
   * ``SpyNet``                          -- basicsr/archs/spynet_arch.py (7x7 convs + flow_warp, coarse to fine)
   * ``VGG19Slice1``                     -- model/VGG.py slice1 + the patch-similarity mask of model/GPEMSR.py:344-353
+  * ``GPEMSR``                          -- model/GPEMSR.py (the whole model: reference fusion, POD, ThreeDA, SR tail)
   * ``Indexer16`` / ``Indexer8`` / ``lrGenerator16`` / ``lrGenerator8`` (inference methods) -- model/indexer.py, model/vqgan_indexer.py
 
 The CUDA library is mandatory: nothing here falls back to PyTorch or the CPU.
@@ -21,5 +22,6 @@ from .sr_tail import SRTail  # noqa: F401
 from .indexer import Indexer8, Indexer16, lrGenerator8, lrGenerator16  # noqa: F401
 from .spynet import SpyNet  # noqa: F401
 from .vgg import VGG19Slice1  # noqa: F401
+from .gpemsr import GPEMSR  # noqa: F401
 
-__all__ = ['flow_warp', 'Decoder', 'SRTail', 'Indexer16', 'Indexer8', 'lrGenerator16', 'lrGenerator8', 'SpyNet', 'VGG19Slice1', 'Codebook', 'vq_lookup', 'logits_argmax_gather', 'argmax_gather', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']
+__all__ = ['GPEMSR', 'flow_warp', 'Decoder', 'SRTail', 'Indexer16', 'Indexer8', 'lrGenerator16', 'lrGenerator8', 'SpyNet', 'VGG19Slice1', 'Codebook', 'vq_lookup', 'logits_argmax_gather', 'argmax_gather', 'GpemsrError', 'lib', 'kernel_launches', 'LIB_PATH']

@@ -56,6 +56,13 @@ SIGNATURES = {
     'gpemsr_softmax_cells_blocked': (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     'gpemsr_border_phase_conv': (_i, [_p, _i, _p, _p, _p, _i, _p, _p]),
     'gpemsr_add_bilinear_base': (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    'gpemsr_cells_upsample2x': (_i, [_p, _p, _i, _f, _p, _i, _p, _p, _p, _p]),
+    'gpemsr_cells_mul_mask': (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    'gpemsr_cells_pool3x3s2': (_i, [_p, _p, _i, _p, _p, _p, _p]),
+    'gpemsr_cells_copy': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    'gpemsr_temporal_attn_scale': (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    'gpemsr_threeda_combine': (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    'gpemsr_conv3x3_direct': (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     'gpemsr_selftest_gemm_workspace_bytes': (_sz, [_i64, _i, _i]),
     'gpemsr_selftest_gemm': (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _sz, _p]),
     'gpemsr_selftest_gemm_status': (_i, [_p, _i64, _i, _i, _p]),

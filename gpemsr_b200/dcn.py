@@ -74,5 +74,27 @@ class DCNv2Pack(nn.Module):
         self._last_err = P['err']
         return out
 
+    def run_acts(self, P, name, x_f32, g, feat, out, err, act=G.ACT_NONE, slope=0.0, c_off=0, out_f32=True, out_planes=True):
+        """The same three launches on tensors already in the internal format (used by ``gpemsr_b200.GPEMSR``'s POD): x_f32 =
+        fp32 master cells of the input (64 channels, geometry g), feat = Act with the offset features' operand planes; the
+        result goes to channel slot c_off of Act `out` with `act` fused.  `P` is the caller's buffer / weight cache."""
+        c = self.in_channels
+        w_off = P.wts.get(name + '.off')
+        if w_off is None:
+            w_off = P.wts[name + '.off'] = G.Weights(self.conv_offset.weight, 'conv', split=self.split)
+            P.wts[name + '.main'] = G.Weights(self.weight.detach().permute(0, 2, 3, 1).reshape(self.out_channels, 9 * c).contiguous(),
+                                              'linear', split=self.split)
+        key = f'dcn.om{g.key()}'
+        om = P.bufs.get(key)
+        if om is None:
+            om = P.bufs[key] = torch.empty(g.n, 3 * self.deformable_groups * 9, g.h, g.w, dtype=torch.float32, device=x_f32.device)
+        col = P.act(f'dcn.col{g.key()}', g, 9 * c, f32=False)
+        G.igemm(feat, w_off, err, split=self.split, bias=self.conv_offset.bias.detach(), out_nchw=om, nchw_c=om.shape[1])
+        gc = g.c
+        _lib.check(_lib.lib().gpemsr_deform_im2col(_lib.ptr(x_f32), C.byref(gc), c, self.deformable_groups, _lib.ptr(om),
+                                                   _lib.ptr(col.hi), _lib.ptr(col.lo), C.byref(gc), _lib.stream_ptr()))
+        G.igemm(col, P.wts[name + '.main'], err, split=self.split, bias=self.bias.detach(), act=act, slope=slope, out=out,
+                c_off=c_off, out_f32=out_f32, out_planes=out_planes)
+
     def check(self):
         G.check_pipeline(self._last_err)

@@ -1,0 +1,463 @@
+"""Host-side mirror of the whole reference model ``GPEMSR`` (model/GPEMSR.py:237-456) with ``POD`` (:64-150) and ``ThreeDA``
+(:153-234) on the sm_100a kernels: the drop-in for ``output_GPEMSR.py:36-52`` (same constructor arguments, same parameter
+names, ``forward(x f32[B, N, 1, H, W]) -> (out f32[B, 1, sH, sW], ref_img f32[B, N, 1, sH, sW])``).
+
+The nn.Modules only HOLD parameters under the reference's names; ``forward`` chains the C-ABI kernels:
+
+  * every convolution is ``gpemsr_igemm`` (stride-2 convs = space-to-depth + 2x2 taps, ConvTranspose2d = merged parity phases,
+    Conv3d(k=1) over the frame axis = a 1x1 conv with the Kronecker-expanded weight) with bias / LeakyReLU / residual fused;
+  * ``torch.cat(...) -> conv`` pairs never materialise the concatenation: producers write into channel slots of one operand
+    buffer per resolution, laid out so that BOTH consumers of a level read a contiguous channel range
+    (``[R_j | carried_j | LRfeat_j | decoder_j]``: ``down_fea_conv`` / ``reduce_dim_conv`` read the head, ``reffusionconv``
+    the tail, with its input channels permuted once on the host);
+  * the glue between the convolutions (bilinear x2, mask multiply, 3x3/s2 max+avg pool, temporal attention, the ThreeDA
+    combination, the strided flow convs) are the HBM-bound kernels of ``csrc/fusion_ops.cu``;
+  * the five frames of a window are one batch everywhere (``POD`` runs once on 5 (neighbour, centre) pairs; the reference's
+    duplicated SpyNet call (:99-100) is evaluated once).
+
+Inference only, CUDA only (no CPU fallback).  ``refmodel.encoder.*`` (training only) and ``vgg.slice2..5`` (never reach an
+output) are not instantiated: ``load_state_dict`` drops those keys of a reference checkpoint and loads the rest strictly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import igemm as G
+from .dcn import DCNv2Pack
+from .decoder import _Plan, _View
+from .indexer import lrGenerator8, lrGenerator16
+from .spynet import SpyNet, resize_bilinear
+from .sr_tail import LRELU_SLOPE, ResidualBlockNoBN, SRTail
+from .vgg import VGG19Slice1
+
+DEAD_PREFIXES = ('refmodel.encoder.', 'vgg.slice2.', 'vgg.slice3.', 'vgg.slice4.', 'vgg.slice5.')
+
+
+def _conv(cin, cout, k=3, s=1, p=1):
+    return nn.Conv2d(cin, cout, k, s, p, bias=True)
+
+
+class POD(nn.Module):                                            # parameter holder for model/GPEMSR.py:64-97
+    def __init__(self, nf=64, groups=8, precision='fp32'):
+        super().__init__()
+        self.spynet = SpyNet(precision=precision)
+        self.flowdsconv0_1, self.flowdsconv0_2 = _conv(2, 16, 3, 4, 1), _conv(2, 16, 3, 4, 1)
+        self.flowdsconv1_1, self.flowdsconv1_2 = _conv(16, 16, 3, 2, 1), _conv(16, 16, 3, 2, 1)
+        self.flowdsconv2_1, self.flowdsconv2_2 = _conv(16, 16, 3, 2, 1), _conv(16, 16, 3, 2, 1)
+        dcn = lambda: DCNv2Pack(nf, nf, 3, stride=1, padding=1, dilation=1, deformable_groups=groups, precision=precision)
+        self.L3_offset_conv1, self.L3_offset_conv2 = _conv(nf * 2 + 34, nf), _conv(nf, nf)
+        self.L3_dcnpack = dcn()
+        self.L2_offset_conv1, self.L2_offset_conv2, self.L2_offset_conv3 = _conv(nf * 2 + 34, nf), _conv(nf * 2, nf), _conv(nf, nf)
+        self.L2_dcnpack = dcn()
+        self.L2_fea_conv = _conv(nf * 2, nf)
+        self.L1_offset_conv1, self.L1_offset_conv2, self.L1_offset_conv3 = _conv(nf * 2 + 34, nf), _conv(nf * 2, nf), _conv(nf, nf)
+        self.L1_dcnpack = dcn()
+        self.L1_fea_conv = _conv(nf * 2, nf)
+        self.cas_offset_conv1, self.cas_offset_conv2 = _conv(nf * 2, nf), _conv(nf, nf)
+        self.cas_dcnpack = dcn()
+
+
+class ThreeDA(nn.Module):                                        # parameter holder for model/GPEMSR.py:153-179
+    def __init__(self, num_feat=64, num_frame=5, center_frame_idx=2):
+        super().__init__()
+        self.center_frame_idx = center_frame_idx
+        nf, t = num_feat, num_frame
+        self.temporal_attn1, self.temporal_attn2 = _conv(nf, nf), _conv(nf, nf)
+        self.feat_fusion = _conv(t * nf, nf, 1, 1, 0)
+        self.conv3D_1 = nn.Conv3d(t, t, kernel_size=1, bias=True)
+        self.conv3D_2 = nn.Conv3d(t, t, kernel_size=1, bias=True)
+        self.conv3D_fusion_1, self.conv3D_fusion_2 = _conv(t * nf, nf, 1, 1, 0), _conv(t * nf, nf, 1, 1, 0)
+        self.conv2D_fusion_3 = _conv(nf, nf, 1, 1, 0)
+        self.spatial_attn1 = _conv(t * nf, nf, 1, 1, 0)
+        self.spatial_attn2 = _conv(nf * 2, nf, 1, 1, 0)
+        self.spatial_attn3 = _conv(nf, nf)
+        self.spatial_attn4 = _conv(nf, nf, 1, 1, 0)
+        self.spatial_attn5 = _conv(nf, nf)
+        self.spatial_attn_l1 = _conv(nf, nf, 1, 1, 0)
+        self.spatial_attn_l2 = _conv(nf * 2, nf)
+        self.spatial_attn_l3 = _conv(nf, nf)
+        self.spatial_attn_add1, self.spatial_attn_add2 = _conv(nf, nf, 1, 1, 0), _conv(nf, nf, 1, 1, 0)
+
+
+class _Bias:
+    """Stand-in for a module whose weight / bias were rebuilt on the host (Kronecker-expanded Conv3d)."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class GPEMSR(SRTail):
+    def __init__(self, ref_path_G=None, ref_path_Indexer=None, argref=None, nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10,
+                 w_ref=True, ref_fusion_feat_RBs=3, align_mode='POD', fusion_mode='ThreeDA', mode='16to1', scale=16,
+                 precision='fp32'):
+        """Constructor arguments of model/GPEMSR.py:238-241.  ``ref_path_G`` / ``ref_path_Indexer`` (the hard-coded
+        ``torch.load`` paths of :275-284) are loaded into ``refmodel`` when given; pass None and load a state dict instead."""
+        if not (w_ref and align_mode == 'POD' and fusion_mode == 'ThreeDA' and nf == 64):
+            raise _lib.GpemsrError(-6, 'GPEMSR: built for the configuration of option/output_GPEMSR_x{8,16}.yml '
+                                       '(w_ref, POD alignment, ThreeDA fusion, nf = 64)')
+        if (mode, scale) not in (('16to1', 16), ('8to1', 8)):
+            raise ValueError('scale is wrong!')                                    # model/GPEMSR.py:299
+        super().__init__(nf=nf, back_RBs=back_RBs, scale=scale, precision=precision)
+        self.center, self.w_ref, self.align_mode, self.fusion_mode, self.mode, self.nframes = nframes // 2, w_ref, align_mode, fusion_mode, mode, nframes
+        self.conv_first = _conv(1, nf)
+        self.feature_extraction = nn.Sequential(*[ResidualBlockNoBN(nf) for _ in range(front_RBs)])
+        self.vgg = VGG19Slice1(precision=precision)
+        self.refmaskconv1, self.refmaskconv2, self.refmaskconv3 = _conv(1, nf), _conv(nf, nf), _conv(nf, 1)
+        for k in (2, 3, 4):
+            setattr(self, f'reffea_L{k}_conv1', nn.ConvTranspose2d(nf, nf, 3, 2, 1, 1, bias=True))
+        for j, cin in enumerate((nf + 64, 2 * nf + 128, 3 * nf + 256, 4 * nf + 512)):
+            setattr(self, f'reffusionconv{j + 1}', _conv(cin, nf))
+            setattr(self, f'fusion_fea_block{j + 1}', nn.Sequential(*[ResidualBlockNoBN(nf) for _ in range(ref_fusion_feat_RBs)]))
+        for j in (1, 2, 3):
+            setattr(self, f'down_fea_conv{j}', _conv(nf * j, nf * j, 3, 2, 1))
+        self.reduce_dim_conv = _conv((5 if scale == 16 else 4) * nf, nf, 1, 1, 0)
+        self.refmodel = (lrGenerator16 if scale == 16 else lrGenerator8)(argref, precision=precision)
+        if ref_path_G:
+            self.refmodel.load_state_dict({k: v for k, v in torch.load(ref_path_G, map_location='cpu').items()
+                                           if not k.startswith('encoder.')}, strict=False)
+        if ref_path_Indexer:
+            self.refmodel.indexer.load_state_dict(torch.load(ref_path_Indexer, map_location='cpu'), strict=True)
+        self.fea_L2_conv1, self.fea_L2_conv2 = _conv(nf, nf, 3, 2, 1), _conv(nf, nf)
+        self.fea_L3_conv1, self.fea_L3_conv2 = _conv(nf, nf, 3, 2, 1), _conv(nf, nf)
+        self.align_module = POD(nf=nf, groups=groups, precision=precision)
+        self.ThreeDA = ThreeDA(num_feat=nf, num_frame=nframes, center_frame_idx=self.center)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.debug = None                 # set to a dict to collect NCHW copies of intermediate tensors (tests)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts the reference model's ``state_dict()``: the parameters of modules that never run in inference
+        (``refmodel.encoder``, ``vgg.slice2..5``) are dropped, everything else loads with ``strict``."""
+        return super().load_state_dict({k: v for k, v in state_dict.items() if not k.startswith(DEAD_PREFIXES)}, strict=strict, **kw)
+
+    def check(self):
+        """Synchronise and raise if any GEMM pipeline of the last forward timed out (tests / smoke)."""
+        G.check_pipeline(self._last_plan.err)
+        for m in (self.refmodel.indexer, self.refmodel.decoder, self.vgg, self.align_module.spynet):
+            m.check()
+
+    # ------------------------------------------------------------------ helpers
+    def _c(self, P, name, mod, x, out, act=G.ACT_NONE, weight=None, **kw):
+        wt = P.wts.get(name)
+        if wt is None:
+            wt = P.wts[name] = G.Weights(mod.weight if weight is None else weight, 'conv', split=P.split)
+        G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
+
+    def _s2conv(self, P, name, mod, x, out, act=G.ACT_NONE, **kw):
+        """Conv2d(k3, s2, p1) = space-to-depth + 2x2 taps (model/GPEMSR.py:257,260,263,288,290)."""
+        g = x.geom
+        og = G.Geom(g.n, (g.h + 1) // 2, (g.w + 1) // 2, True)
+        s2d = P.act(name + '.s2d', og, 4 * x.c, f32=False)
+        G.space_to_depth(x, s2d)
+        wt = P.wts.get(name)
+        if wt is None:
+            m, taps = G.down_conv_weight(mod.weight.detach())
+            wt = P.wts[name] = G.Weights(m, 'conv', taps=taps, split=P.split)
+        G.igemm(s2d, wt, P.err, split=P.split, bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
+
+    def _convT(self, P, name, mod, x, out, **kw):
+        """lrelu(ConvTranspose2d(k3, s2, p1, op1)) as ONE GEMM over the four output-parity phases (:335-340)."""
+        wt = P.wts.get(name)
+        if wt is None:
+            wt = P.wts[name] = G.Weights(G.convT_merged_weight(mod.weight.detach()), 'conv', taps='offsets01', split=P.split)
+            wt.bias4 = mod.bias.detach().repeat(4).contiguous()
+        G.igemm(x, wt, P.err, split=P.split, bias=wt.bias4, act=G.ACT_LRELU, slope=LRELU_SLOPE, out=out, up=2,
+                phase_cols=mod.weight.shape[1], **kw)
+
+    def _rbs(self, P, name, blocks, cur, g):
+        """make_layer(ResidualBlockNoBN): x + conv2(relu(conv1(x))); `cur` carries fp32 master + planes."""
+        t = P.act(f'rbt{g.key()}', g, self.nf, f32=False)
+        pp = [P.act(f'rba{g.key()}', g, self.nf, f32=True), P.act(f'rbb{g.key()}', g, self.nf, f32=True)]
+        for i, rb in enumerate(blocks):
+            self._c(P, f'{name}.{i}.1', rb.conv1, cur, t, act=G.ACT_RELU, out_f32=False)
+            nxt = pp[0] if cur is not pp[0] else pp[1]
+            self._c(P, f'{name}.{i}.2', rb.conv2, t, nxt, residual=cur.f32)
+            cur = nxt
+        return cur
+
+    @staticmethod
+    def _view(act, c0, c):
+        """Channels [c0, c0 + c) of an activation buffer as an operand of their own (same geometry, same row stride)."""
+        v = _View(act.hi[c0 // 8:], None if act.lo is None else act.lo[c0 // 8:], act.geom)
+        v.f32 = None if act.f32 is None else act.f32[c0 // 8:]
+        v.c = c
+        return v
+
+    @staticmethod
+    def _up2(x_f32, gi, c, out, c_off=0, mul=1.0, f32=False, planes=True):
+        gic, goc = gi.c, out.geom.c
+        _lib.check(_lib.lib().gpemsr_cells_upsample2x(_lib.ptr(x_f32), C.byref(gic), c, float(mul), C.byref(goc), c_off,
+                                                      _lib.ptr(out.f32) if f32 else None, _lib.ptr(out.hi) if planes else None,
+                                                      _lib.ptr(out.lo) if planes else None, _lib.stream_ptr()))
+
+    @staticmethod
+    def _copy(src, src_c_off, c, dst, c_off, bcast_t=0, center=0, f32=False):
+        gs, gd = src.geom.c, dst.geom.c
+        _lib.check(_lib.lib().gpemsr_cells_copy(_lib.ptr(src.f32) if f32 else None, _lib.ptr(src.hi), _lib.ptr(src.lo), C.byref(gs),
+                                                src_c_off, c, bcast_t, center, C.byref(gd), c_off, _lib.ptr(dst.f32) if f32 else None,
+                                                _lib.ptr(dst.hi), _lib.ptr(dst.lo), _lib.stream_ptr()))
+
+    def _tap(self, name, act, c=None, c_off=0):
+        if self.debug is not None:
+            self.debug[name] = act if isinstance(act, torch.Tensor) else G.unpack_nchw(act, act.c if c is None else c, c_off)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x):
+        if not x.is_cuda:
+            raise _lib.GpemsrError(-3, 'GPEMSR needs CUDA tensors: there is no CPU fallback')
+        B, N, Cc, H, W = x.shape
+        if Cc != 1 or N != self.nframes:
+            raise ValueError(f'expected x of shape [B, {self.nframes}, 1, H, W]')
+        if H % 4 or W % 4 or min(H, W) < 16:
+            raise _lib.GpemsrError(-1, 'GPEMSR: H and W must be multiples of 4 and >= 16 (the POD pyramid halves them twice and '
+                                       'SpyNet needs a 64-pixel input at x4)')
+        outs, refs = [], []
+        for b in range(B):                                       # windows are independent (output_GPEMSR.py runs B = 1)
+            o, r = self._forward_window(x[b].float().contiguous())
+            outs.append(o)
+            refs.append(r.view(1, N, 1, H * self.scale, W * self.scale))
+        return (outs[0], refs[0]) if B == 1 else (torch.cat(outs), torch.cat(refs))
+
+    def _forward_window(self, x):
+        N, _, H, W = x.shape
+        dev, nf, s, ctr = x.device, self.nf, self.scale, self.center
+        key = ('win', N, H, W, dev.index)
+        P = self._plans.get(key)
+        if P is None:
+            P = self._plans[key] = _Plan(self, N, H, W, dev)
+        self._last_plan = P
+        L = _lib.lib()
+        st = _lib.stream_ptr
+        lre = G.ACT_LRELU
+        J = 4 if s == 16 else 3
+        geo = [G.Geom(N, H << (J - 1 - j), W << (J - 1 - j), True) for j in range(J)]       # finest first
+        g1 = geo[J - 1]
+        U = [P.act(f'U{j}', geo[j], 128 + 64 * j + (64 << j), f32=False) for j in range(J)]  # [R | carried | LR feat | decoder]
+
+        # ---- per-frame LR features (:329-330) and their up-sampled pyramid (:335-340 / 381-384)
+        xin = P.act('x', g1, 1, f32=False)
+        G.pack_nchw(x, xin)
+        f0 = P.act('conv_first', g1, nf, f32=True)
+        self._c(P, 'conv_first', self.conv_first, xin, f0, act=lre)
+        L1 = self._rbs(P, 'fe', self.feature_extraction, f0, g1)
+        self._tap('L1_fea0', L1)
+        self._copy(L1, 0, nf, U[J - 1], 64 + 64 * (J - 1))
+        for j in range(J - 2, -1, -1):                           # lrelu(reffea_L{k}_conv1): level j from level j + 1
+            self._convT(P, f'reffea{j}', getattr(self, f'reffea_L{J - j}_conv1'), self._view(U[j + 1], 64 + 64 * (j + 1), nf),
+                        U[j], c_off=64 + 64 * j, out_f32=False)
+
+        # ---- generative-prior features of every frame (:342 / 385) and the similarity mask (:344-357 / 387-400)
+        feats = self.refmodel.ref_extract(x)
+        ref_img = feats[-1]
+        dec = feats[:-1][::-1]                                   # ref_x2, ref_x4, ref_x8(, ref_x16): finest first
+        for j in range(J):
+            G.pack_nchw(dec[j], U[j], c_off=128 + 64 * j)
+        m0 = self.vgg.similarity_mask(ref_img, x, s)
+        hm, wm = m0.shape[2], m0.shape[3]
+        gm = G.Geom(N, hm, wm, True)
+        ma, mb, mc = P.act('mask.in', gm, 1, f32=False), P.act('mask.a', gm, nf, f32=False), P.act('mask.b', gm, nf, f32=False)
+        G.pack_nchw(m0, ma)
+        self._c(P, 'refmaskconv1', self.refmaskconv1, ma, mb, act=lre, out_f32=False)
+        self._c(P, 'refmaskconv2', self.refmaskconv2, mb, mc, act=lre, out_f32=False)
+        mask = P.bufs.get('mask.out')
+        if mask is None:
+            mask = P.bufs['mask.out'] = torch.empty(N, 1, hm, wm, dtype=torch.float32, device=dev)
+        self._c(P, 'refmaskconv3', self.refmaskconv3, mc, None, act=lre, out_nchw=mask, nchw_c=1)      # sigmoid: in mul_mask
+        self._tap('mask_logit', mask)
+
+        # ---- reference-feature fusion, finest level first (:360-378 / 403-417)
+        for j in range(J):
+            g = geo[j]
+            kin = 64 * j + 64 + (64 << j)
+            conv = getattr(self, f'reffusionconv{j + 1}')
+            wname = f'reffusionconv{j + 1}'
+            if wname not in P.wts:                               # reference input order (LR feat, decoder, carried) -> buffer order
+                w = conv.weight.detach()
+                d = 64 << j
+                P.wts[wname] = G.Weights(torch.cat([w[:, 64 + d:], w[:, :64], w[:, 64:64 + d]], dim=1).contiguous(), 'conv', split=P.split)
+            r = P.act(f'fus.r{g.key()}', g, nf, f32=True)
+            self._c(P, wname, conv, self._view(U[j], 64, kin), r)
+            r = self._rbs(P, f'ffb{j}', getattr(self, f'fusion_fea_block{j + 1}'), r, g)
+            gc = g.c
+            _lib.check(L.gpemsr_cells_mul_mask(_lib.ptr(r.f32), C.byref(gc), nf, _lib.ptr(mask), hm, wm, g.h // hm, 1, 0, None,
+                                               _lib.ptr(U[j].hi), _lib.ptr(U[j].lo), st()))
+            if self.debug is not None:
+                dbg = G.Act(g, nf, x.device, f32=True, planes=False)
+                _lib.check(L.gpemsr_cells_mul_mask(_lib.ptr(r.f32), C.byref(gc), nf, _lib.ptr(mask), hm, wm, g.h // hm, 1, 0,
+                                                   _lib.ptr(dbg.f32), None, None, st()))
+                self._tap(f'fusion.r{j}', dbg)
+            if j < J - 1:
+                self._s2conv(P, f'down_fea_conv{j + 1}', getattr(self, f'down_fea_conv{j + 1}'), self._view(U[j], 0, 64 * (j + 1)),
+                             U[j + 1], c_off=64, out_f32=False)
+        # L1_fea = reduce_dim_conv(cat(R, carried, L1)) -> slot 0 of the level-1 alignment operand (:377-378 / 416-417)
+        gL = [g1, G.Geom(N, H // 2, W // 2, True), G.Geom(N, H // 4, W // 4, True)]
+        catL = [P.act(f'catL{k}', gL[k], 162, f32=True) for k in range(3)]        # [nbr 64 | ref 64 | flow1 16 | flow2 16 | frames 2]
+        self._c(P, 'reduce_dim_conv', self.reduce_dim_conv, self._view(U[J - 1], 0, 128 + 64 * (J - 1)), catL[0])
+        self._tap('L1_fea', catL[0], nf)
+
+        # ---- alignment pyramid (:421-425), all N frames as one batch
+        t64 = [P.act(f't64.{k}', gL[k], nf, f32=False) for k in range(3)]
+        for k in (1, 2):
+            self._s2conv(P, f'fea_L{k + 1}_conv1', getattr(self, f'fea_L{k + 1}_conv1'), self._view(catL[k - 1], 0, nf), t64[k],
+                         act=lre, out_f32=False)
+            self._c(P, f'fea_L{k + 1}_conv2', getattr(self, f'fea_L{k + 1}_conv2'), t64[k], catL[k], act=lre)
+        self._tap('L2_fea', catL[1], nf)
+        self._tap('L3_fea', catL[2], nf)
+        for k in range(3):                                       # the centre frame's features next to every frame's (:426-431)
+            self._copy(catL[k], 0, nf, catL[k], 64, bcast_t=N, center=ctr)
+        aligned = self._pod(P, x, catL, gL, t64)
+        self._tap('aligned', aligned)
+        fea = self._threeda(P, aligned, gL[0])
+        self._tap('fea', fea)
+        out = self._tail(P, fea, x[ctr:ctr + 1])
+        return out, ref_img
+
+    # ------------------------------------------------------------------ POD.forward (:99-150), N (neighbour, centre) pairs at once
+    def _pod(self, P, x, catL, gL, t64):
+        am = self.align_module
+        N, _, H, W = x.shape
+        nf, ctr, lre, dev = self.nf, self.center, G.ACT_LRELU, x.device
+        L = _lib.lib()
+        st = _lib.stream_ptr
+        xc = x[ctr:ctr + 1]
+        nbr4 = resize_bilinear(x, 4 * H, 4 * W, False, scale=4.0)
+        ref4 = resize_bilinear(xc, 4 * H, 4 * W, False, scale=4.0, c_out=N).view(N, 1, 4 * H, 4 * W)
+        flow = am.spynet(nbr4, ref4)                             # :99-100 (both calls are the same function of the same inputs)
+        self._tap('pod.flow', flow)
+        nb, rf = [x], [resize_bilinear(xc, H, W, False, c_out=N).view(N, 1, H, W)]
+        for k in (1, 2):                                         # :107-110
+            h, w = nb[-1].shape[2] // 2, nb[-1].shape[3] // 2
+            nb.append(resize_bilinear(nb[-1], h, w, False, scale=0.5))
+            rf.append(resize_bilinear(rf[-1], h, w, False, scale=0.5))
+        for br in (1, 2):                                        # :101-106  (no activation between the strided convs)
+            f = flow
+            for k in range(3):
+                conv = getattr(am, f'flowdsconv{k}_{br}')
+                n_, ci, hh, ww = f.shape
+                stride = conv.stride[0]
+                o = torch.empty(n_, 16, (hh - 1) // stride + 1, (ww - 1) // stride + 1, dtype=torch.float32, device=dev)
+                _lib.check(L.gpemsr_conv3x3_direct(_lib.ptr(f), n_, ci, hh, ww, _lib.ptr(conv.weight.detach()), _lib.ptr(conv.bias.detach()),
+                                                   16, stride, _lib.ptr(o), st()))
+                G.pack_nchw(o, catL[k], c_off=128 + 16 * (br - 1))
+                f = o
+        for k in range(3):
+            gc = gL[k].c
+            _lib.check(L.gpemsr_pack_concat3(_lib.ptr(nb[k]), 1, _lib.ptr(rf[k]), 1, None, 0, C.byref(gc), _lib.ptr(catL[k].hi[20:]),
+                                             _lib.ptr(catL[k].lo[20:]), st()))
+        cat2 = [P.act(f'cat2.{k}', gL[k], 2 * nf, f32=False) for k in range(3)]
+        oa = [P.act(f'off.a{k}', gL[k], nf, f32=True) for k in range(3)]
+        fe = [P.act(f'fea.{k}', gL[k], nf, f32=True) for k in range(3)]
+        nbr_f32 = lambda k: catL[k].f32                          # channels 0..63 of the level operand = the neighbour features
+
+        # L3 (:112-115)
+        self._c(P, 'L3_offset_conv1', am.L3_offset_conv1, catL[2], t64[2], act=lre, out_f32=False)
+        self._c(P, 'L3_offset_conv2', am.L3_offset_conv2, t64[2], oa[2], act=lre)
+        am.L3_dcnpack.run_acts(P, 'L3_dcn', nbr_f32(2), gL[2], oa[2], fe[2], P.err, act=lre, slope=LRELU_SLOPE, out_planes=False)
+        self._tap('pod.o3', oa[2]); self._tap('pod.fea3', fe[2])
+        # L2 (:117-124)
+        self._c(P, 'L2_offset_conv1', am.L2_offset_conv1, catL[1], cat2[1], act=lre, out_f32=False)
+        self._up2(oa[2].f32, gL[2], nf, cat2[1], c_off=nf, mul=2.0)
+        self._c(P, 'L2_offset_conv2', am.L2_offset_conv2, cat2[1], t64[1], act=lre, out_f32=False)
+        self._c(P, 'L2_offset_conv3', am.L2_offset_conv3, t64[1], oa[1], act=lre)
+        am.L2_dcnpack.run_acts(P, 'L2_dcn', nbr_f32(1), gL[1], oa[1], cat2[1], P.err, out_f32=False)
+        self._up2(fe[2].f32, gL[2], nf, cat2[1], c_off=nf)
+        self._c(P, 'L2_fea_conv', am.L2_fea_conv, cat2[1], fe[1], act=lre, out_planes=False)
+        self._tap('pod.o2', oa[1]); self._tap('pod.fea2', fe[1])
+        # L1 (:126-133)
+        self._c(P, 'L1_offset_conv1', am.L1_offset_conv1, catL[0], cat2[0], act=lre, out_f32=False)
+        self._up2(oa[1].f32, gL[1], nf, cat2[0], c_off=nf, mul=2.0)
+        self._c(P, 'L1_offset_conv2', am.L1_offset_conv2, cat2[0], t64[0], act=lre, out_f32=False)
+        self._c(P, 'L1_offset_conv3', am.L1_offset_conv3, t64[0], oa[0], act=lre)
+        am.L1_dcnpack.run_acts(P, 'L1_dcn', nbr_f32(0), gL[0], oa[0], cat2[0], P.err, out_f32=False)
+        self._up2(fe[1].f32, gL[1], nf, cat2[0], c_off=nf)
+        catC = P.act('catC', gL[0], 2 * nf, f32=True)            # [L1_fea | centre features] (:135)
+        self._c(P, 'L1_fea_conv', am.L1_fea_conv, cat2[0], catC)
+        self._tap('pod.o1', oa[0]); self._tap('pod.fea1', catC, nf)
+        # cascading (:135-138)
+        self._copy(catL[0], 64, nf, catC, 64)
+        self._c(P, 'cas_offset_conv1', am.cas_offset_conv1, catC, t64[0], act=lre, out_f32=False)
+        self._c(P, 'cas_offset_conv2', am.cas_offset_conv2, t64[0], oa[0], act=lre)
+        self._tap('pod.off', oa[0])
+        am.cas_dcnpack.run_acts(P, 'cas_dcn', catC.f32, gL[0], oa[0], fe[0], P.err, act=lre, slope=LRELU_SLOPE)
+        return fe[0]
+
+    # ------------------------------------------------------------------ ThreeDA.forward (:181-234)
+    def _threeda(self, P, aligned, g):
+        td = self.ThreeDA
+        N, nf, ctr, lre = g.n, self.nf, self.center, G.ACT_LRELU
+        L = _lib.lib()
+        st = _lib.stream_ptr
+        dev = aligned.f32.device
+        g1 = G.Geom(1, g.h, g.w, True)
+        g2 = G.Geom(1, (g.h - 1) // 2 + 1, (g.w - 1) // 2 + 1, True)
+        g4 = G.Geom(1, (g2.h - 1) // 2 + 1, (g2.w - 1) // 2 + 1, True)
+        A = lambda name, geom, c, f32, planes=True: P.act('tda.' + name, geom, c, f32=f32, planes=planes)
+        emb, emb_ref = A('emb', g, nf, True, False), A('emb_ref', g1, nf, True, False)
+        self._c(P, 'tda.ta2', td.temporal_attn2, aligned, emb, out_planes=False)
+        self._c(P, 'tda.ta1', td.temporal_attn1, aligned, emb_ref, a_geom=g.sample(ctr), o_geom=g1, out_planes=False)
+        al = A('al', g1, N * nf, False)
+        gc, g1c = g.c, g1.c
+        _lib.check(L.gpemsr_temporal_attn_scale(_lib.ptr(emb.f32), _lib.ptr(emb_ref.f32), _lib.ptr(aligned.f32), C.byref(gc), C.byref(g1c),
+                                                nf, N, C.byref(g1c), _lib.ptr(al.hi), _lib.ptr(al.lo), st()))
+        feat0, feat = A('feat0', g1, nf, True, False), A('feat', g1, nf, True)
+        self._c(P, 'tda.feat_fusion', td.feat_fusion, al, feat0, act=lre, out_planes=False)
+        t3d = A('t3d', g1, N * nf, False)
+        f3 = []
+        for i, (c3, cf) in enumerate(((td.conv3D_1, td.conv3D_fusion_1), (td.conv3D_2, td.conv3D_fusion_2))):
+            kname = f'tda.c3d{i}'
+            k3 = P.bufs.get(kname)
+            if k3 is None:                                       # Conv3d(t, t, k=1) over [b, t, c, h, w] = 1x1 conv with W (x) I_c
+                w = c3.weight.detach().reshape(N, N).float()
+                eye = torch.eye(nf, device=w.device)
+                k3 = P.bufs[kname] = _Bias(torch.kron(w, eye).reshape(N * nf, N * nf, 1, 1).contiguous(),
+                                           c3.bias.detach().float().repeat_interleave(nf).contiguous())
+            self._c(P, kname, k3, al, t3d, act=lre, out_f32=False)
+            if i == 0:                                           # feat = feat + fea_3d1 (:211): the residual epilogue
+                self._c(P, f'tda.c3dfus{i}', cf, t3d, feat, act=lre, residual=feat0.f32)
+                f3.append(None)
+            else:
+                o = A(f'f3d{i}', g1, nf, True, False)
+                self._c(P, f'tda.c3dfus{i}', cf, t3d, o, act=lre, out_planes=False)
+                f3.append(o)
+        f3d3 = A('f3d3', g1, nf, True, False)
+        self._c(P, 'tda.c2dfus3', td.conv2D_fusion_3, feat, f3d3, out_planes=False)
+        # spatial attention (:215-231)
+        a1 = A('a1', g1, nf, True, False)
+        self._c(P, 'tda.sa1', td.spatial_attn1, al, a1, act=lre, out_planes=False)
+        p2 = A('p2', g2, 2 * nf, False)
+        g2c, g4c = g2.c, g4.c
+        _lib.check(L.gpemsr_cells_pool3x3s2(_lib.ptr(a1.f32), C.byref(g1c), nf, C.byref(g2c), _lib.ptr(p2.hi), _lib.ptr(p2.lo), st()))
+        a2 = A('a2', g2, nf, False)
+        self._c(P, 'tda.sa2', td.spatial_attn2, p2, a2, act=lre, out_f32=False)
+        l1 = A('l1', g2, nf, True, False)
+        self._c(P, 'tda.sal1', td.spatial_attn_l1, a2, l1, act=lre, out_planes=False)
+        p4 = A('p4', g4, 2 * nf, False)
+        _lib.check(L.gpemsr_cells_pool3x3s2(_lib.ptr(l1.f32), C.byref(g2c), nf, C.byref(g4c), _lib.ptr(p4.hi), _lib.ptr(p4.lo), st()))
+        l2, l3 = A('l2', g4, nf, False), A('l3', g4, nf, True, False)
+        self._c(P, 'tda.sal2', td.spatial_attn_l2, p4, l2, act=lre, out_f32=False)
+        self._c(P, 'tda.sal3', td.spatial_attn_l3, l2, l3, act=lre, out_planes=False)
+        lup = A('lup', g2, nf, True, False)
+        self._up2(l3.f32, g4, nf, lup, f32=True, planes=False)
+        a3 = A('a3', g2, nf, False)
+        self._c(P, 'tda.sa3', td.spatial_attn3, a2, a3, act=lre, residual=lup.f32, out_f32=False)
+        a4 = A('a4', g2, nf, True, False)
+        self._c(P, 'tda.sa4', td.spatial_attn4, a3, a4, act=lre, out_planes=False)
+        a4u = A('a4u', g1, nf, False)
+        self._up2(a4.f32, g2, nf, a4u)
+        attn = A('attn', g1, nf, True)
+        self._c(P, 'tda.sa5', td.spatial_attn5, a4u, attn)
+        ad1, add = A('ad1', g1, nf, False), A('add', g1, nf, True, False)
+        self._c(P, 'tda.add1', td.spatial_attn_add1, attn, ad1, act=lre, out_f32=False)
+        self._c(P, 'tda.add2', td.spatial_attn_add2, ad1, add, out_planes=False)
+        fea = A('fea', g1, nf, True)
+        _lib.check(L.gpemsr_threeda_combine(_lib.ptr(feat.f32), _lib.ptr(attn.f32), _lib.ptr(add.f32), _lib.ptr(f3[1].f32),
+                                            _lib.ptr(f3d3.f32), C.byref(g1c), nf, _lib.ptr(fea.f32), _lib.ptr(fea.hi), _lib.ptr(fea.lo),
+                                            st()))
+        if self.debug is not None:
+            self._tap('tda.feat', feat); self._tap('tda.f2', f3[1]); self._tap('tda.attn', attn); self._tap('tda.add', add)
+        return fea

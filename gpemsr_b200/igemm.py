@@ -234,7 +234,7 @@ def border_phase_conv(x, wc, bias, cout, out):
 
 
 def _p(t):
-    return None if t is None else t.data_ptr()
+    return None if t is None else t if isinstance(t, int) else t.data_ptr()
 
 
 def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row=False, act=ACT_NONE, slope=0.0,

@@ -54,10 +54,17 @@ class SRTail(nn.Module):
             from .decoder import _Plan
             P = _Plan(self, n, h, w, fea.device)
             self._plans[key] = P
-        sp = P.split
         g = G.Geom(n, h, w, True)
         cur = P.act('in', g, c, f32=True)
         G.pack_nchw(fea.float(), cur)
+        return self._tail(P, cur, x_center)
+
+    def _tail(self, P, cur, x_center):
+        """The tail from an activation already in the internal format (fp32 master + planes): used by ``forward`` and by the
+        whole-model mirror ``gpemsr_b200.GPEMSR``."""
+        sp = P.split
+        g = cur.geom
+        n = g.n
         t = P.act('trunk.t', g, self.nf, f32=False)
         pp = [P.act('trunk.a', g, self.nf, f32=True), P.act('trunk.b', g, self.nf, f32=True)]
         for i, rb in enumerate(self.recon_trunk):          # x + conv2(relu(conv1(x)))
@@ -77,7 +84,7 @@ class SRTail(nn.Module):
         hr = P.act('hr', cur.geom, 64, f32=False)
         G.igemm(cur, P.weights('hr', self.HRconv.weight, 'conv'), P.err, split=sp, bias=self.HRconv.bias.detach(),
                 act=G.ACT_LRELU, slope=LRELU_SLOPE, out=hr, out_f32=False)
-        out = torch.empty(n, 1, cur.geom.h, cur.geom.w, dtype=torch.float32, device=fea.device)
+        out = torch.empty(n, 1, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x_center.device)
         G.igemm(hr, P.weights('last', self.conv_last.weight, 'conv'), P.err, split=sp, bias=self.conv_last.bias.detach(),
                 out_nchw=out, nchw_c=1)
         G.add_bilinear_base(x_center.float(), self.scale, out)

@@ -180,3 +180,39 @@ def spynet_spec():
         for i in range(5):
             _conv(spec, f'basic_module.{lv}.basic_module.{2 * i}', chans[i + 1], chans[i], 7)
     return spec
+
+
+def fill_state(shapes, seed, gain=3.0 ** 0.5, offset_gain=0.5):
+    """Deterministic parameters for a whole module tree given only its ``state_dict`` names and shapes (``gpemsr_b200.GPEMSR``
+    or the reference ``GPEMSR``: same names).  The kind of every tensor is read off its name / rank:
+
+      5-D / 4-D ``weight``: convolution (``reffea_L*_conv1`` / ``upblock``: transposed), bound gain / sqrt(fan_in) (gain
+        sqrt(3) = Kaiming-uniform keeps activations O(1) through the ~60-layer chain); ``conv_offset`` (zero-initialised in
+        BasicSR) gets small random weights (``offset_gain``) so the deformable sampling is exercised with offsets of ~1 pixel;
+      2-D: ``codebook.embedding.weight`` U(+-1/K) (model/codebook.py:13), else Linear;  1-D: GroupNorm affine or bias;
+      ``spynet.mean`` / ``spynet.std``: the ImageNet constants BasicSR registers as buffers."""
+    out = OrderedDict()
+    for name, shape in shapes.items():
+        shape = tuple(shape)
+        g = _gen(seed, name)
+        if name.endswith('spynet.mean'):
+            t = torch.tensor([0.485, 0.456, 0.406]).view(shape)
+        elif name.endswith('spynet.std'):
+            t = torch.tensor([0.229, 0.224, 0.225]).view(shape)
+        elif len(shape) >= 4:
+            transposed = 'upblock' in name or 'reffea_L' in name
+            fan = (shape[0] if transposed else shape[1]) * math.prod(shape[2:])
+            if transposed:
+                fan /= 4.0
+            gn = offset_gain if 'conv_offset' in name else 1.0 if 'spynet' in name else gain
+            t = _uniform(shape, gn / math.sqrt(fan), g)
+        elif len(shape) == 2:
+            t = _uniform(shape, 1.0 / shape[0], g) if name.endswith('codebook.embedding.weight') else _uniform(shape, 1.0 / math.sqrt(shape[1]), g)
+        elif name.endswith('.weight'):                      # GroupNorm scale
+            t = 1.0 + _uniform(shape, 0.2, g)
+        elif name.endswith('.bias') and len(shapes.get(name[:-4] + 'weight', (0, 0))) == 1:
+            t = _uniform(shape, 0.1, g)                     # GroupNorm shift
+        else:
+            t = _uniform(shape, 0.05, g)
+        out[name] = t.contiguous()
+    return out

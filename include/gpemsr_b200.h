@@ -245,6 +245,39 @@ GPEMSR_API int gpemsr_border_phase_conv(const float* x_f32, int cin, const gpems
 GPEMSR_API int gpemsr_add_bilinear_base(const float* x_center, int n, int h, int w, int scale, float* out,
                              gpemsr_stream_t stream);
 
+/* ---- glue of GPEMSR.forward between the convolutions (model/GPEMSR.py:64-234 POD / ThreeDA, :323-440 reference-feature
+ *      fusion and alignment) -- element-wise / resampling kernels on the padded K8-blocked format.  `c`, `c_off` are multiples
+ *      of 8; outputs go to channel slot c_off of the destination buffers (any of f32 / hi / lo may be NULL), so the operands
+ *      of the reference's torch.cat(...) -> conv pairs are assembled in place. ----
+ * gpemsr_cells_upsample2x: F.interpolate(x, scale_factor=2, 'bilinear', align_corners=False) * mul  (:130,132,136,142,144,148,226,231).
+ * gpemsr_cells_mul_mask:   x * F.interpolate(sigmoid?(mask), scale_factor=scale, 'bilinear', align_corners=False); mask is NCHW
+ *                          fp32 [n, 1, hm, wm] (:354-362); sigmoid != 0 applies torch.sigmoid to the mask values first (:357).
+ * gpemsr_cells_pool3x3s2:  cat([MaxPool2d(3,2,1)(x), AvgPool2d(3,2,1)(x)], 1) -> 2c channels (hi, lo planes) (:217-218, 222-223).
+ * gpemsr_cells_copy:       channel-slot copy between buffers of one image size; bcast_t > 0: destination image i reads source
+ *                          image (i / bcast_t) * bcast_t + center (the centre frame's features next to every neighbour's, :421-431).
+ * gpemsr_temporal_attn_scale: ThreeDA temporal attention (:181-196): out[b, i*c + ch] = aligned[b*t + i, ch] *
+ *                          sigmoid(sum_ch emb[b*t + i, ch] * emb_ref[b, ch]); emb / aligned: n = b*t images, emb_ref / out: n = b.
+ * gpemsr_threeda_combine:  feat * sigmoid(attn) * 2 + attn_add + fea_3d2 + fea_3d3 (:232-233).
+ * gpemsr_conv3x3_direct:   Conv2d(cin, cout, 3, stride, padding 1) on CUDA cores, NCHW fp32 in / out [n, cout, (h-1)/stride+1,
+ *                          (w-1)/stride+1] -- POD.flowdsconv* (:71-76, 101-106), a few hundred MACs per output. */
+GPEMSR_API int gpemsr_cells_upsample2x(const float* x_f32, const gpemsr_geom_t* gi, int c, float mul, const gpemsr_geom_t* go,
+                            int c_off, float* out_f32, void* out_hi, void* out_lo, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_cells_mul_mask(const float* x_f32, const gpemsr_geom_t* g, int c, const float* mask, int hm, int wm, int scale,
+                          int sigmoid, int c_off, float* out_f32, void* out_hi, void* out_lo, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_cells_pool3x3s2(const float* x_f32, const gpemsr_geom_t* gi, int c, const gpemsr_geom_t* go, void* out_hi,
+                           void* out_lo, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_cells_copy(const float* src_f32, const void* src_hi, const void* src_lo, const gpemsr_geom_t* gs, int src_c_off,
+                      int c, int bcast_t, int center, const gpemsr_geom_t* gd, int c_off, float* dst_f32, void* dst_hi,
+                      void* dst_lo, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_temporal_attn_scale(const float* emb_f32, const float* emb_ref_f32, const float* aligned_f32,
+                               const gpemsr_geom_t* g, const gpemsr_geom_t* g_ref, int c, int t, const gpemsr_geom_t* g_out,
+                               void* out_hi, void* out_lo, gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_threeda_combine(const float* feat, const float* attn, const float* attn_add, const float* fea_3d2,
+                           const float* fea_3d3, const gpemsr_geom_t* g, int c, float* out_f32, void* out_hi, void* out_lo,
+                           gpemsr_stream_t stream);
+GPEMSR_API int gpemsr_conv3x3_direct(const float* x, int n, int cin, int h, int w, const float* wgt, const float* bias, int cout,
+                          int stride, float* out, gpemsr_stream_t stream);
+
 /* ---- self-test of the tcgen05 GEMM core (used by tests/, not by the product path) ------
  * D[m,n] = A[m,k] * B[n,k]^T, fp32 row-major; split = 1 (single bf16 pass) or 3 (hi/lo bf16,
  * fp32-faithful); block_n in {64,128,256}.  _status() synchronises and reports pipeline time-outs. */

@@ -222,6 +222,38 @@ def gen_vgg_mask(ref):
     _save('vgg_mask_small', x=_np(x), ref_img=_np(ref_img), relu1_2=_np(r12[:1, :, :16, :16]), mask=_np(mask), seed=np.array([81]))
 
 
+def gen_full(ref):
+    """The WHOLE reference model: ``GPEMSR(...)`` built from option/output_GPEMSR_x{8,16}.yml by the reference's own
+    model/GPEMSR.py (through the BasicSR shim), every live parameter overwritten by ``fill_state`` (names / shapes asserted
+    equal to ``gpemsr_b200.GPEMSR``'s own), run on a seeded 5-frame 16 x 16 LR window."""
+    import yaml
+    import gpemsr_b200
+    from gpemsr_b200.gpemsr import DEAD_PREFIXES
+    kw = lambda net: dict(argref=net['argref'], nf=net['nf'], nframes=net['nframes'], groups=net['groups'], front_RBs=net['front_RBs'],
+                          back_RBs=net['back_RBs'], w_ref=net['w_ref'], ref_fusion_feat_RBs=net['ref_fusion_feat_RBs'],
+                          align_mode=net['align_mode'], fusion_mode=net['fusion_mode'], mode=net['mode'])
+    nets, shapes = {}, {}
+    for scale in (8, 16):                                  # the mirror's own names / shapes (before torch.load is neutralised)
+        with open(os.path.join(ref, 'option', f'output_GPEMSR_x{scale}.yml')) as f:
+            nets[scale] = yaml.safe_load(f)['network']
+        mine = gpemsr_b200.GPEMSR(None, None, scale=scale, **kw(nets[scale]))
+        shapes[scale] = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    gp = basicsr_shim.install(ref)
+    for scale in (8, 16):
+        model = gp.GPEMSR(ref_path_G=None, ref_path_Indexer=None, scale=scale, **kw(nets[scale])).eval()
+        live = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith(DEAD_PREFIXES)}
+        assert live == shapes[scale], (set(live) ^ set(shapes[scale]))
+        sd = W.fill_state(shapes[scale], seed=900 + scale)
+        res = model.load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys and all(k.startswith(DEAD_PREFIXES) for k in res.missing_keys)
+        x = torch.rand(1, 5, 1, 16, 16, generator=torch.Generator().manual_seed(910 + scale))
+        with torch.no_grad():
+            out, ref_img = model(x)
+        _save(f'full_x{scale}', x=_np(x), out=_np(out), ref_img_sub=_np(ref_img[0, :, 0, ::4, ::4]), seed=np.array([900 + scale]),
+              scale=np.array([scale]))
+    gp._oracle_restore()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference/GPEMSR-CREMI/GPEMSR')
@@ -230,7 +262,7 @@ def main():
     sys.path.insert(0, a.ref)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gens = dict(codebook=gen_codebook, decoder=gen_decoder, blocks=gen_blocks, tail=gen_tail,
-                flow_warp=gen_flow_warp, indexer=gen_indexer, vgg_mask=gen_vgg_mask)
+                flow_warp=gen_flow_warp, indexer=gen_indexer, vgg_mask=gen_vgg_mask, full=gen_full)
     for n, fn in gens.items():
         if a.only and n not in a.only.split(','):
             continue

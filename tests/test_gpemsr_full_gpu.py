@@ -1,0 +1,87 @@
+"""GPU parity of the WHOLE model: ``gpemsr_b200.GPEMSR.forward`` (reference fusion + POD + ThreeDA + SR tail through the C ABI)
+vs the golden outputs of the unmodified reference model/GPEMSR.py and, stage by stage, vs the CPU oracle restatement.
+
+Tolerance (BASELINE north_star): HR image <= 1e-3 max-abs; the stage checks use 1e-3 relative to the stage's max-abs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gpemsr_model as GM
+from full_model_util import build
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+STAGES = ['L1_fea0', 'fusion.r0', 'fusion.r1', 'fusion.r2', 'fusion.r3', 'L1_fea', 'L2_fea', 'L3_fea', 'pod.flow', 'pod.o3', 'pod.fea3',
+          'pod.o2', 'pod.fea2', 'pod.o1', 'pod.fea1', 'pod.off', 'aligned', 'tda.feat', 'tda.f2', 'tda.attn', 'tda.add', 'fea']
+
+
+def _stage_report(model, sd, x, scale):
+    model.debug = {}
+    out, ref_img = model(x.cuda())
+    model.check()
+    dbg, model.debug = model.debug, None
+    taps = {}
+    with torch.no_grad():
+        want_out, want_ref = GM.forward(x, sd, scale, taps)
+    rows, bad = [], []
+    for k in STAGES:
+        if k not in taps:
+            continue
+        w = taps[k]
+        w = torch.cat(w, 0) if isinstance(w, list) else w
+        got = dbg[k].cpu()
+        w = w.reshape(got.shape)
+        e, mx = float((got - w).abs().max()), float(w.abs().max())
+        rows.append(f'{k:10s} err {e:.3e}  max {mx:.3e}')
+        if not e <= 1e-3 * max(1.0, mx):
+            bad.append(k)
+    e_ref = float((ref_img.cpu() - want_ref).abs().max())
+    e_out = float((out.cpu() - want_out).abs().max())
+    rows.append(f'ref_img    err {e_ref:.3e}')
+    rows.append(f'out        err {e_out:.3e}')
+    print('\n'.join(rows))
+    return out, ref_img, want_out, want_ref, bad, rows
+
+
+@pytest.mark.parametrize('scale', [8, 16])
+def test_full_model_golden_and_stages(golden, cuda_dev, scale):
+    g = golden(f'full_x{scale}')
+    model, sd = build(scale, device=cuda_dev)
+    x = T(g['x'])
+    out, ref_img, want_out, want_ref, bad, rows = _stage_report(model, sd, x, scale)
+    assert not bad, (bad, rows)
+    assert tuple(out.shape) == g['out'].shape and tuple(ref_img.shape) == (1, 5, 1, 16 * scale, 16 * scale)
+    assert float(np.abs(out.cpu().numpy() - g['out']).max()) <= 1e-3, rows
+    assert float(np.abs(ref_img[0, :, 0, ::4, ::4].cpu().numpy() - g['ref_img_sub']).max()) <= 1e-3, rows
+    # the second call reuses the cached plan / packed weights and must reproduce the first bit for bit
+    out2, _ = model(x.cuda())
+    assert torch.equal(out, out2)
+
+
+def test_config1_x8_window_32(cuda_dev):
+    """BASELINE configs[0]: x8 on a 5-frame 32 x 32 LR window -> 256 x 256, vs the oracle on the same parameters."""
+    model, sd = build(8, seed=77, device=cuda_dev)
+    x = torch.rand(1, 5, 1, 32, 32, generator=torch.Generator().manual_seed(78))
+    out, ref_img, want_out, want_ref, bad, rows = _stage_report(model, sd, x, 8)
+    assert not bad, (bad, rows)
+    assert float((out.cpu() - want_out).abs().max()) <= 1e-3, rows
+    mse = float(((out.cpu() - want_out) ** 2).mean())
+    assert mse < 1e-8                                  # PSNR delta < 0.01 dB territory: the images differ by ~1e-5
+
+
+def test_x16_non_square_window(cuda_dev):
+    """x16 on a 20 x 24 window (sizes that are not powers of two: SpyNet resizes 80 x 96 -> 96 x 96 internally)."""
+    model, sd = build(16, seed=79, device=cuda_dev)
+    x = torch.rand(1, 5, 1, 20, 24, generator=torch.Generator().manual_seed(80))
+    out, ref_img, want_out, want_ref, bad, rows = _stage_report(model, sd, x, 16)
+    assert not bad, (bad, rows)
+    assert float((out.cpu() - want_out).abs().max()) <= 1e-3, rows
+
+
+def test_rejects_cpu_and_bad_sizes(cuda_dev):
+    import gpemsr_b200
+    model, _ = build(8, device=cuda_dev)
+    with pytest.raises(gpemsr_b200.GpemsrError):
+        model(torch.rand(1, 5, 1, 16, 16))
+    with pytest.raises(gpemsr_b200.GpemsrError):
+        model(torch.rand(1, 5, 1, 18, 16, device='cuda'))

@@ -1,5 +1,6 @@
 """CPU: the oracle restatement reproduces the golden vectors made by the reference's own modules."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import ref_ops as R
@@ -140,3 +141,17 @@ def test_vgg_mask_bitexact(golden):
     assert np.array_equal(r12[:1, :, :16, :16].numpy(), g['relu1_2'])
     mask = R.similarity_mask(T(g['ref_img']), T(g['x']), sd, 16)
     assert np.array_equal(mask.numpy(), g['mask'])
+
+
+@pytest.mark.parametrize('scale', [8, 16])
+def test_full_model_restatement_bitexact(golden, scale):
+    """oracle/gpemsr_model.py (GPEMSR.forward + POD + ThreeDA restated) == the unmodified reference model/GPEMSR.py on the
+    committed window; the parameter names / shapes of the mirror module were asserted equal to the reference's at generation."""
+    from oracle import gpemsr_model as GM
+    from full_model_util import build
+    g = golden(f'full_x{scale}')
+    _, sd = build(scale)
+    with torch.no_grad():
+        out, ref_img = GM.forward(T(g['x']), sd, scale)
+    assert np.array_equal(out.numpy(), g['out'])
+    assert np.array_equal(ref_img[0, :, 0, ::4, ::4].numpy(), g['ref_img_sub'])
