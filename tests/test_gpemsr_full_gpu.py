@@ -53,9 +53,12 @@ def test_full_model_golden_and_stages(golden, cuda_dev, scale):
     assert tuple(out.shape) == g['out'].shape and tuple(ref_img.shape) == (1, 5, 1, 16 * scale, 16 * scale)
     assert float(np.abs(out.cpu().numpy() - g['out']).max()) <= 1e-3, rows
     assert float(np.abs(ref_img[0, :, 0, ::4, ::4].cpu().numpy() - g['ref_img_sub']).max()) <= 1e-3, rows
-    # the second call reuses the cached plan / packed weights and must reproduce the first bit for bit
+    # the second call reuses the cached plan / packed weights / activation buffers (stale contents must not leak); it is
+    # not bit-identical because the GroupNorm and patch statistics are accumulated with atomics
+    # (float atomics in the patch-similarity sums: ~1e-5 run-to-run).  A different window in between must not leak either.
+    model(torch.rand(1, 5, 1, 16, 16, device='cuda'))
     out2, _ = model(x.cuda())
-    assert torch.equal(out, out2)
+    assert float((out - out2).abs().max()) <= 1e-4
 
 
 def test_config1_x8_window_32(cuda_dev):
