@@ -3,25 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--no-cpu-baseline]
 
-A "step" is one pass of the hot path over one slice window of BASELINE.json configs[1]
-(GPEMSR x16, N_frames = 5 per option/output_GPEMSR_x16.yml, 80x80 LR -> 1280x1280 HR; 78x78 cannot run through the
-reference):
+A "step" is ONE WHOLE FORWARD of the model on one slice window of BASELINE.json configs[1] (GPEMSR x16, N_frames = 5 per
+option/output_GPEMSR_x16.yml, 80x80 LR -> 1280x1280 HR; 78x78 cannot run through the reference):
+``gpemsr_b200.GPEMSR.forward(x[1, 5, 1, 80, 80]) -> (out[1, 1, 1280, 1280], ref_img[1, 5, 1, 1280, 1280])``, i.e. everything
+model/GPEMSR.py:323-456 does:
 
-    f-4  Indexer16 conv stack (model/indexer.py) on the 5 x 1 x 80 x 80 LR frames -> 5 x 512 x 80 x 80 features
-    a-2  Indexer head Linear(512->1024) + softmax/top-1 + codebook gather on those features
-    a-3  Decoder.multi_scale_feat_calculate on the 5 quantised latents  (-> 5 x 1 x 1280 x 1280 reference images)
-    f-1  VGG19 relu1_2 patch-similarity mask of the reference images vs the bilinearly upsampled LR frames
-         (model/GPEMSR.py:344-353: 2 x (conv 3->64, conv 64->64) on 5 x 1280 x 1280, 16 x 16 patch cosine -> 5 x 1 x 80 x 80)
-    f-3  SpyNet on the 10 (neighbour, centre) frame pairs of the window (model/GPEMSR.py:99-100: 5 frames x 2 identical
-         calls, frames upsampled x4 to 320 x 320), 6 pyramid levels of five 7x7 convs each, and inside it
-    a-5  its 60 warps (10 pairs x 6 levels, 3 x 10^2 .. 3 x 320^2; batched: 6 flow_warp launches)
-    a-4  the SR tail on the fused 64 x 80 x 80 feature (-> 1 x 1 x 1280 x 1280)
+    per-frame LR features (conv_first + 5 residual blocks) and their ConvTranspose pyramid
+    f-4  Indexer16 conv stack -> a-2 head + softmax/top-1 + codebook gather -> a-3 Decoder.multi_scale_feat_calculate
+    f-1  VGG19 relu1_2 patch-similarity mask (5 x 1280 x 1280, 16 x 16 patch cosine) -> refmaskconv1..3
+    reference-feature fusion at 640^2 / 320^2 / 160^2 / 80^2 (reffusionconv, fusion blocks, mask multiply, strided convs)
+    POD alignment of the 5 (neighbour, centre) pairs: f-3 SpyNet at 320^2 (with a-5 flow_warp inside), strided flow convs,
+         3-level offset pyramid, four DCNv2Pack deformable convolutions
+    ThreeDA fusion (temporal attention, Conv3d frame mixing, 3-level spatial attention)
+    a-4  the SR tail (10 residual blocks, 4 x [conv -> PixelShuffle -> LeakyReLU], HRconv, conv_last, + bilinear base)
 
 `value` times the step with inputs resident in HBM; `e2e` re-times it through the same public API with every step
 input coming from pinned host memory and the HR slice read back.  N > 1: one process per GPU (torchrun), each rank
 processes its own slice windows (weak scaling, no collective on the hot path); the HR slices are all-gathered (NCCL)
-once per step.  `--impl reference` times the CPU restatement of the reference (oracle/, PyTorch fp32, all host cores)
-on a bounded LR crop of the same window.
+once per step.  `--impl reference` times the CPU restatement of the reference's whole forward (oracle/gpemsr_model.py, pinned
+bit-exact to model/GPEMSR.py; PyTorch fp32, all host cores) on a bounded LR crop of the same window.
 """
 from __future__ import annotations
 
@@ -40,95 +40,58 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SCALE, NFRAMES, LR = 16, 5, 80
-DEC_CFG = dict(channel_list=[512, 256, 128, 64, 64], im_channel=1, num_resblock_per_scale=1, num_input_resblck=3,
-               latent_dim=512, use_non_local=True)
-IDX_CFG = dict(channel_list=[64, 64, 128, 256, 512], im_channel=1, num_resblock_per_scale=2, num_output_resblck=3,
-               latent_dim=512, use_non_local=True)                      # option/output_GPEMSR_x16.yml:30-36
 METRIC, UNIT = 'hr_megapixels_per_s', 'MP/s'
+ARGREF = {'Indexer16': dict(channel_list=[64, 64, 128, 256, 512], im_channel=1, num_resblock_per_scale=2, num_output_resblck=3,
+                            latent_dim=512, use_non_local=True),
+          'Codebook': dict(num_codebook_vectors=1024, latent_dim=512, beta=1),
+          'Decoder': dict(channel_list=[512, 256, 128, 64, 64], im_channel=1, num_resblock_per_scale=1, num_input_resblck=3,
+                          latent_dim=512, use_non_local=True)}
+NET = dict(argref=ARGREF, nf=64, nframes=NFRAMES, groups=8, front_RBs=5, back_RBs=10, w_ref=True, ref_fusion_feat_RBs=1,
+           align_mode='POD', fusion_mode='ThreeDA', mode='16to1', scale=SCALE)       # option/output_GPEMSR_x16.yml network block
 
 
 def make_inputs(lr, nframes, seed, pin=False):
     g = torch.Generator().manual_seed(seed)
-    ins = {
-        'lr_frames': torch.rand(nframes, 1, lr, lr, generator=g),          # the LR slice window (EM intensities in [0, 1])
-        'fea': torch.randn(1, 64, lr, lr, generator=g),                    # ThreeDA output
-        'x_center': torch.rand(1, 1, lr, lr, generator=g),
-    }
+    ins = {'x': torch.rand(1, nframes, 1, lr, lr, generator=g)}            # the LR slice window (EM intensities in [0, 1])
     if pin:
         ins = {k: v.pin_memory() for k, v in ins.items()}
     return ins
 
 
-def spynet_pairs(frames_x4, nframes):
-    """The (ref, supp) batches of model/GPEMSR.py:99-100: for every frame i, spynet(frame_i, centre) -- issued twice."""
-    idx = torch.arange(nframes, device=frames_x4.device).repeat(2)
-    ref = frames_x4.index_select(0, idx)
-    supp = frames_x4[nframes // 2:nframes // 2 + 1].expand(2 * nframes, -1, -1, -1).contiguous()
-    return ref, supp
+_MODEL = []
+
+
+def native_model():
+    """The mirror module (CPU, random init); its state_dict names / shapes define the synthetic parameters of BOTH arms."""
+    if not _MODEL:
+        import gpemsr_b200
+        _MODEL.append(gpemsr_b200.GPEMSR(None, None, **NET).eval())
+    return _MODEL[0]
 
 
 def make_weights(seed=1):
     from gpemsr_b200 import synth_weights as W      # deterministic random-init parameters (no checkpoints offline)
-    return dict(dec=W.fill(W.decoder_spec(), seed), emb=W.fill(W.codebook_spec(), seed + 1)['embedding.weight'],
-                idx=W.fill(W.indexer_spec(16), seed + 2), vgg=W.fill(W.vgg_slice1_spec(), seed + 4),
-                spy=W.fill(W.spynet_spec(), seed + 5, gain=2.0), tail=W.fill(W.tail_spec(64, 10, SCALE), seed + 3, gain=3.0 ** 0.5))
+    return W.fill_state({k: tuple(v.shape) for k, v in native_model().state_dict().items()}, seed=seed)
 
 
 # ----------------------------------------------------------------------------------------------- native arm
 class NativeHotPath:
     def __init__(self, wts, device):
-        import gpemsr_b200
-        self.g = gpemsr_b200
-        self.cb = gpemsr_b200.Codebook({'num_codebook_vectors': 1024, 'latent_dim': 512, 'beta': 1}).to(device)
-        self.cb.load_state_dict({'embedding.weight': wts['emb']})
-        self.dec = gpemsr_b200.Decoder(DEC_CFG).to(device)
-        self.dec.load_state_dict(wts['dec'], strict=True)
-        self.tail = gpemsr_b200.SRTail(64, 10, SCALE).to(device)
-        self.tail.load_state_dict(wts['tail'], strict=True)
-        from gpemsr_b200.indexer import Indexer16
-        self.idx = Indexer16(IDX_CFG).to(device)
-        self.idx.load_state_dict(wts['idx'], strict=True)
-        from gpemsr_b200.vgg import VGG19Slice1
-        self.vgg = VGG19Slice1().to(device)
-        self.vgg.load_reference_state_dict(wts['vgg'])
-        from gpemsr_b200.spynet import SpyNet
-        self.spy = SpyNet().to(device)
-        self.spy.load_state_dict({**wts['spy'], 'mean': self.spy.mean, 'std': self.spy.std}, strict=True)
+        self.model = native_model()
+        self.model.load_state_dict(wts, strict=True)
+        self.model.to(device)
 
     def step(self, d):
-        feat = self.idx.features(d['lr_frames'])
-        zq = self.cb.inference_from_feat(feat, self.idx.embedding.weight.detach(), self.idx.embedding.bias.detach())
-        feats = self.dec.multi_scale_feat_calculate(zq)
-        mask = self.vgg.similarity_mask(feats[-1], d['lr_frames'], SCALE)
-        from gpemsr_b200.spynet import resize_bilinear
-        x4 = resize_bilinear(d['lr_frames'], 4 * d['lr_frames'].shape[2], 4 * d['lr_frames'].shape[3], False, scale=4)
-        flows = self.spy(*spynet_pairs(x4, x4.shape[0]))
-        out = self.tail(d['fea'], d['x_center'])
-        return out, feats + [mask, flows]
+        out, ref_img = self.model(d['x'])
+        return out, [ref_img]
 
 
 # ----------------------------------------------------------------------------------------------- reference (CPU) arm
-_CPU_SPY = []
-
-
-def _cpu_spynet(wts):
-    if not _CPU_SPY:
-        from oracle.basicsr_shim import SpyNet
-        m = SpyNet().eval()
-        m.load_state_dict({**wts['spy'], 'mean': m.mean, 'std': m.std}, strict=True)
-        _CPU_SPY.append(m)
-    return _CPU_SPY[0]
-
-
 def cpu_step(wts, ins):
-    from oracle import ref_ops as R
+    from oracle import gpemsr_model as GM           # the restatement of model/GPEMSR.py pinned bit-exact to the reference
     with torch.no_grad():
-        feats, _ = R.ref_extract(ins['lr_frames'], wts['idx'], wts['emb'], wts['dec'])
-        feats = feats + [R.similarity_mask(feats[-1], ins['lr_frames'], wts['vgg'], SCALE)]
-        x4 = torch.nn.functional.interpolate(ins['lr_frames'], scale_factor=4, mode='bilinear', align_corners=False)
-        feats = feats + [_cpu_spynet(wts)(*spynet_pairs(x4, x4.shape[0]))]
-        out = R.sr_tail(ins['fea'], ins['x_center'], wts['tail'], SCALE)
-    return out, feats
+        out, ref_img = GM.forward(ins['x'], wts, SCALE)
+    return out, [ref_img]
 
 
 def cpu_time(wts, lr, steps, warmup):
@@ -144,11 +107,11 @@ def cpu_time(wts, lr, steps, warmup):
 
 
 def pick_cpu_crop(wts, budget_s):
-    """Largest LR crop (multiple of 4, <= 80) whose step fits `budget_s`, from a 16x16 probe (cost ~ pixels)."""
+    """Largest LR crop (multiple of 4, 16..80) whose forward fits `budget_s`, from a 16x16 probe (cost ~ pixels)."""
     dt, _ = cpu_time(wts, 16, 1, 1)
     per_px = dt / 256.0
     lr = int((budget_s / per_px) ** 0.5) // 4 * 4
-    return max(8, min(LR, lr))
+    return max(16, min(LR, lr))
 
 
 # ----------------------------------------------------------------------------------------------- helpers
@@ -324,8 +287,9 @@ def run_reference(args, rank, world):
 
 
 def config_block(world):
-    return {'workload': f'GPEMSR x16 hot path (Indexer16 conv stack + head + codebook lookup, VQ decoder multi-scale, VGG relu1_2 similarity mask, '
-                        f'SpyNet on the 10 frame pairs incl. its 60 flow_warp calls, SR tail), {NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
+    return {'workload': f'GPEMSR x16 whole forward (gpemsr_b200.GPEMSR.forward = model/GPEMSR.py:323-456: LR features, Indexer16 + codebook '
+                        f'lookup + VQ decoder, VGG similarity mask, reference fusion, POD alignment incl. SpyNet / flow_warp / DCNv2, ThreeDA, SR tail), '
+                        f'{NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
             'lr': LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
             'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '
             'exceeds the 126 MB L2; no explicit flush', 'precision': 'bf16 x3 split (fp32-faithful) on tcgen05'}
@@ -391,7 +355,7 @@ def main():
     with ClockSampler(local) as cs:
         for _ in range(W):
             step(dev_in)
-        hp.dec.check(); hp.tail.check()
+        hp.model.check()
 
         # ---- value: inputs resident in HBM
         barrier()
@@ -485,7 +449,7 @@ def main():
             dt, mps = cpu_time(wts, lr, 1, 0)
             line['cpu_baseline'] = {'value': mps, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
                                     'sample': f'1 step on a {NFRAMES}x{lr}x{lr} LR crop of the window ({dt:.1f} s of CPU work), '
-                                              'oracle/ref_ops.py on all host cores'}
+                                              'oracle/gpemsr_model.py (whole forward) on all host cores'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
