@@ -304,6 +304,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying a CUDA graph')
+    ap.add_argument('--profile-step', action='store_true', help='warm up, run ONE eager step between cudaProfilerStart/Stop and exit '
+                    '(for `ncu --profile-from-start off ...`: the launch list of exactly one step; prints no bench line)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -328,6 +330,16 @@ def main():
     dev_in = {k: v.to(dev) for k, v in host_in.items()}
     hr_px = (SCALE * LR) ** 2
     gathered = torch.empty(world, 1, 1, SCALE * LR, SCALE * LR, device=dev) if world > 1 else None
+
+    if args.profile_step:
+        for _ in range(3):
+            hp.step(dev_in)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        hp.step(dev_in)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     graphed = {}
 
