@@ -268,6 +268,59 @@ def micro_rooflines(peaks):
     return out
 
 
+# ----------------------------------------------------------------------------------------------- config 5: whole volume
+VOL_SLICES, VOL_LR, VOL_SCALE = 125, 156, 8          # BASELINE configs[4]: 125 slices, x8, 156^2 LR -> 1248^2 HR
+
+
+def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
+    """BASELINE configs[4]: the reference's output loop (output_GPEMSR.py:54-128) over a synthetic 125-slice x8 volume,
+    slice-sharded over `world` ranks (strong scaling).  Timed end to end per pass: H2D of the LR volume from pinned host
+    memory, per-slice encoding (each slice ONCE: the per-frame cache of SURVEY.md 8f-2), the 125 window fusions, the
+    all-gather of the HR slices (N > 1) and the D2H of this rank's HR block."""
+    import gpemsr_b200
+    from gpemsr_b200 import synth_weights as W
+    from gpemsr_b200.volume import gather_slices, shard_range
+    net = dict(NET, mode='8to1', scale=VOL_SCALE, argref={'Indexer8': ARGREF['Indexer16'], 'Codebook': ARGREF['Codebook'],
+                                                           'Decoder': ARGREF['Decoder']})
+    model = gpemsr_b200.GPEMSR(None, None, **net).eval()
+    model.load_state_dict(W.fill_state({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=2), strict=True)
+    model.to(dev)
+    vol_host = torch.rand(n_slices, 1, VOL_LR, VOL_LR, generator=torch.Generator().manual_seed(4)).pin_memory()
+    lo, hi = shard_range(n_slices, world, rank)
+    hr = VOL_SCALE * VOL_LR
+    out_host = torch.empty(hi - lo, 1, hr, hr).pin_memory()
+    out_dev = torch.empty(hi - lo, 1, hr, hr, device=dev)
+
+    def one_pass():
+        vol = vol_host.to(dev, non_blocking=True)
+        model.forward_volume(vol, lo, hi, out=out_dev)
+        if world > 1:
+            gather_slices(out_dev, n_slices, world, rank, dist)
+        out_host.copy_(out_dev, non_blocking=True)
+
+    one_pass()                                          # warm-up: builds plans, packs weights
+    model.check()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = gpemsr_b200.kernel_launches()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(passes):
+        one_pass()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / passes
+    return {'value': n_slices * hr * hr / 1e6 / (ms / 1e3), 'unit': UNIT, 'ms_per_volume': ms, 'ms_per_slice': ms / n_slices * world,
+            'workload': f'{n_slices} slices x{VOL_SCALE}, {VOL_LR}^2 LR -> {hr}^2 HR, windows of output_GPEMSR.py:54-128, every slice '
+                        f'encoded once (per-frame cache), slice blocks over {world} GPU(s), HR slices all-gathered',
+            'h2d_bytes': vol_host.numel() * 4, 'd2h_bytes': out_host.numel() * 4, 'scaling': 'strong',
+            'gpu_launches_per_pass': int((gpemsr_b200.kernel_launches() - l0) / passes), 'passes': passes}
+
+
 # ----------------------------------------------------------------------------------------------- main
 def run_reference(args, rank, world):
     if rank != 0:
@@ -304,6 +357,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying a CUDA graph')
+    ap.add_argument('--volume', action='store_true', help='time BASELINE configs[4] instead (125-slice x8 volume, strong scaling over --gpus)')
     ap.add_argument('--profile-step', action='store_true', help='warm up, run ONE eager step between cudaProfilerStart/Stop and exit '
                     '(for `ncu --profile-from-start off ...`: the launch list of exactly one step; prints no bench line)')
     args = ap.parse_args()
@@ -324,6 +378,17 @@ def main():
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # keep NCCL's version banner off stdout: ONE JSON line there
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     import gpemsr_b200
+    if args.volume:
+        v = volume_bench(dev, rank, world, dist)
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': v['value'], 'unit': UNIT, 'n_gpus': world, 'steps': v['passes'], 'warmup': 1,
+                              'ms_per_step': v['ms_per_volume'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                              'dtype': 'bf16x3->f32', 'data': 'synthetic', 'config': {'workload': v['workload']}, 'volume': v,
+                              'impl': 'native'}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     wts = make_weights()
     hp = NativeHotPath(wts, dev)
     host_in = make_inputs(LR, NFRAMES, seed=100 + rank, pin=True)
@@ -456,6 +521,13 @@ def main():
                 'cuda_graph': not args.no_graph}
         if world == 1 and not args.no_micro:
             line['micro'] = micro_rooflines(peaks)
+        if world == 1 and not args.no_micro:
+            try:
+                del hp, graphed
+                torch.cuda.empty_cache()
+                line['volume'] = volume_bench(dev, 0, 1, None, passes=1)
+            except Exception as ex:                              # an extra must never take the bench line down
+                line['volume'] = {'error': repr(ex)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             lr = pick_cpu_crop(wts, 20.0)
             dt, mps = cpu_time(wts, lr, 1, 0)

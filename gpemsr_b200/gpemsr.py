@@ -136,7 +136,8 @@ class GPEMSR(SRTail):
 
     def check(self):
         """Synchronise and raise if any GEMM pipeline of the last forward timed out (tests / smoke)."""
-        G.check_pipeline(self._last_plan.err)
+        for P in self._plans.values():
+            G.check_pipeline(P.err)
         for m in (self.refmodel.indexer, self.refmodel.decoder, self.vgg, self.align_module.spynet):
             m.check()
 
@@ -223,13 +224,29 @@ class GPEMSR(SRTail):
             refs.append(r.view(1, N, 1, H * self.scale, W * self.scale))
         return (outs[0], refs[0]) if B == 1 else (torch.cat(outs), torch.cat(refs))
 
-    def _forward_window(self, x):
-        N, _, H, W = x.shape
-        dev, nf, s, ctr = x.device, self.nf, self.scale, self.center
-        key = ('win', N, H, W, dev.index)
+    def _plan(self, kind, n, H, W, dev):
+        key = (kind, n, H, W, dev.index)
         P = self._plans.get(key)
         if P is None:
-            P = self._plans[key] = _Plan(self, N, H, W, dev)
+            P = self._plans[key] = _Plan(self, n, H, W, dev)
+        return P
+
+    def _forward_window(self, x):
+        """One window = per-frame encoding of its N frames + the window fusion (the reference does both per window)."""
+        Pe, ref_img = self._encode_frames(x)
+        enc = [Pe.bufs[f'encL{k}'] for k in range(3)]
+        out = self._fuse_window(x, [(enc, i) for i in range(x.shape[0])])
+        return out, ref_img
+
+    # ------------------------------------------------------------------ per-frame part (:329-425): depends on ONE frame only
+    def _encode_frames(self, x):
+        """Everything of model/GPEMSR.py:329-425 for n frames at once: LR features, generative-prior features + similarity
+        mask, reference fusion, the 3-level alignment pyramid.  Batch entries never interact (GroupNorm and the non-local
+        block are per sample), so a frame's result does not depend on which window it is computed in -- ``forward_volume``
+        evaluates it once per slice instead of once per window.  Returns (plan holding ``encL0..2``, ref_img)."""
+        N, _, H, W = x.shape
+        dev, nf, s = x.device, self.nf, self.scale
+        P = self._plan('enc', N, H, W, dev)
         self._last_plan = P
         L = _lib.lib()
         st = _lib.stream_ptr
@@ -294,28 +311,93 @@ class GPEMSR(SRTail):
             if j < J - 1:
                 self._s2conv(P, f'down_fea_conv{j + 1}', getattr(self, f'down_fea_conv{j + 1}'), self._view(U[j], 0, 64 * (j + 1)),
                              U[j + 1], c_off=64, out_f32=False)
-        # L1_fea = reduce_dim_conv(cat(R, carried, L1)) -> slot 0 of the level-1 alignment operand (:377-378 / 416-417)
+        # L1_fea = reduce_dim_conv(cat(R, carried, L1)) (:377-378 / 416-417), then the alignment pyramid (:421-425)
         gL = [g1, G.Geom(N, H // 2, W // 2, True), G.Geom(N, H // 4, W // 4, True)]
-        catL = [P.act(f'catL{k}', gL[k], 162, f32=True) for k in range(3)]        # [nbr 64 | ref 64 | flow1 16 | flow2 16 | frames 2]
-        self._c(P, 'reduce_dim_conv', self.reduce_dim_conv, self._view(U[J - 1], 0, 128 + 64 * (J - 1)), catL[0])
-        self._tap('L1_fea', catL[0], nf)
-
-        # ---- alignment pyramid (:421-425), all N frames as one batch
-        t64 = [P.act(f't64.{k}', gL[k], nf, f32=False) for k in range(3)]
+        encL = [P.act(f'encL{k}', gL[k], nf, f32=True) for k in range(3)]
+        self._c(P, 'reduce_dim_conv', self.reduce_dim_conv, self._view(U[J - 1], 0, 128 + 64 * (J - 1)), encL[0])
         for k in (1, 2):
-            self._s2conv(P, f'fea_L{k + 1}_conv1', getattr(self, f'fea_L{k + 1}_conv1'), self._view(catL[k - 1], 0, nf), t64[k],
-                         act=lre, out_f32=False)
-            self._c(P, f'fea_L{k + 1}_conv2', getattr(self, f'fea_L{k + 1}_conv2'), t64[k], catL[k], act=lre)
-        self._tap('L2_fea', catL[1], nf)
-        self._tap('L3_fea', catL[2], nf)
-        for k in range(3):                                       # the centre frame's features next to every frame's (:426-431)
+            t = P.act(f'enc.t{k}', gL[k], nf, f32=False)
+            self._s2conv(P, f'fea_L{k + 1}_conv1', getattr(self, f'fea_L{k + 1}_conv1'), encL[k - 1], t, act=lre, out_f32=False)
+            self._c(P, f'fea_L{k + 1}_conv2', getattr(self, f'fea_L{k + 1}_conv2'), t, encL[k], act=lre)
+        self._tap('L1_fea', encL[0]); self._tap('L2_fea', encL[1]); self._tap('L3_fea', encL[2])
+        return P, ref_img
+
+    # ------------------------------------------------------------------ per-window part (:426-455)
+    def _fuse_window(self, x, src):
+        """POD alignment of every frame to the centre frame, ThreeDA fusion and the SR tail for ONE window.  x f32[N, 1, H, W]
+        (the LR frames: POD also reads them, :99-110); src[j] = (per-level feature buffers, image index) of window frame j."""
+        N, _, H, W = x.shape
+        nf, ctr, dev = self.nf, self.center, x.device
+        P = self._plan('win', N, H, W, dev)
+        self._last_plan = P
+        gL = [G.Geom(N, H, W, True), G.Geom(N, H // 2, W // 2, True), G.Geom(N, H // 4, W // 4, True)]
+        catL = [P.act(f'catL{k}', gL[k], 162, f32=True) for k in range(3)]        # [nbr 64 | ref 64 | flow1 16 | flow2 16 | frames 2]
+        t64 = [P.act(f't64.{k}', gL[k], nf, f32=False) for k in range(3)]
+        whole = all(e is src[0][0] and i == j for j, (e, i) in enumerate(src)) and src[0][0][0].geom.n == N
+        for k in range(3):
+            if whole:                                            # the window's frames are one encoded batch, in order
+                self._copy(src[0][0][k], 0, nf, catL[k], 0, f32=True)
+            else:
+                for j, (e, i) in enumerate(src):
+                    a = e[k]
+                    sv = _View(a.hi, a.lo, a.geom.sample(i)); sv.f32 = a.f32
+                    dv = _View(catL[k].hi, catL[k].lo, gL[k].sample(j)); dv.f32 = catL[k].f32
+                    self._copy(sv, 0, nf, dv, 0, f32=True)
+            # the centre frame's features next to every frame's (:426-431)
             self._copy(catL[k], 0, nf, catL[k], 64, bcast_t=N, center=ctr)
         aligned = self._pod(P, x, catL, gL, t64)
         self._tap('aligned', aligned)
         fea = self._threeda(P, aligned, gL[0])
         self._tap('fea', fea)
-        out = self._tail(P, fea, x[ctr:ctr + 1])
-        return out, ref_img
+        return self._tail(P, fea, x[ctr:ctr + 1])
+
+    # ------------------------------------------------------------------ whole volumes (output_GPEMSR.py:54-128)
+    @torch.no_grad()
+    def forward_volume(self, vol, lo=0, hi=None, frames_per_batch=5, out=None):
+        """Super-resolve output slices [lo, hi) of an LR volume vol f32[S, 1, H, W] -> f32[hi - lo, 1, sH, sW].
+
+        Window of slice i = slices i-2 .. i+2 with replicate padding at the volume ends (output_GPEMSR.py:54-128).  The
+        reference runs the whole model on every window, i.e. it evaluates the per-frame part five times per slice; here
+        every needed slice is encoded ONCE (in batches of `frames_per_batch`), kept in the internal format, and each window
+        only runs alignment + fusion + tail.  Results equal ``forward`` on the explicit windows."""
+        if not vol.is_cuda:
+            raise _lib.GpemsrError(-3, 'GPEMSR needs CUDA tensors: there is no CPU fallback')
+        from .volume import window_indices
+        S, _, H, W = vol.shape
+        hi = S if hi is None else hi
+        if not (0 <= lo <= hi <= S):
+            raise ValueError('forward_volume: need 0 <= lo <= hi <= number of slices')
+        if H % 4 or W % 4 or min(H, W) < 16:
+            raise _lib.GpemsrError(-1, 'GPEMSR: H and W must be multiples of 4 and >= 16')
+        vol = vol.float().contiguous()
+        N, nf, dev, sc = self.nframes, self.nf, vol.device, self.scale
+        if out is None:
+            out = torch.empty(hi - lo, 1, sc * H, sc * W, dtype=torch.float32, device=dev)
+        if hi == lo:
+            return out
+        f_lo, f_hi = max(lo - N // 2, 0), min(hi + N // 2, S)    # slices whose features are needed (block + halo)
+        nfr = f_hi - f_lo
+        Pb = self._plan('bank', nfr, H, W, dev)
+        gB = [G.Geom(nfr, H, W, True), G.Geom(nfr, H // 2, W // 2, True), G.Geom(nfr, H // 4, W // 4, True)]
+        bank = [Pb.act(f'bank{k}', gB[k], nf, f32=True) for k in range(3)]
+        fb = frames_per_batch
+        for s0 in range(f_lo, f_hi, fb):
+            idx = [min(s0 + t, f_hi - 1) for t in range(fb)]     # the last batch repeats its last slice (one plan shape)
+            frames = vol[s0:s0 + fb] if idx[-1] == s0 + fb - 1 else vol[torch.tensor(idx, device=dev)]
+            Pe, _ = self._encode_frames(frames)
+            nv = min(fb, f_hi - s0)
+            for k in range(3):
+                a, b = Pe.bufs[f'encL{k}'], bank[k]
+                ga, gb = a.geom, gB[k]
+                sv = _View(a.hi, a.lo, G.Geom(nv, ga.h, ga.w, True, m0=ga.m0, rows_alloc=ga.rows_alloc, r_img=ga.r_img)); sv.f32 = a.f32
+                dv = _View(b.hi, b.lo, G.Geom(nv, gb.h, gb.w, True, m0=gb.m0 + (s0 - f_lo) * gb.r_img, rows_alloc=gb.rows_alloc,
+                                              r_img=gb.r_img)); dv.f32 = b.f32
+                self._copy(sv, 0, nf, dv, 0, f32=True)
+        for i in range(lo, hi):
+            win = window_indices(i, S, N)
+            xw = vol[win[0]:win[0] + N] if win == list(range(win[0], win[0] + N)) else vol[torch.tensor(win, device=dev)]
+            out[i - lo] = self._fuse_window(xw, [(bank, w - f_lo) for w in win])[0]
+        return out
 
     # ------------------------------------------------------------------ POD.forward (:99-150), N (neighbour, centre) pairs at once
     def _pod(self, P, x, catL, gL, t64):

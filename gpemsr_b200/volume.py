@@ -39,3 +39,15 @@ def gather_slices(local, n_units, world_size, rank, dist=None):
         lo, hi = shard_range(n_units, world_size, r)
         parts.append(bufs[r][: hi - lo])
     return torch.cat(parts, 0)
+
+
+def super_resolve_volume(model, vol, rank=0, world_size=1, dist=None, gather=True):
+    """The reference's output loop (output_GPEMSR.py:54-128) over a whole LR volume vol [S, 1, H, W], slice-sharded:
+    rank r super-resolves the contiguous block ``shard_range(S, world_size, r)`` with ``model.forward_volume`` (which encodes
+    the block's slices plus a 2-slice halo once each -- no halo exchange: every rank holds the LR volume) and, if `gather`,
+    the HR slices are all-gathered once (the only collective).  Returns [S, 1, sH, sW] (or the local block if not gather)."""
+    lo, hi = shard_range(vol.shape[0], world_size, rank)
+    local = model.forward_volume(vol, lo, hi)
+    if not gather:
+        return local
+    return gather_slices(local, vol.shape[0], world_size, rank, dist)

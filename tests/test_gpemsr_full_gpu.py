@@ -88,3 +88,24 @@ def test_rejects_cpu_and_bad_sizes(cuda_dev):
         model(torch.rand(1, 5, 1, 16, 16))
     with pytest.raises(gpemsr_b200.GpemsrError):
         model(torch.rand(1, 5, 1, 18, 16, device='cuda'))
+
+
+def test_forward_volume_matches_windows_and_oracle(cuda_dev):
+    """Per-frame feature cache: forward_volume (every slice encoded once) == forward on the explicit
+    windows of output_GPEMSR.py:54-128 (replicate padding at both ends), and == the oracle on the first / a middle slice."""
+    from gpemsr_b200.volume import window_indices
+    model, sd = build(8, seed=81, device=cuda_dev)
+    vol = torch.rand(7, 1, 16, 20, generator=torch.Generator().manual_seed(82))
+    got = model.forward_volume(vol.cuda())
+    model.check()
+    assert tuple(got.shape) == (7, 1, 128, 160)
+    for i in range(7):
+        win = vol[window_indices(i, 7)].unsqueeze(0)
+        ref, _ = model(win.cuda())
+        assert float((got[i:i + 1] - ref).abs().max()) <= 1e-4, i
+        if i in (0, 3):
+            with torch.no_grad():
+                want, _ = GM.forward(win, sd, 8)
+            assert float((got[i:i + 1].cpu() - want).abs().max()) <= 1e-3, i
+    block = model.forward_volume(vol.cuda(), 2, 5)             # a rank's block: slices 2..4 with their halo
+    assert float((block - got[2:5]).abs().max()) <= 1e-4

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gpemsr_b200.volume import gather_slices, shard_range, window_indices
+from gpemsr_b200.volume import gather_slices, shard_range, super_resolve_volume, window_indices
 
 
 def test_shard_range_partitions():
@@ -40,6 +40,32 @@ def _worker(rank, world, port, n_units):
     assert torch.equal(full[:, 0, 0], torch.arange(n_units, dtype=torch.float32))
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _FakeModel:
+    """Stands in for gpemsr_b200.GPEMSR on CPU: slice i of the output is a known function of its window's slice indices."""
+
+    def forward_volume(self, vol, lo=0, hi=None):
+        hi = vol.shape[0] if hi is None else hi
+        rows = [sum(float(vol[j, 0, 0, 0]) * (k + 1) for k, j in enumerate(window_indices(i, vol.shape[0]))) for i in range(lo, hi)]
+        return torch.tensor(rows).view(-1, 1, 1, 1) * torch.ones(1, 1, 2, 2)
+
+
+def _volume_worker(rank, world, port, n_slices):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    vol = torch.arange(n_slices, dtype=torch.float32).view(-1, 1, 1, 1) * torch.ones(1, 1, 4, 4)
+    full = super_resolve_volume(_FakeModel(), vol, rank, world, dist)
+    want = _FakeModel().forward_volume(vol)
+    assert full.shape == want.shape and torch.equal(full, want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_super_resolve_volume_two_ranks_gloo():
+    """N > 1 path of the volume driver: contiguous slice blocks per rank, one all_gather, no other collective."""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_volume_worker, args=(2, port, 9), nprocs=2, join=True)
 
 
 def test_gather_two_ranks_gloo():

@@ -46,3 +46,10 @@ for scale, hw in ((8, (16, 16)), (16, (20, 24))):
     out, ref = m(torch.rand(1, 5, 1, *hw))
     print(scale, tuple(out.shape), tuple(ref.shape), len(calls), 'calls;', sorted(m.debug))
     calls.clear()
+
+m, sd = build(8)
+vol = torch.rand(7, 1, 16, 16)
+o = m.forward_volume(vol)
+print('volume', tuple(o.shape), len(calls), 'calls')
+o = m.forward_volume(vol, 2, 5)
+print('volume block', tuple(o.shape))
