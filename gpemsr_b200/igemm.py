@@ -7,6 +7,7 @@ PyTorch only provides device memory and the stream.  The activation format is de
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -110,7 +111,11 @@ class Weights:
         self.taps = [(dy, dx) for _, dy, dx in taps]
         src = torch.tensor([t[0] for t in taps], dtype=torch.int32, device=dev)
         L = _lib.lib()
-        if kind == 'conv' and len(taps) > 9 and n <= 64 and not plain and self._full_grid():
+        # 3x3 convs with more than 64 input channels and <= 64 output channels (reference fusion, POD offsets): all nine taps'
+        # weights do not fit shared memory next to the A stages, so the tap-fused kernel cannot run them and the streaming kernel
+        # re-reads A nine times; the dy-fused kernel reads it three times: measured ~2x (reffusionconv1: 1.96 -> 0.99 ms).
+        dy3 = len(taps) == 9 and k > 64 and os.environ.get('GPEMSR_DYFUSE3X3', '1') == '1'
+        if kind == 'conv' and (len(taps) > 9 or dy3) and n <= 64 and not plain and self._full_grid():
             # large tap grids on narrow layers (SpyNet's 7x7): weights streamed per (16-wide k slab, tap row) -- the layout
             # [slab][dy][plane][dx][cell][block_n][8] makes every pipeline stage's weights one contiguous copy
             bn = 16 if n <= 16 else 32 if n <= 32 else 64
