@@ -115,6 +115,23 @@ def pick_cpu_crop(wts, budget_s):
 
 
 # ----------------------------------------------------------------------------------------------- helpers
+_REAL_STDOUT = []
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL's version banner ignores NCCL_DEBUG_FILE
+    here): keep a private duplicate of fd 1 for that line and point fd 1 at stderr for everything else."""
+    if not _REAL_STDOUT:
+        sys.stdout.flush()
+        _REAL_STDOUT.append(os.fdopen(os.dup(1), 'w'))
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT[0] if _REAL_STDOUT else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 class ClockSampler:
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
@@ -336,7 +353,7 @@ def run_reference(args, rank, world):
             'dtype': 'f32', 'data': 'synthetic', 'config': config_block(1),
             'cpu_baseline': {'value': mps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': mps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_block(world):
@@ -361,6 +378,7 @@ def main():
     ap.add_argument('--profile-step', action='store_true', help='warm up, run ONE eager step between cudaProfilerStart/Stop and exit '
                     '(for `ncu --profile-from-start off ...`: the launch list of exactly one step; prints no bench line)')
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -381,10 +399,10 @@ def main():
     if args.volume:
         v = volume_bench(dev, rank, world, dist)
         if rank == 0:
-            print(json.dumps({'metric': METRIC, 'value': v['value'], 'unit': UNIT, 'n_gpus': world, 'steps': v['passes'], 'warmup': 1,
+            emit({'metric': METRIC, 'value': v['value'], 'unit': UNIT, 'n_gpus': world, 'steps': v['passes'], 'warmup': 1,
                               'ms_per_step': v['ms_per_volume'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
                               'dtype': 'bf16x3->f32', 'data': 'synthetic', 'config': {'workload': v['workload']}, 'volume': v,
-                              'impl': 'native'}), flush=True)
+                  'impl': 'native'})
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -534,7 +552,7 @@ def main():
             line['cpu_baseline'] = {'value': mps, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
                                     'sample': f'1 step on a {NFRAMES}x{lr}x{lr} LR crop of the window ({dt:.1f} s of CPU work), '
                                               'oracle/gpemsr_model.py (whole forward) on all host cores'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
