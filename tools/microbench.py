@@ -42,7 +42,7 @@ def flow_warp_bench():
     return out
 
 
-def vq_bench(sizes=((1 << 20, 512), (1 << 20, 256), (1 << 16, 512))):
+def vq_bench(sizes=tuple((1 << e, d) for d in (512, 256) for e in (20, 18, 16, 14, 12, 10))):       # BASELINE configs[2]: N = 1 Ki ... 1 Mi
     from oracle import ref_ops as R
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     out = []
