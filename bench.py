@@ -204,11 +204,12 @@ def instrumented_step(hp, dev_in):
         else:
             n, k, taps = kw['n_cols'], kw['k_pad'], 1
         bn = 16 if (n <= 16 and not kw.get('pixel_shuffle')) else 64 if n <= 64 else 128 if n <= 128 else 256
+        name = getattr(w, 'kernel', None) or f'gemm_kernel<{bn}>'             # the kernel template gpemsr_igemm() launches
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         orig(a, w, err, **kw)
         e.record()
-        rec.append((f'gemm_kernel<{bn},split{kw.get("split", 3)}>', 2.0 * rows * n * k * taps, s, e, (rows, n, k, taps)))
+        rec.append((name, 2.0 * rows * n * k * taps, s, e, (rows, n, k, taps)))
 
     G.igemm = wrapped
     import gpemsr_b200.decoder as D
@@ -519,7 +520,7 @@ def main():
         name, (fl, tms, cnt) = max(agg.items(), key=lambda kv: kv[1][1])
         step_ms = ms_total / args.steps
         # DRAM bytes per launch of that kernel class: from the committed ncu pass over one eager step (profiles/README.md)
-        prof = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        prof = os.path.join(ROOT, 'profiles', 'r01_full_traffic.json')
         traffic = None
         if os.path.exists(prof):
             ent = json.load(open(prof))['per_step'].get(name)
@@ -527,7 +528,7 @@ def main():
         roof = {'bound': 'tensor', 'kernel': name, 'achieved': fl / tms / 1e9, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
                 'frac': fl / tms / 1e9 / peaks['tf'], 'traffic': traffic, 'launches_per_step': cnt,
                 'ms_per_launch': tms / cnt, 'share_of_step': tms / step_ms, 'peak_source': peaks['src'] + ' (bf16 sustained)',
-                'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_traffic.json)',
+                'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_full_traffic.json)',
                 'note': 'algorithmic FLOPs = 2*rows*cols*k*taps (one pass); the kernel issues 3 bf16 MMAs per product '
                         '(fp32-faithful split), so frac <= 1/3 by construction',
                 'by_kernel': {k: {'tflops': v[0] / v[1] / 1e9, 'ms': v[1], 'launches': v[2]} for k, v in agg.items()}}

@@ -131,6 +131,7 @@ class Weights:
             self.hi = st.permute(3, 1, 0, 2, 4, 5, 6).contiguous()                              # [slab, dy, plane, dx, cell, bn, 8]
             self.lo = None
             self.packed, self.b_rows, self.k_pad = 2, bn, k16
+            self.kernel = f'gemm_dyfuse_kernel<{bn}>'
             self._keep = (w, src)
             return
         self.k_pad = _round_up(k, 32 if split == 3 else 64)      # one k-chunk of the streaming kernel (narrow inputs: less padding)
@@ -145,6 +146,7 @@ class Weights:
         bn, fused = C.c_int32(), C.c_int32()
         _lib.check(L.gpemsr_igemm_plan(C.byref(d), C.byref(bn), C.byref(fused)))
         self.packed = int((not fused.value) and min_rows == 0 and not plain)
+        self.kernel = f'gemm_tapfuse_kernel<{bn.value}>' if fused.value else f'gemm_kernel<{bn.value}>'       # what gpemsr_igemm() will launch
         if self.packed:
             nbytes = L.gpemsr_pack_weights_tiled_bytes(n, self.k_pad, len(taps), bn.value, split)
             self.hi = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
