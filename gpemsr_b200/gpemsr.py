@@ -429,8 +429,9 @@ class GPEMSR(SRTail):
                 f = o
         for k in range(3):
             gc = gL[k].c
-            _lib.check(L.gpemsr_pack_concat3(_lib.ptr(nb[k]), 1, _lib.ptr(rf[k]), 1, None, 0, C.byref(gc), _lib.ptr(catL[k].hi[20:]),
-                                             _lib.ptr(catL[k].lo[20:]), st()))
+            fr = self._view(catL[k], 160, 2)                     # channels 160, 161: (neighbour frame, centre frame)
+            _lib.check(L.gpemsr_pack_concat3(_lib.ptr(nb[k]), 1, _lib.ptr(rf[k]), 1, None, 0, C.byref(gc), _lib.ptr(fr.hi),
+                                             _lib.ptr(fr.lo), st()))
         cat2 = [P.act(f'cat2.{k}', gL[k], 2 * nf, f32=False) for k in range(3)]
         oa = [P.act(f'off.a{k}', gL[k], nf, f32=True) for k in range(3)]
         fe = [P.act(f'fea.{k}', gL[k], nf, f32=True) for k in range(3)]

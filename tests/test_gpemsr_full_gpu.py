@@ -109,3 +109,14 @@ def test_forward_volume_matches_windows_and_oracle(cuda_dev):
             assert float((got[i:i + 1].cpu() - want).abs().max()) <= 1e-3, i
     block = model.forward_volume(vol.cuda(), 2, 5)             # a rank's block: slices 2..4 with their halo
     assert float((block - got[2:5]).abs().max()) <= 1e-4
+
+
+def test_batch_of_windows_equals_single_windows(cuda_dev):
+    """forward(x[B > 1]) = the per-window results stacked (windows are independent; output_GPEMSR.py uses B = 1)."""
+    model, _ = build(8, seed=83, device=cuda_dev)
+    x = torch.rand(2, 5, 1, 16, 16, generator=torch.Generator().manual_seed(84)).cuda()
+    out, ref = model(x)
+    assert tuple(out.shape) == (2, 1, 128, 128) and tuple(ref.shape) == (2, 5, 1, 128, 128)
+    for b in range(2):
+        o1, r1 = model(x[b:b + 1])
+        assert float((out[b:b + 1] - o1).abs().max()) <= 1e-4 and float((ref[b:b + 1] - r1).abs().max()) <= 1e-4
