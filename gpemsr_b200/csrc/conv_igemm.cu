@@ -32,6 +32,8 @@ struct EpiConv {
   long long ld;
   double* gn_sums;
   int gn_cpg;
+  int pair_off;               // > 0: the accumulator is split over two column ranges (c, c + pair_off): the paired-N MMAs of the
+                              // tap-fused / dy-fused kernels keep a_hi * w_lo apart from a_hi * w_hi + a_lo * w_hi; summed here
   const float* patch_other;   // fp32 cells in the output geometry: the tensor the stored values are correlated with
   float* patch_sums;          // [n][h / patch][w / patch][3] = (sum v*o, sum v*v, sum o*o) per patch x patch block of pixels
   int patch_size;
@@ -231,6 +233,14 @@ struct EpiConv {
       uint32_t r[CHUNK];
       if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + c0, r);
       else sm100::tmem_ld_32x16(tmem_acc + c0, r);
+      if (pair_off) {
+        uint32_t r2[CHUNK];
+        if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + pair_off + c0, r2);
+        else sm100::tmem_ld_32x16(tmem_acc + pair_off + c0, r2);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
       sm100::tmem_ld_wait();
       const int col0 = n_tile * BLOCK_N + c0;
       if ((st.valid || gn_sums) && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
@@ -273,6 +283,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.pair_off = 0;
   const int sms = gpemsr::num_sms();
   const bool clustered = BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters();
   // grid: gx persistent row-tile walkers x gy column-tile splitters.  Model: one CTA per SM, CTAs run in waves, a CTA's
@@ -320,6 +331,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
@@ -361,6 +373,7 @@ int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_dyfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());

@@ -445,6 +445,11 @@ __global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
 gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
   constexpr int PLANES = SPLIT == 3 ? 2 : 1;
   constexpr int KCH = 2;                                   // one UMMA k-step (16 bf16) per stage
+  // SPLIT == 3 pairs the two products that share the A operand: a_hi * [w_hi | w_lo] is ONE MMA with N = 2 * BLOCK_N (the hi and
+  // lo weight rows of a (tap, k-cell) sit next to each other in shared memory), a_lo * w_hi the second (N = BLOCK_N, into the
+  // first half).  The accumulator is 2 * BLOCK_N columns and the epilogue adds column c + BLOCK_N to column c (same TMEM lane).
+  // A narrow MMA costs ~60 cycles whatever N is (the A fetch from shared memory), so 2 MMAs instead of 3 is ~1.4x.
+  constexpr int NMUL = SPLIT == 3 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int kcells = op.k / 8;
   const uint32_t b_tap_bytes = (uint32_t)kcells * BLOCK_N * 16;               // one tap, one plane
@@ -466,7 +471,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     sm100::mbar_init(&bars->b_full, 1);
     sm100::fence_mbar_init();
   }
-  constexpr int TMEM_COLS = Config<BLOCK_N, 16, SPLIT, 2>::TMEM_COLS;
+  constexpr int TMEM_COLS = (2 * NMUL * BLOCK_N <= 32) ? 32 : (2 * NMUL * BLOCK_N <= 64) ? 64 : (2 * NMUL * BLOCK_N <= 128) ? 128 : 256;
   if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   sm100::tc_fence_before();
   __syncthreads();
@@ -483,7 +488,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
       for (int c = lane; c < ncopies; c += 32) {
         const int plane = c / (op.taps * kcells), r = c % (op.taps * kcells);      // r = tap * kcells + kc
         const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + (long long)r * op.b_rows * 8;
-        sm100::bulk_g2s(b_res + (size_t)c * BLOCK_N * 16, src, BLOCK_N * 16, &bars->b_full);
+        sm100::bulk_g2s(b_res + ((size_t)r * PLANES + plane) * BLOCK_N * 16, src, BLOCK_N * 16, &bars->b_full);   // [tap][kc][plane][n]
       }
     }
     uint32_t stage = 0, phase = 0;
@@ -511,6 +516,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc_pair = sm100::idesc_bf16_f32(BLOCK_M, NMUL * BLOCK_N);
     uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
     bool ok = true;
     if (blockIdx.x < op.m_tiles) ok = sm100::mbar_wait(&bars->b_full, 0, op.err_flag, 5);
@@ -519,17 +525,17 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     uint32_t* tap_tab = bars->tap_tab;
     for (int t = lane; t < op.taps; t += 32) {
       tap_tab[2 * t] = ((uint32_t)(op.tap_seg[t] * KCH) * seg_bytes + (uint32_t)op.tap_dx[t] * 16) >> 4;
-      tap_tab[2 * t + 1] = ((uint32_t)t * b_tap_bytes) >> 4;
+      tap_tab[2 * t + 1] = ((uint32_t)t * PLANES * b_tap_bytes) >> 4;
     }
     __syncwarp();
     constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1
     const uint32_t a_desc_lo = ((seg_bytes >> 4) & 0x3FFFu) << 16;           // LBO = one k-cell column of a segment
-    const uint32_t b_desc_lo = (((uint32_t)BLOCK_N * 16 >> 4) & 0x3FFFu) << 16;
+    const uint32_t b_desc_lo = (((uint32_t)PLANES * BLOCK_N * 16 >> 4) & 0x3FFFu) << 16;      // LBO: the next k-cell's [plane][n] block
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
       ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
       if (!ok) break;
       sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+      const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N);
       for (int it = 0; it < kiters && ok; ++it) {
         ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
         if (!ok) break;
@@ -538,16 +544,16 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
           // descriptors differ from a per-stage base only in the 14-bit start-address field (16-byte units): the issuing
           // thread -- the serial bottleneck of this loop -- does two adds per MMA, offsets come from a smem table
           const uint32_t a_lo0 = a_desc_lo + (sm100::smem_u32(stages + (size_t)stage * stage_bytes) >> 4);
-          const uint32_t b_lo0 = b_desc_lo + ((sb0 + (uint32_t)(it * KCH) * (BLOCK_N * 16)) >> 4);
+          const uint32_t b_lo0 = b_desc_lo + ((sb0 + (uint32_t)(it * KCH) * (PLANES * BLOCK_N * 16)) >> 4);
           for (int t = 0; t < op.taps; ++t) {
             const uint32_t a_lo = a_lo0 + tap_tab[2 * t], b_lo = b_lo0 + tap_tab[2 * t + 1];
             const uint64_t a_hi_d = ((uint64_t)kDescHi << 32) | a_lo, b_hi_d = ((uint64_t)kDescHi << 32) | b_lo;
-            sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
             if constexpr (SPLIT == 3) {
               const uint64_t a_lo_d = ((uint64_t)kDescHi << 32) | (a_lo + (a_plane_bytes >> 4));
-              const uint64_t b_lo_d = ((uint64_t)kDescHi << 32) | (b_lo + (((uint32_t)op.taps * b_tap_bytes) >> 4));
-              sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);
-              sm100::umma_bf16(tmem_acc, a_hi_d, b_lo_d, idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc_pair, (it | t) != 0);      // a_hi * [w_hi | w_lo]
+              sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);                    // a_lo * w_hi
+            } else {
+              sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
             }
           }
           sm100::umma_commit(&bars->empty[stage]);
@@ -569,7 +575,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
       ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
       if (!ok) break;
       sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
       epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);
       sm100::tc_fence_before();
       __syncwarp();
@@ -591,19 +597,20 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
 // fetches the A tile once per tap (49x) and the tap-fused kernel needs every tap's weights resident (401 KB for 64x32x49 in
 // (hi, lo) planes: impossible).  Here a pipeline stage is one (16-wide k-slab, tap row dy): ONE A segment of 128 + 2P rows --
 // the n_dx taps of that row are 16-byte start-address shifts inside it -- plus the n_dx weight blocks of that (slab, dy),
-// which arrive as one contiguous copy from a [slab][dy][plane][dx][cell][BLOCK_N][8] packing.  A is read n_dy times instead
+// which arrive as one contiguous copy from a [slab][dy][dx][cell][plane][BLOCK_N][8] packing (hi and lo weight rows of a
+// (tap, k-cell) adjacent: the paired-N MMA of the SPLIT == 3 path reads them as one N = 2 * BLOCK_N operand).  A is read n_dy times instead
 // of n_dy * n_dx times; a stage carries n_dx * SPLIT MMAs.
 template <int BLOCK_N, int SPLIT, class Epi>
 __global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
 gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
   constexpr int PLANES = SPLIT == 3 ? 2 : 1;
+  constexpr int NMUL = SPLIT == 3 ? 2 : 1;                 // paired-N MMAs, see gemm_tapfuse_kernel
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t seg_bytes = (uint32_t)op.seg_len * 16;                       // one 16-byte k-cell column of the segment
   const uint32_t a_plane_bytes = 2 * seg_bytes;
   const uint32_t a_bytes = PLANES * a_plane_bytes;
-  const uint32_t b_tap_bytes = 2 * BLOCK_N * 16;                              // one tap, one plane, one k-slab
-  const uint32_t b_plane_bytes = (uint32_t)op.n_dx * b_tap_bytes;
-  const uint32_t b_bytes = PLANES * b_plane_bytes;
+  const uint32_t b_tap_bytes = PLANES * 2 * BLOCK_N * 16;                     // one tap, one k-slab: [cell][plane][n][8]
+  const uint32_t b_bytes = (uint32_t)op.n_dx * b_tap_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* stages = smem;
   Barriers* bars = reinterpret_cast<Barriers*>(stages + (size_t)op.nstage * stage_bytes);
@@ -617,7 +624,7 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
     sm100::fence_mbar_init();
   }
-  constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : 256;
+  constexpr int TMEM_COLS = (2 * NMUL * BLOCK_N <= 32) ? 32 : (2 * NMUL * BLOCK_N <= 64) ? 64 : (2 * NMUL * BLOCK_N <= 128) ? 128 : 256;
   if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   sm100::tc_fence_before();
   __syncthreads();
@@ -655,6 +662,7 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
     // ===================== MMA issuer (one elected thread) =====================
     if (sm100::elect_one()) {
       constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_pair = sm100::idesc_bf16_f32(BLOCK_M, NMUL * BLOCK_N);
       uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
       bool ok = true;
       // descriptors differ only in their low word (LBO << 16 | start address >> 4); the high word (SBO = 128 B, version 1) is
@@ -663,13 +671,13 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
       // rate; keeping the (small) weight sets resident instead of streaming them was measured and changes nothing.
       constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_base = (((seg_bytes >> 4) & 0x3FFFu) << 16) | (sm100::smem_u32(stages) >> 4);
-      const uint32_t b_lo_base = ((((uint32_t)BLOCK_N * 16 >> 4) & 0x3FFFu) << 16) | ((sm100::smem_u32(stages) + a_bytes) >> 4);
-      const uint32_t a_pl = a_plane_bytes >> 4, b_pl = b_plane_bytes >> 4, b_tap = b_tap_bytes >> 4;
+      const uint32_t b_lo_base = ((((uint32_t)PLANES * BLOCK_N * 16 >> 4) & 0x3FFFu) << 16) | ((sm100::smem_u32(stages) + a_bytes) >> 4);
+      const uint32_t a_pl = a_plane_bytes >> 4, b_tap = b_tap_bytes >> 4;
       for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
         ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
         if (!ok) break;
         sm100::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+        const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N);
         for (int it = 0; it < kiters && ok; ++it) {
           ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
           if (!ok) break;
@@ -678,10 +686,11 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
           uint32_t b = b_lo_base + stage * (stage_bytes >> 4);
           for (int dx = 0; dx < op.n_dx; ++dx, ++a, b += b_tap) {                   // one row = one 16-byte unit
             const uint64_t a_hi = ((uint64_t)kDescHi << 32) | a, b_hi = ((uint64_t)kDescHi << 32) | b;
-            sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | dx) != 0);
             if constexpr (SPLIT == 3) {
-              sm100::umma_bf16(tmem_acc, ((uint64_t)kDescHi << 32) | (a + a_pl), b_hi, idesc, true);
-              sm100::umma_bf16(tmem_acc, a_hi, ((uint64_t)kDescHi << 32) | (b + b_pl), idesc, true);
+              sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc_pair, (it | dx) != 0);                               // a_hi * [w_hi | w_lo]
+              sm100::umma_bf16(tmem_acc, ((uint64_t)kDescHi << 32) | (a + a_pl), b_hi, idesc, true);            // a_lo * w_hi
+            } else {
+              sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | dx) != 0);
             }
           }
           sm100::umma_commit(&bars->empty[stage]);
@@ -703,7 +712,7 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
       ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
       if (!ok) break;
       sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
       epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);
       sm100::tc_fence_before();
       __syncwarp();

@@ -117,7 +117,7 @@ class Weights:
         dy3 = len(taps) == 9 and k > 64 and os.environ.get('GPEMSR_DYFUSE3X3', '1') == '1'
         if kind == 'conv' and (len(taps) > 9 or dy3) and n <= 64 and not plain and self._full_grid():
             # large tap grids on narrow layers (SpyNet's 7x7): weights streamed per (16-wide k slab, tap row) -- the layout
-            # [slab][dy][plane][dx][cell][block_n][8] makes every pipeline stage's weights one contiguous copy
+            # [slab][dy][dx][cell][plane][block_n][8] makes every pipeline stage's weights one contiguous copy
             bn = 16 if n <= 16 else 32 if n <= 32 else 64
             k16 = _round_up(k, 16)
             n_dx = sum(1 for dy, _ in self.taps if dy == self.taps[0][0])
@@ -128,7 +128,8 @@ class Weights:
             _lib.check(L.gpemsr_pack_weights(_lib.ptr(w), n, k, n_stride, k_stride, len(taps), _lib.ptr(src), bn, k16,
                                              _lib.ptr(planes[0]), _lib.ptr(planes[1]) if split == 3 else None, _lib.stream_ptr()))
             st = torch.stack([p.view(n_dy, n_dx, k16 // 16, 2, bn, 8) for p in planes])      # [plane, dy, dx, slab, cell, bn, 8]
-            self.hi = st.permute(3, 1, 0, 2, 4, 5, 6).contiguous()                              # [slab, dy, plane, dx, cell, bn, 8]
+            # [slab, dy, dx, cell, plane, bn, 8]: the hi and lo rows of a (tap, k-cell) side by side = ONE N = 2 * bn B operand
+            self.hi = st.permute(3, 1, 2, 4, 0, 5, 6).contiguous()
             self.lo = None
             self.packed, self.b_rows, self.k_pad = 2, bn, k16
             self.kernel = f'gemm_dyfuse_kernel<{bn}>'
