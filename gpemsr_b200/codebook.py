@@ -120,4 +120,5 @@ class Codebook(nn.Module):
 
     @torch.no_grad()
     def inference_from_feat(self, feat, weight, bias):
-        return logits_argmax_gather(feat, weight, bias, self.embedding.weight.detach())[0]
+        zq, self.last_idx = logits_argmax_gather(feat, weight, bias, self.embedding.weight.detach())[:2]     # indices kept for the tests
+        return zq

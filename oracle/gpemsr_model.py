@@ -124,7 +124,7 @@ def three_da(aligned, sd, center, taps=None):
     return out
 
 
-def forward(x, sd, scale, taps=None):
+def forward(x, sd, scale, taps=None, idx_override=None, logits_out=None):
     """``GPEMSR.forward`` -- model/GPEMSR.py:323-456 with the option/*.yml configuration (w_ref, POD, ThreeDA)."""
     B, N, C, H, W = x.size()
     center = N // 2
@@ -136,7 +136,8 @@ def forward(x, sd, scale, taps=None):
         lr.append(_lrelu(_convT(lr[-1], sd, f'reffea_L{k}_conv1')))
     lr = lr[::-1]                                                                               # finest first
     gen = 'refmodel.'
-    dec_feats, _ = R.ref_extract(xf, _sub(sd, gen + 'indexer.'), sd[gen + 'codebook.embedding.weight'], _sub(sd, gen + 'decoder.'))
+    dec_feats, _ = R.ref_extract(xf, _sub(sd, gen + 'indexer.'), sd[gen + 'codebook.embedding.weight'], _sub(sd, gen + 'decoder.'),
+                                 idx_override=idx_override, logits_out=logits_out)     # (test hooks, see ref_ops.ref_extract)
     ref_img = dec_feats[-1]                                                                     # :342 / 385
     dec = dec_feats[:-1][::-1]                                                                  # ref_x2, ref_x4, ref_x8(, ref_x16)
     mask = R.similarity_mask(ref_img, xf, _sub(sd, 'vgg.'), scale)                              # :344-353 / 387-396

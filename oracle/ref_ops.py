@@ -243,9 +243,19 @@ def indexer_forward(x, sd):
     return indexer_logits(indexer_features(x, sd), sd['embedding.weight'], sd['embedding.bias'])
 
 
-def ref_extract(imgs, sd_indexer, emb, sd_decoder, **dec_kw):
-    """``lrGenerator{8,16}.ref_extract`` -- model/vqgan_indexer.py:44-48 / 87-91."""
-    zq, idx = codebook_inference_lr(indexer_forward(imgs, sd_indexer), emb)
+def ref_extract(imgs, sd_indexer, emb, sd_decoder, idx_override=None, logits_out=None, **dec_kw):
+    """``lrGenerator{8,16}.ref_extract`` -- model/vqgan_indexer.py:44-48 / 87-91.
+
+    Test hooks (not part of the reference): ``idx_override`` replaces the top-1 indices (so a comparison downstream of the
+    DISCRETE lookup cannot be derailed by a near-tied pair of logits), ``logits_out`` (a list) receives the logits."""
+    logits = indexer_forward(imgs, sd_indexer)
+    if logits_out is not None:
+        logits_out.append(logits)
+    zq, idx = codebook_inference_lr(logits, emb)
+    if idx_override is not None:
+        B, H, W, _ = logits.shape
+        idx = idx_override.view(-1)
+        zq = F.embedding(idx, emb).view(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
     return decoder_multi_scale(zq, sd_decoder, **dec_kw), idx
 
 
