@@ -21,7 +21,9 @@
 // equals the algorithmic bytes (413 MB read, ~400 MB written).  Variants tried on the B200 and rejected because they were no
 // faster: 64x4 / 128x2 / 32x32 tiles, CH_UNROLL 2 / 8, 32-bit precomputed offsets (-37 % instructions), two pixels per lane,
 // four rows per thread with vertical tap reuse, channel-split grids.  All land at 0.22-0.25 ms: the limiter is the L1 / memory
-// path of sector-granular gathers over 64 interleaved planes, not issue rate or occupancy.
+// path of sector-granular gathers over 64 interleaved planes, not issue rate or occupancy.  Also rejected: staging each plane's
+// tap box (11 rows x 192 B per 32 x 8 tile) in shared memory with one cp.async.bulk per row, 8 planes in flight per CTA:
+// correct, but 0.395 ms -- the bulk-copy engine sustains only ~1 such small copy per ~26 cycles per SM.
 //
 // Bit-faithful coordinates: each elementwise op of the reference is one separately
 // rounded fp32 op here (__fadd_rn/__fmul_rn/__fdiv_rn, no contraction), in the reference order:
