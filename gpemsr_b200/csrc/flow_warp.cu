@@ -31,8 +31,6 @@
 //     u = ((n + 1) / 2) * (size - 1) ; [border: u = min(size-1, max(u, 0))]   (ATen unnormalize/clip)
 // then ATen's bilinear weights (x_se - x)(y_se - y)... and the accumulation order nw, ne, sw, se.
 #include "capi_common.h"
-#include "sm100.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -163,139 +161,6 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, fl
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Bulk-staged variant.  The gather above keeps ~32 bytes per thread in flight (4 planes x 2 west taps): about 40 KB per SM,
-// which is what HBM latency x bandwidth needs and no more -- the kernel is latency-bound at ~55 % of the copy peak.  Here the
-// bulk-copy engine does the fetching: per channel plane the CTA needs the rows [ymin, ymax] x columns [xmin, xmax] that its
-// 32 x 8 pixels' taps touch (smooth flow: a few pixels more than the tile); each row is ONE cp.async.bulk of LROW floats from the
-// 16-byte-aligned address at or before (row, xmin) into a shared-memory stage, 2 x G planes are in flight per CTA without
-// occupying a single register, and the four taps of every pixel are then conflict-free shared-memory loads.  CTAs whose tap
-// box does not fit the stage (large or noisy flow) take the gather path of the kernel above.
-template <int TILE_W, int TILE_H, int G, int MAXR, int LROW>
-__global__ void __launch_bounds__(TILE_W * TILE_H, 4)
-flow_warp_bulk_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                      int c, int h, int w, int c_per_cta, int border, int align_corners) {
-  constexpr int NT = TILE_W * TILE_H;
-  __shared__ __align__(128) float s_stage[2 * G][MAXR * LROW];
-  __shared__ int4 s_off[NT];
-  __shared__ float4 s_wgt[NT];
-  __shared__ __align__(8) uint64_t s_full[2 * G];
-  __shared__ int s_box[4];                       // ymin, ymax, xmin, xmax over the valid pixels' (clamped) taps
-
-  const int tx = threadIdx.x & (TILE_W - 1), ty = threadIdx.x / TILE_W;
-  const int px = blockIdx.x * TILE_W + tx, py = blockIdx.y * TILE_H + ty;
-  const int c_splits = (c + c_per_cta - 1) / c_per_cta;
-  const int n = blockIdx.z / c_splits;
-  const int c0 = (blockIdx.z % c_splits) * c_per_cta;
-  const int c1 = min(c0 + c_per_cta, c);
-  const size_t plane = (size_t)h * w;
-  const bool inside = (px < w) & (py < h);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    s_box[0] = h; s_box[1] = -1; s_box[2] = w; s_box[3] = -1;
-    for (int i = 0; i < 2 * G; ++i) sm100::mbar_init(&s_full[i], 1);
-    sm100::fence_mbar_init();
-  }
-  __syncthreads();
-  Taps t = zero_taps();
-  if (inside) {
-    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)n * plane + (size_t)py * w + px));
-    t = make_taps(f.x, f.y, px, py, h, w, border != 0, align_corners != 0);
-    const int cy0 = t.o_nw / w, cy1 = t.o_sw / w;
-    const int cx0 = t.o_nw - cy0 * w, cx1 = t.o_ne - cy0 * w;
-    // warp-level reduction first: one atomic per warp and bound
-    int ymn = cy0, ymx = cy1, xmn = cx0, xmx = cx1;
-    const unsigned m = __activemask();
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      ymn = min(ymn, __shfl_xor_sync(m, ymn, o)); ymx = max(ymx, __shfl_xor_sync(m, ymx, o));
-      xmn = min(xmn, __shfl_xor_sync(m, xmn, o)); xmx = max(xmx, __shfl_xor_sync(m, xmx, o));
-    }
-    if (lane == (__ffs(m) - 1)) {
-      atomicMin(&s_box[0], ymn); atomicMax(&s_box[1], ymx); atomicMin(&s_box[2], xmn); atomicMax(&s_box[3], xmx);
-    }
-  }
-  s_off[threadIdx.x] = make_int4(t.o_nw, t.o_ne, t.o_sw, t.o_se);
-  s_wgt[threadIdx.x] = make_float4(t.w_nw, t.w_ne, t.w_sw, t.w_se);
-  __syncthreads();
-  const int ymin = s_box[0], ymax = s_box[1], xmin = s_box[2], xmax = s_box[3];
-  const int R = ymax - ymin + 1, C = xmax - xmin + 1;
-  const float4 wt = s_wgt[threadIdx.x];
-  const float* xp = x + ((size_t)n * c + c0) * plane;
-  float* op = out + ((size_t)n * c + c0) * plane + (size_t)(inside ? py : 0) * w + (inside ? px : 0);
-
-  if (R >= 1 && R <= MAXR && C + 3 <= LROW) {
-    // ---- bulk-staged path: per-thread tap positions inside a stage
-    int so[4] = {0, 0, 0, 0};
-    if (inside) {
-      const int g[4] = {t.o_nw, t.o_ne, t.o_sw, t.o_se};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int cy = g[k] / w;
-        const int s_r = (cy * w + xmin) & ~3;                  // 16-byte-aligned flat start of that stage row
-        so[k] = (cy - ymin) * LROW + (g[k] - s_r);
-      }
-    }
-    // producer lanes (warp 0, lane r < R): source offset and length of stage row r (identical for every plane)
-    int row_src = 0; uint32_t row_bytes = 0, total_bytes = 0;
-    if (warp == 0) {
-      if (lane < R) {
-        row_src = ((ymin + lane) * w + xmin) & ~3;
-        row_bytes = 4u * (uint32_t)min((long long)LROW, (long long)plane - row_src);
-      }
-      total_bytes = row_bytes;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) total_bytes += __shfl_xor_sync(0xffffffffu, total_bytes, o);
-    }
-    const int nplanes = c1 - c0;
-    const int ngroups = (nplanes + G - 1) / G;
-    auto issue_group = [&](int grp) {
-      for (int u = 0; u < G; ++u) {
-        const int p = grp * G + u;
-        if (p >= nplanes) break;
-        const int st = (grp & 1) * G + u;
-        if (lane == 0) sm100::mbar_arrive_expect_tx(&s_full[st], total_bytes);
-        __syncwarp();
-        if (lane < R) sm100::bulk_g2s(&s_stage[st][lane * LROW], xp + (size_t)p * plane + row_src, row_bytes, &s_full[st]);
-      }
-    };
-    if (warp == 0) issue_group(0);
-    for (int grp = 0; grp < ngroups; ++grp) {
-      if (warp == 0 && grp + 1 < ngroups) issue_group(grp + 1);
-      const uint32_t parity = (uint32_t)(grp >> 1) & 1u;
-#pragma unroll
-      for (int u = 0; u < G; ++u) {
-        const int p = grp * G + u;
-        if (p >= nplanes) break;
-        const int st = (grp & 1) * G + u;
-        for (uint32_t spin = 0; spin < (1u << 22) && !sm100::mbar_try_wait(&s_full[st], parity); ++spin) {}     // bounded: never hangs
-        const float* sp = s_stage[st];
-        float acc = __fmul_rn(sp[so[0]], wt.x);
-        acc = __fmaf_rn(sp[so[1]], wt.y, acc);
-        acc = __fmaf_rn(sp[so[2]], wt.z, acc);
-        acc = __fmaf_rn(sp[so[3]], wt.w, acc);
-        if (inside) __stcs(op + (size_t)p * plane, acc);
-      }
-      __syncthreads();                             // every warp is done with this half before it is refilled
-    }
-    return;
-  }
-
-  // ---- gather path (same arithmetic as flow_warp_kernel)
-  const int4 o = s_off[threadIdx.x];
-  for (int ch = c0; ch < c1; ++ch) {
-    const float a0 = __ldg(xp + o.x), b0 = __ldg(xp + o.y), d0 = __ldg(xp + o.z), e0 = __ldg(xp + o.w);
-    float acc = __fmul_rn(a0, wt.x);
-    acc = __fmaf_rn(b0, wt.y, acc);
-    acc = __fmaf_rn(d0, wt.z, acc);
-    acc = __fmaf_rn(e0, wt.w, acc);
-    if (inside) __stcs(op, acc);
-    xp += plane;
-    op += plane;
-  }
-}
-
 }  // namespace
 
 extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c, int h, int w,
@@ -330,14 +195,6 @@ extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c,
     return set_error(GPEMSR_ERR_BAD_SHAPE, "flow_warp: grid too large (n*c_splits=%lld, tiles_y=%d)",
                      (long long)n * c_splits, tiles_y);
   dim3 grid(tiles_x, tiles_y, n * c_splits);
-  // bulk-staged variant: needs 16-byte-aligned planes (h * w a multiple of 4 floats, aligned base) and enough planes per CTA
-  static const int bulk_mode = [] { const char* e = getenv("GPEMSR_FLOW_BULK"); return e ? atoi(e) : 0; }();
-  if (bulk_mode && ((size_t)h * w) % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && c_per_cta >= 8) {
-    flow_warp_bulk_kernel<TILE_W, TILE_H, 4, 16, 48><<<grid, TILE_W * TILE_H, 0, (cudaStream_t)stream>>>(
-        x, flow, out, c, h, w, c_per_cta, padding_mode == GPEMSR_PAD_BORDER, align_corners);
-    GPEMSR_LAUNCH_OK("flow_warp_bulk_kernel");
-    return GPEMSR_OK;
-  }
   flow_warp_kernel<TILE_W, TILE_H, CH_UNROLL><<<grid, TILE_W * TILE_H, 0, (cudaStream_t)stream>>>(
       x, flow, out, c, h, w, c_per_cta, padding_mode == GPEMSR_PAD_BORDER, align_corners);
   GPEMSR_LAUNCH_OK("flow_warp_kernel");
