@@ -119,8 +119,10 @@ class _BlockNet(nn.Module):
         wt = P.weights(name, mod.weight, 'conv')
         G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), out=out, **kw)
 
-    def _res_block(self, P, name, rb, x, nchw_out=None):
-        """x + ReLU(GN(conv(ReLU(GN(conv(x))))))  (model/blocks.py:25-29); x carries fp32 master + planes."""
+    def _res_block(self, P, name, rb, x, nchw_out=None, planes_into=None):
+        """x + ReLU(GN(conv(ReLU(GN(conv(x))))))  (model/blocks.py:25-29); x carries fp32 master + planes.
+        planes_into = (Act, c_off): the block's operand planes are written straight into that channel slot of a wider buffer
+        of the same geometry (the consumer's concat operand) and the returned activation reads them from there."""
         g, c = x.geom, rb.out_channels
         raw = P.act(f'raw{g.key()}_{c}', g, c, f32=True, planes=False)
         h = P.act(f'h{g.key()}_{c}', g, c, f32=False)
@@ -141,6 +143,11 @@ class _BlockNet(nn.Module):
             res = short.f32
         else:
             res = x.f32
+        if planes_into is not None:
+            dst, c_off = planes_into
+            out = _View(dst.hi[c_off // 8:], None if dst.lo is None else dst.lo[c_off // 8:], g)
+            out.f32, out.c = y.f32, c
+            y = out
         G.group_norm_act(raw, rb.block[4].weight.detach(), rb.block[4].bias.detach(), sc, y, act=G.ACT_RELU, residual=res,
                          fused_stats=fused, out_nchw=nchw_out)
         return y
@@ -300,7 +307,14 @@ class Decoder(_BlockNet):
     def forward(self, x):                                     # model/decoder.py:37-38
         return self._run(x, want_feats=False)[1]
 
-    def _run(self, x, want_feats):
+    @torch.no_grad()
+    def multi_scale_feat_into(self, x, sinks):
+        """``multi_scale_feat_calculate`` for a caller that consumes the four features as convolution operands: sinks[i] =
+        (Act, c_off) receives the operand planes of feature i (coarse to fine; None = not needed) directly from the block's
+        last GroupNorm pass -- no NCHW copy, no re-pack.  Returns the decoded image (NCHW)."""
+        return self._run(x, want_feats=False, sinks=sinks)[1]
+
+    def _run(self, x, want_feats, sinks=None):
         P = self._plan_for(x)
         n, c, h, w = x.shape
         g = G.Geom(n, h, w, True)
@@ -310,7 +324,7 @@ class Decoder(_BlockNet):
         self._conv(P, 'input_layer.0', self.input_layer[0], xin, cur)
         for i in range(self.num_input_resblck):
             cur = self._res_block(P, f'input_layer.{i + 1}', self.input_layer[i + 1], cur)
-        feats = []
+        feats, n_feat = [], 0
         nlayers = len(self.feat_extract)
         for li, mod in enumerate(self.feat_extract):
             name = f'feat_extract.{li}'
@@ -318,11 +332,15 @@ class Decoder(_BlockNet):
                 cur = self._non_local(P, name, mod, cur)
             elif isinstance(mod, ResidualBlock):
                 nxt = self.feat_extract[li + 1] if li + 1 < nlayers else None
-                nchw = None
-                if want_feats and isinstance(nxt, UpBlock):    # the tensors model/decoder.py:46/51 collects
-                    nchw = torch.empty(n, mod.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
-                    feats.append(nchw)                         # written by the block's last GroupNorm pass, no extra copy
-                cur = self._res_block(P, name, mod, cur, nchw_out=nchw)
+                nchw, sink = None, None
+                if isinstance(nxt, UpBlock):                   # the tensors model/decoder.py:46/51 collects
+                    if want_feats:
+                        nchw = torch.empty(n, mod.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
+                        feats.append(nchw)                     # written by the block's last GroupNorm pass, no extra copy
+                    elif sinks is not None:
+                        sink = sinks[n_feat]
+                    n_feat += 1
+                cur = self._res_block(P, name, mod, cur, nchw_out=nchw, planes_into=sink)
             else:
                 last = li == nlayers - 1
                 if last and self.compose_final and 4 * self.output_layer.out_channels <= 16:

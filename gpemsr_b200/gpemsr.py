@@ -269,11 +269,10 @@ class GPEMSR(SRTail):
                         U[j], c_off=64 + 64 * j, out_f32=False)
 
         # ---- generative-prior features of every frame (:342 / 385) and the similarity mask (:344-357 / 387-400)
-        feats = self.refmodel.ref_extract(x)
-        ref_img = feats[-1]
-        dec = feats[:-1][::-1]                                   # ref_x2, ref_x4, ref_x8(, ref_x16): finest first
-        for j in range(J):
-            G.pack_nchw(dec[j], U[j], c_off=128 + 64 * j)
+        # the decoder's features (ref_x16 ... ref_x2, coarse to fine) go straight into the decoder slot of their level's operand
+        # buffer: level j takes feature 3 - j (x8 has three levels: ref_x16 at H/2 is not used, model/GPEMSR.py:403-417)
+        sinks = [(U[3 - i], 128 + 64 * (3 - i)) if 3 - i < J else None for i in range(4)]
+        ref_img = self.refmodel.ref_extract_into(x, sinks)
         m0 = self.vgg.similarity_mask(ref_img, x, s)
         hm, wm = m0.shape[2], m0.shape[3]
         gm = G.Geom(N, hm, wm, True)

@@ -142,6 +142,12 @@ class _LrGenerator(nn.Module):
     def ref_extract(self, imgs):                               # vqgan_indexer.py:44-48
         return self.decoder.multi_scale_feat_calculate(self._lookup(imgs))
 
+    @torch.no_grad()
+    def ref_extract_into(self, imgs, sinks):
+        """``ref_extract`` whose four feature maps land as operand planes in the caller's buffers (``Decoder.multi_scale_feat_into``);
+        returns the decoded reference images."""
+        return self.decoder.multi_scale_feat_into(self._lookup(imgs), sinks)
+
 
 class lrGenerator16(_LrGenerator):
     indexer_cls, key = Indexer16, 'Indexer16'
