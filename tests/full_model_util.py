@@ -15,16 +15,16 @@ def argref(scale):
                             latent_dim=512, use_non_local=True)}
 
 
-def network_kwargs(scale):
+def network_kwargs(scale, nframes=5):
     """``network`` block of the yml: nf 64, nframes 5, groups 8, front_RBs 5, back_RBs 10, ref_fusion_feat_RBs 1, POD, ThreeDA."""
-    return dict(argref=argref(scale), nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, w_ref=True, ref_fusion_feat_RBs=1,
+    return dict(argref=argref(scale), nf=64, nframes=nframes, groups=8, front_RBs=5, back_RBs=10, w_ref=True, ref_fusion_feat_RBs=1,
                 align_mode='POD', fusion_mode='ThreeDA', mode='16to1' if scale == 16 else '8to1', scale=scale)
 
 
-def build(scale, seed=None, device=None):
+def build(scale, seed=None, device=None, nframes=5):
     """(mirror module with the fixture's synthetic parameters loaded, the same parameters as a CPU state dict)."""
     import gpemsr_b200
-    m = gpemsr_b200.GPEMSR(None, None, **network_kwargs(scale))
+    m = gpemsr_b200.GPEMSR(None, None, **network_kwargs(scale, nframes))
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     sd = W.fill_state(shapes, seed=900 + scale if seed is None else seed)
     m.load_state_dict(sd, strict=True)

@@ -152,3 +152,31 @@ def test_full_size_windows(cuda_dev, scale, lr):
     print(f'out err {e:.3e}, ref_img err {er:.3e}')
     assert e <= 1e-3 and er <= 1e-3, (e, er)
     assert float(((out.cpu() - want) ** 2).mean()) < 1e-8
+
+
+def test_three_slice_window_x8(cuda_dev):
+    """BASELINE configs[0] says "3-slice 32 x 32 LR -> 256 x 256": the same model built with nframes = 3 (centre = 1; ThreeDA's
+    Conv3d and 1x1 fusions are sized by the frame count), against the oracle."""
+    model, sd = build(8, seed=87, device=cuda_dev, nframes=3)
+    x = torch.rand(1, 3, 1, 32, 32, generator=torch.Generator().manual_seed(88))
+    out, ref_img = model(x.cuda())
+    model.check()
+    with torch.no_grad():
+        want, want_ref = GM.forward(x, sd, 8)
+    assert tuple(out.shape) == (1, 1, 256, 256) and tuple(ref_img.shape) == (1, 3, 1, 256, 256)
+    assert float((out.cpu() - want).abs().max()) <= 1e-3 and float((ref_img.cpu() - want_ref).abs().max()) <= 1e-3
+
+
+def test_forward_volume_tiny_volumes(cuda_dev):
+    """Edge cases of the slice loop: one slice (every window is that slice five times) and two slices."""
+    from gpemsr_b200.volume import window_indices
+    model, _ = build(8, seed=89, device=cuda_dev)
+    for S in (1, 2):
+        vol = torch.rand(S, 1, 16, 16, generator=torch.Generator().manual_seed(90 + S))
+        got = model.forward_volume(vol.cuda())
+        model.check()
+        assert tuple(got.shape) == (S, 1, 128, 128)
+        for i in range(S):
+            ref, _ = model(vol[window_indices(i, S)].unsqueeze(0).cuda())
+            assert float((got[i:i + 1] - ref).abs().max()) <= 1e-4, (S, i)
+    assert tuple(model.forward_volume(torch.rand(3, 1, 16, 16).cuda(), 1, 1).shape) == (0, 1, 128, 128)       # empty block
