@@ -22,14 +22,16 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 }
 
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  // packed conversions (F2FP.BF16.PACK_AB: two values per instruction on the FMA pipe) instead of one F2F each on the
+  // conversion pipe: the epilogues convert 2 x 64 values per output row
   uint32_t h[4], l[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);              // .x (low half) = v[2j]
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    h[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    l[j] = *reinterpret_cast<const uint32_t*>(&l2);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
