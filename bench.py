@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- GPEMSR inference hot path on B200: HR megapixels / s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--no-cpu-baseline]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--no-cpu-baseline] [--no-micro] [--no-graph]
+    python bench.py [--gpus N] --volume          # BASELINE configs[4]: the 125-slice x8 volume, strong scaling over N
+    python bench.py --profile-step               # one eager step between cudaProfilerStart/Stop (for ncu --profile-from-start off)
 
 A "step" is ONE WHOLE FORWARD of the model on one slice window of BASELINE.json configs[1] (GPEMSR x16, N_frames = 5 per
 option/output_GPEMSR_x16.yml, 80x80 LR -> 1280x1280 HR; 78x78 cannot run through the reference):
