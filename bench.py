@@ -116,6 +116,49 @@ def pick_cpu_crop(wts, budget_s):
     return max(16, min(LR, lr))
 
 
+# ----------------------------------------------------------------------------------------------- GPU-eager baseline
+def gpu_eager_baseline(dev, steps=5, warmup=2):
+    """the reference's own device path -- PyTorch eager on the same B200 -- timed beside the native
+    arm (a baseline leg: it may execute oracle/).  `oracle/gpemsr_model.py` is the functional restatement of model/GPEMSR.py
+    (pinned bit-exact on CPU) and dispatches to the same cuDNN / cuBLAS / ATen kernels as the reference's nn.Modules.  Two
+    numerics: TF32 off (the parity oracle's setting) and PyTorch's defaults (cuDNN may use TF32: what a user of the reference
+    gets).  Workloads: the configs[1] window and one window of configs[4] (x8, 5 x 156 x 156)."""
+    from oracle import gpu_eager as GE
+    import gpemsr_b200
+    from gpemsr_b200 import synth_weights as W
+    out = {'what': 'oracle/gpemsr_model.py (restatement of model/GPEMSR.py) in PyTorch eager on cuda: cuDNN / cuBLAS / ATen kernels; '
+                   f'CUDA events, {warmup} warm-up + {steps} timed forwards each'}
+    for tag, scale, lr, net in (('configs1_x16_5x80x80', SCALE, LR, NET),
+                                ('configs4_window_x8_5x156x156', VOL_SCALE, VOL_LR, vol_net())):
+        m = gpemsr_b200.GPEMSR(None, None, **net)
+        sd = W.fill_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=1 if scale == SCALE else 2)
+        del m
+        sd_dev = GE.to_device(sd, dev)
+        x = torch.rand(1, NFRAMES, 1, lr, lr, generator=torch.Generator().manual_seed(100)).to(dev)
+        ent = {}
+        for name, tf32 in (('tf32_off', False), ('pytorch_default_tf32_conv', True)):
+            for _ in range(warmup):
+                GE.forward(x, sd_dev, scale, tf32=tf32)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                GE.forward(x, sd_dev, scale, tf32=tf32)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / steps
+            ent[name] = {'ms_per_step': ms, 'value': (scale * lr) ** 2 / 1e6 / (ms / 1e3), 'unit': UNIT, 'tf32': tf32}
+        out[tag] = ent
+        del sd_dev
+        torch.cuda.empty_cache()
+    return out
+
+
+def vol_net():
+    return dict(NET, mode='8to1', scale=VOL_SCALE, argref={'Indexer8': ARGREF['Indexer16'], 'Codebook': ARGREF['Codebook'],
+                                                           'Decoder': ARGREF['Decoder']})
+
+
 # ----------------------------------------------------------------------------------------------- helpers
 _REAL_STDOUT = []
 
@@ -211,7 +254,8 @@ def instrumented_step(hp, dev_in):
         s.record()
         orig(a, w, err, **kw)
         e.record()
-        rec.append((name, 2.0 * rows * n * k * taps, s, e, (rows, n, k, taps)))
+        # merged ConvTranspose phases / space-to-depth stride-2 convs launch 16 (tap, phase) blocks where the reference layer has 9 taps
+        rec.append((name, 2.0 * rows * n * k * taps * getattr(w, 'flop_scale', 1.0), s, e, (rows, n, k, taps)))
 
     G.igemm = wrapped
     import gpemsr_b200.decoder as D
@@ -300,9 +344,8 @@ def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
     import gpemsr_b200
     from gpemsr_b200 import synth_weights as W
     from gpemsr_b200.volume import gather_slices, shard_range
-    net = dict(NET, mode='8to1', scale=VOL_SCALE, argref={'Indexer8': ARGREF['Indexer16'], 'Codebook': ARGREF['Codebook'],
-                                                           'Decoder': ARGREF['Decoder']})
-    model = gpemsr_b200.GPEMSR(None, None, **net).eval()
+    # (Indexer8 takes the same argument block as Indexer16 in option/output_GPEMSR_x8.yml; only the class differs)
+    model = gpemsr_b200.GPEMSR(None, None, **vol_net()).eval()
     model.load_state_dict(W.fill_state({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=2), strict=True)
     model.to(dev)
     vol_host = torch.rand(n_slices, 1, VOL_LR, VOL_LR, generator=torch.Generator().manual_seed(4)).pin_memory()
@@ -311,11 +354,15 @@ def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
     out_host = torch.empty(hi - lo, 1, hr, hr).pin_memory()
     out_dev = torch.empty(hi - lo, 1, hr, hr, device=dev)
 
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def one_pass():
         vol = vol_host.to(dev, non_blocking=True)
         model.forward_volume(vol, lo, hi, out=out_dev)
+        g0.record()
         if world > 1:
             gather_slices(out_dev, n_slices, world, rank, dist)
+        g1.record()
         out_host.copy_(out_dev, non_blocking=True)
 
     one_pass()                                          # warm-up: builds plans, packs weights
@@ -334,7 +381,9 @@ def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / passes
+    halo = (min(hi + NFRAMES // 2, n_slices) - max(lo - NFRAMES // 2, 0)) - (hi - lo)
     return {'value': n_slices * hr * hr / 1e6 / (ms / 1e3), 'unit': UNIT, 'ms_per_volume': ms, 'ms_per_slice': ms / n_slices * world,
+            'slices_rank0': hi - lo, 'halo_slices_encoded_rank0': halo, 'gather_ms_rank0': g0.elapsed_time(g1) if world > 1 else 0.0,
             'workload': f'{n_slices} slices x{VOL_SCALE}, {VOL_LR}^2 LR -> {hr}^2 HR, windows of output_GPEMSR.py:54-128, every slice '
                         f'encoded once (per-frame cache), slice blocks over {world} GPU(s), HR slices all-gathered',
             'h2d_bytes': vol_host.numel() * 4, 'd2h_bytes': out_host.numel() * 4, 'scaling': 'strong',
@@ -343,27 +392,35 @@ def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
 
 # ----------------------------------------------------------------------------------------------- main
 def run_reference(args, rank, world):
+    """The CPU arm.  `kind: "port"`: oracle/gpemsr_model.py, the restatement pinned bit-exact to the reference's model/GPEMSR.py
+    (the reference itself is Python under /root/reference, which does not exist on the GPU box and may not be read at run
+    time).  A step is the whole forward on the FULL configs[1] window when steps + warm-up fit ~5 minutes of host time,
+    otherwise on the largest LR crop that does -- `config` names what was really timed (`lr`, `cpu_crop`)."""
     if rank != 0:
         return
     wts = make_weights()
-    budget = 150.0 / max(args.steps + args.warmup, 1)
+    budget = 300.0 / max(args.steps + args.warmup, 1)
     lr = pick_cpu_crop(wts, budget)
     dt, mps = cpu_time(wts, lr, args.steps, args.warmup)
     cores = os.cpu_count() or 1
-    sample = f'{NFRAMES}x{lr}x{lr} LR crop of the {NFRAMES}x{LR}x{LR} window ({SCALE * lr}^2 HR px per step)'
-    line = {'impl': 'reference', 'metric': METRIC, 'value': mps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+    sample = (f'the full {NFRAMES}x{LR}x{LR} window' if lr == LR else f'{NFRAMES}x{lr}x{lr} LR crop of the {NFRAMES}x{LR}x{LR} window') + \
+             f' ({SCALE * lr}^2 HR px per step), oracle/gpemsr_model.py on {cores} host cores'
+    cfg = config_block(1, lr=lr)
+    cfg['parallelism'] = f'CPU only: {cores} host threads, no GPU used (n_gpus echoes --gpus for the driver)'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': mps, 'unit': UNIT, 'n_gpus': args.gpus, 'gpus_used': 0, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': config_block(1),
+            'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
             'cpu_baseline': {'value': mps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': mps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
 
 
-def config_block(world):
+def config_block(world, lr=LR):
+    crop = '' if lr == LR else f' -- TIMED ON A {lr}x{lr} LR CROP ({SCALE * lr}x{SCALE * lr} HR), MP/s normalises the size'
     return {'workload': f'GPEMSR x16 whole forward (gpemsr_b200.GPEMSR.forward = model/GPEMSR.py:323-456: LR features, Indexer16 + codebook '
                         f'lookup + VQ decoder, VGG similarity mask, reference fusion, POD alignment incl. SpyNet / flow_warp / DCNv2, ThreeDA, SR tail), '
-                        f'{NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights',
-            'lr': LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
+                        f'{NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights' + crop,
+            'lr': lr, 'cpu_crop': lr != LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
             'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '
             'exceeds the 126 MB L2; no explicit flush', 'precision': 'bf16 x3 split (fp32-faithful) on tcgen05'}
 
@@ -542,13 +599,27 @@ def main():
                 'cuda_graph': not args.no_graph}
         if world == 1 and not args.no_micro:
             line['micro'] = micro_rooflines(peaks)
+    # BASELINE configs[4] (the 125-slice x8 volume, STRONG scaling over the ranks) rides in the default line at every N, so the
+    # driver's scaling series carries it; every rank takes part (slice blocks + one all-gather), rank 0 reports
+    vol = None
+    if not args.no_micro:
+        try:
+            del hp, graphed
+            torch.cuda.empty_cache()
+            vol = volume_bench(dev, rank, world, dist, passes=1 if world == 1 else 2)
+        except Exception as ex:                                  # an extra must never take the bench line down
+            vol = {'error': repr(ex)[:300]}
+    if rank == 0:
+        if vol is not None:
+            line['volume'] = vol
         if world == 1 and not args.no_micro:
             try:
-                del hp, graphed
                 torch.cuda.empty_cache()
-                line['volume'] = volume_bench(dev, 0, 1, None, passes=1)
-            except Exception as ex:                              # an extra must never take the bench line down
-                line['volume'] = {'error': repr(ex)[:300]}
+                line['gpu_eager_baseline'] = gpu_eager_baseline(dev)
+                ge = line['gpu_eager_baseline']['configs1_x16_5x80x80']
+                line['speedup_vs_gpu_eager'] = {k: ge[k]['ms_per_step'] / step_ms for k in ge}
+            except Exception as ex:
+                line['gpu_eager_baseline'] = {'error': repr(ex)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             lr = pick_cpu_crop(wts, 20.0)
             dt, mps = cpu_time(wts, lr, 1, 0)

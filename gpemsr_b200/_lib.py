@@ -32,6 +32,7 @@ SIGNATURES = {
     'gpemsr_device_check': (_i, [_i]),
     'gpemsr_kernel_launches': (_i64, []),
     'gpemsr_flow_warp': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    'gpemsr_flow_warp_ex': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     'gpemsr_vq_workspace_bytes': (_sz, [_i64, _i, _i]),
     'gpemsr_vq_lookup_nchw': (_i, [_p, _p, _i, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     'gpemsr_logits_argmax_gather': (_i, [_p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
@@ -94,10 +95,17 @@ def check(rc):
 
 
 def ptr(t):
+    """Device pointer of a tensor for the C ABI.  The kernels take raw pointers, so a host tensor (a model that was never moved
+    to the GPU, a checkpoint loaded with map_location='cpu') or a strided view would fault inside the launch: refuse here."""
     if t is None:
         return None
     if isinstance(t, int):
         return C.c_void_p(t)
+    if not t.is_cuda:
+        raise GpemsrError(-3, f'expected a CUDA tensor, got one on {t.device} (move the module and its inputs to the GPU: '
+                              'there is no CPU fallback)')
+    if not t.is_contiguous():
+        raise GpemsrError(-2, f'expected a contiguous tensor, got strides {tuple(t.stride())} for shape {tuple(t.shape)}')
     return C.c_void_p(t.data_ptr())
 
 

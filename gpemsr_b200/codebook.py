@@ -23,13 +23,18 @@ import torch.nn as nn
 from . import _lib
 
 _ws_cache = {}
+_ws_retired = []        # outgrown buffers stay allocated: a captured CUDA graph may have their pointers baked in
 
 
 def workspace(nbytes, device):
-    """Per-device scratch buffer, grown on demand (the C ABI never allocates)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Scratch buffer per (device, stream), grown on demand (the C ABI never allocates).  A buffer that was outgrown is kept
+    alive rather than freed, so replaying a CUDA graph captured with it can never write into recycled memory; streams do not
+    share a buffer, so concurrent lookups on two streams do not race on it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
         buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf

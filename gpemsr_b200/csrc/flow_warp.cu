@@ -47,11 +47,14 @@ __device__ __forceinline__ float unnormalize(float n, int size, bool align_corne
   return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(n, 1.0f), (float)size), 1.0f), 0.5f);
 }
 
+// recip: `tensor / python_scalar` the way ATen's CUDA true-divide kernel evaluates it (BinaryDivTrueKernel.cu: a CPU-scalar
+// divisor becomes a multiplication by inv_b = 1.0f / b, one rounding more than the division ATen's CPU kernel performs).
 __device__ __forceinline__ Taps make_taps(float fx, float fy, int px, int py, int h, int w,
-                                          bool border, bool align_corners) {
+                                          bool border, bool align_corners, bool recip) {
   const float dw = (float)max(w - 1, 1), dh = (float)max(h - 1, 1);
-  float nx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)px, fx)), dw), 1.0f);
-  float ny = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)py, fy)), dh), 1.0f);
+  const float tx2 = __fmul_rn(2.0f, __fadd_rn((float)px, fx)), ty2 = __fmul_rn(2.0f, __fadd_rn((float)py, fy));
+  float nx = __fsub_rn(recip ? __fmul_rn(tx2, __fdiv_rn(1.0f, dw)) : __fdiv_rn(tx2, dw), 1.0f);
+  float ny = __fsub_rn(recip ? __fmul_rn(ty2, __fdiv_rn(1.0f, dh)) : __fdiv_rn(ty2, dh), 1.0f);
   float ix = unnormalize(nx, w, align_corners);
   float iy = unnormalize(ny, h, align_corners);
   if (border) {
@@ -85,7 +88,7 @@ __device__ __forceinline__ Taps zero_taps() { Taps t; t.o_nw = t.o_ne = t.o_sw =
 template <int TILE_W, int TILE_H, int CH_UNROLL, int MIN_BLOCKS = 5>
 __global__ void __launch_bounds__(TILE_W * TILE_H, MIN_BLOCKS)
 flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                 int c, int h, int w, int c_per_cta, int border, int align_corners) {
+                 int c, int h, int w, int c_per_cta, int border, int align_corners, int recip) {
   constexpr int NT = TILE_W * TILE_H;
   __shared__ int4 s_off[NT];
   __shared__ float4 s_wgt[NT];
@@ -103,7 +106,7 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, fl
   // phase 1: flow tile -> tap table in shared memory
   if (inside) {
     const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)n * plane + (size_t)py * w + px));
-    const Taps t = make_taps(f.x, f.y, px, py, h, w, border != 0, align_corners != 0);
+    const Taps t = make_taps(f.x, f.y, px, py, h, w, border != 0, align_corners != 0, recip != 0);
     s_off[threadIdx.x] = make_int4(t.o_nw, t.o_ne, t.o_sw, t.o_se);
     s_wgt[threadIdx.x] = make_float4(t.w_nw, t.w_ne, t.w_sw, t.w_se);
   } else {
@@ -163,9 +166,11 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow, fl
 
 }  // namespace
 
-extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c, int h, int w,
-                                int padding_mode, int align_corners, float* out, gpemsr_stream_t stream) {
+extern "C" int gpemsr_flow_warp_ex(const float* x, const float* flow, int n, int c, int h, int w,
+                                   int padding_mode, int align_corners, int coord_form, float* out, gpemsr_stream_t stream) {
   using namespace gpemsr;
+  if (coord_form != GPEMSR_COORD_DIV && coord_form != GPEMSR_COORD_RECIP)
+    return set_error(GPEMSR_ERR_UNSUPPORTED, "flow_warp: coord_form %d (0 = true division, 1 = reciprocal multiply)", coord_form);
   if (n < 0 || c < 0 || h < 0 || w < 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "flow_warp: negative dimension n=%d c=%d h=%d w=%d", n, c, h, w);
   if (padding_mode != GPEMSR_PAD_ZEROS && padding_mode != GPEMSR_PAD_BORDER)
@@ -196,7 +201,12 @@ extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c,
                      (long long)n * c_splits, tiles_y);
   dim3 grid(tiles_x, tiles_y, n * c_splits);
   flow_warp_kernel<TILE_W, TILE_H, CH_UNROLL><<<grid, TILE_W * TILE_H, 0, (cudaStream_t)stream>>>(
-      x, flow, out, c, h, w, c_per_cta, padding_mode == GPEMSR_PAD_BORDER, align_corners);
+      x, flow, out, c, h, w, c_per_cta, padding_mode == GPEMSR_PAD_BORDER, align_corners, coord_form == GPEMSR_COORD_RECIP);
   GPEMSR_LAUNCH_OK("flow_warp_kernel");
   return GPEMSR_OK;
+}
+
+extern "C" int gpemsr_flow_warp(const float* x, const float* flow, int n, int c, int h, int w,
+                                int padding_mode, int align_corners, float* out, gpemsr_stream_t stream) {
+  return gpemsr_flow_warp_ex(x, flow, n, c, h, w, padding_mode, align_corners, GPEMSR_COORD_DEFAULT, out, stream);
 }

@@ -44,34 +44,44 @@ class DCNv2Pack(nn.Module):
         if P is None:
             g = G.Geom(n, h, w, True)
             c = self.in_channels
-            P = dict(g=g, err=torch.zeros(1, dtype=torch.int32, device=device),
+            P = dict(g=g, err=G.err_flag(device), wts={},
                      x=G.Act(g, c, device, f32=True, planes=False), feat=G.Act(g, c, device, f32=False, split=self.split),
-                     col=G.Act(g, 9 * c, device, f32=False, split=self.split),
-                     w_off=G.Weights(self.conv_offset.weight, 'conv', split=self.split),
-                     # [co, ci, ky, kx] -> [co, (ky*3 + kx) * C + ci]: the channel order the gather writes
-                     w_main=G.Weights(self.weight.detach().permute(0, 2, 3, 1).reshape(self.out_channels, 9 * c).contiguous(),
-                                      'linear', split=self.split))
+                     col=G.Act(g, 9 * c, device, f32=False, split=self.split))
             self._plans[key] = P
         return P
+
+    def _weights(self, cache, name):
+        """(conv_offset weights, main weights as a 1x1 GEMM over the gathered channels), re-packed when the parameters change."""
+        c = self.in_channels
+        w_off = G.cached(cache, name + '.off', (self.conv_offset.weight,),
+                         lambda: G.Weights(self.conv_offset.weight, 'conv', split=self.split))
+        # [co, ci, ky, kx] -> [co, (ky*3 + kx) * C + ci]: the channel order the gather writes
+        w_main = G.cached(cache, name + '.main', (self.weight,),
+                          lambda: G.Weights(self.weight.detach().permute(0, 2, 3, 1).reshape(self.out_channels, 9 * c).contiguous(),
+                                            'linear', split=self.split))
+        return w_off, w_main
 
     @torch.no_grad()
     def forward(self, x, feat):
         if not x.is_cuda:
             raise _lib.GpemsrError(-3, 'DCNv2Pack needs CUDA tensors: there is no CPU fallback')
+        G.poll_error(x.device)
         n, c, h, w = x.shape
         P = self._plan(n, h, w, x.device)
         G.pack_nchw(x.float(), P['x'])
         G.pack_nchw(feat.float(), P['feat'])
         om = torch.empty(n, 3 * self.deformable_groups * 9, h, w, dtype=torch.float32, device=x.device)
-        G.igemm(P['feat'], P['w_off'], P['err'], split=self.split, bias=self.conv_offset.bias.detach(), out_nchw=om,
+        w_off, w_main = self._weights(P['wts'], 'dcn')
+        G.igemm(P['feat'], w_off, P['err'], split=self.split, bias=self.conv_offset.bias.detach(), out_nchw=om,
                 nchw_c=om.shape[1])
         g = P['g'].c
         col = P['col']
         _lib.check(_lib.lib().gpemsr_deform_im2col(_lib.ptr(P['x'].f32), C.byref(g), c, self.deformable_groups, _lib.ptr(om),
                                                    _lib.ptr(col.hi), _lib.ptr(col.lo), C.byref(g), _lib.stream_ptr()))
         out = torch.empty(n, self.out_channels, h, w, dtype=torch.float32, device=x.device)
-        G.igemm(col, P['w_main'], P['err'], split=self.split, bias=self.bias.detach(), out_nchw=out, nchw_c=self.out_channels)
+        G.igemm(col, w_main, P['err'], split=self.split, bias=self.bias.detach(), out_nchw=out, nchw_c=self.out_channels)
         self._last_err = P['err']
+        G.post_error_check(x.device)
         return out
 
     def run_acts(self, P, name, x_f32, g, feat, out, err, act=G.ACT_NONE, slope=0.0, c_off=0, out_f32=True, out_planes=True):
@@ -79,11 +89,7 @@ class DCNv2Pack(nn.Module):
         fp32 master cells of the input (64 channels, geometry g), feat = Act with the offset features' operand planes; the
         result goes to channel slot c_off of Act `out` with `act` fused.  `P` is the caller's buffer / weight cache."""
         c = self.in_channels
-        w_off = P.wts.get(name + '.off')
-        if w_off is None:
-            w_off = P.wts[name + '.off'] = G.Weights(self.conv_offset.weight, 'conv', split=self.split)
-            P.wts[name + '.main'] = G.Weights(self.weight.detach().permute(0, 2, 3, 1).reshape(self.out_channels, 9 * c).contiguous(),
-                                              'linear', split=self.split)
+        w_off, w_main = self._weights(P.wts, name)
         key = f'dcn.om{g.key()}'
         om = P.bufs.get(key)
         if om is None:
@@ -93,7 +99,7 @@ class DCNv2Pack(nn.Module):
         gc = g.c
         _lib.check(_lib.lib().gpemsr_deform_im2col(_lib.ptr(x_f32), C.byref(gc), c, self.deformable_groups, _lib.ptr(om),
                                                    _lib.ptr(col.hi), _lib.ptr(col.lo), C.byref(gc), _lib.stream_ptr()))
-        G.igemm(col, P.wts[name + '.main'], err, split=self.split, bias=self.bias.detach(), act=act, slope=slope, out=out,
+        G.igemm(col, w_main, err, split=self.split, bias=self.bias.detach(), act=act, slope=slope, out=out,
                 c_off=c_off, out_f32=out_f32, out_planes=out_planes)
 
     def check(self):

@@ -59,7 +59,7 @@ class _Plan:
     def __init__(self, dec, n, h, w, device):
         self.split = 3 if dec.precision == 'fp32' else 1
         self.device = device
-        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = G.err_flag(device)           # one flag per device, read back once per forward (igemm.post_error_check)
         self.n, self.h, self.w = n, h, w
         self.bufs = {}
         self.wts = {}
@@ -73,12 +73,14 @@ class _Plan:
             self.bufs[key] = a
         return a
 
-    def weights(self, name, param, kind, taps=None, min_rows=0):
-        wt = self.wts.get(name)
-        if wt is None:
-            wt = G.Weights(param, kind, taps=taps, split=self.split, min_rows=min_rows)
-            self.wts[name] = wt
-        return wt
+    def weights(self, name, param, kind, taps=None, min_rows=0, split=None):
+        """Packed B operand of `param`, re-packed whenever the live parameter changes (igemm.cached)."""
+        return G.cached(self.wts, name, (param,),
+                        lambda: G.Weights(param, kind, taps=taps, split=split or self.split, min_rows=min_rows))
+
+    def derived(self, name, params, build):
+        """Anything computed on the host from parameters (merged phases, composed layers, Kronecker weights), same caching."""
+        return G.cached(self.wts, name, tuple(params), build)
 
     def scratch(self, n, c):
         key = (n, c)
@@ -111,7 +113,7 @@ class _BlockNet(nn.Module):
         return P
 
     def check(self):
-        """Synchronise and raise if a GEMM pipeline timed out (tests / smoke)."""
+        """Synchronise and raise if a GEMM pipeline timed out."""
         G.check_pipeline(self._last_plan.err)
 
     # ------------------------------------------------------------------ building blocks
@@ -160,11 +162,12 @@ class _BlockNet(nn.Module):
         y = P.act(name + '.out', og, cout, f32=need_f32)
         if cout % 32 == 0 and cout <= 64:
             # narrow up-blocks are bound by memory traffic: run the four phases as ONE GEMM with 4*cout columns
-            wt = P.wts.get(name + '.merged')
-            if wt is None:
-                wt = G.Weights(G.convT_merged_weight(ub.upblock.weight.detach()), 'conv', taps='offsets01', split=P.split)
+            def build():
+                wt = G.Weights(G.convT_merged_weight(ub.upblock.weight.detach()), 'conv', taps='offsets01', split=P.split,
+                               flop_scale=9 / 16)
                 wt.bias4 = ub.upblock.bias.detach().repeat(4).contiguous()
-                P.wts[name + '.merged'] = wt
+                return wt
+            wt = P.derived(name + '.merged', (ub.upblock.weight, ub.upblock.bias), build)
             G.igemm(x, wt, P.err, split=P.split, bias=wt.bias4, out=y, up=2, phase_cols=cout, out_f32=need_f32)
             return y
         for py in (0, 1):
@@ -181,11 +184,10 @@ class _BlockNet(nn.Module):
         og = G.Geom(g.n, (g.h + 1) // 2, (g.w + 1) // 2, True)
         s2d = P.act(name + '.s2d', og, 4 * conv.in_channels, f32=False)
         G.space_to_depth(x, s2d)
-        wt = P.wts.get(name)
-        if wt is None:
+        def build():
             m, taps = G.down_conv_weight(conv.weight.detach())
-            wt = G.Weights(m, 'conv', taps=taps, split=P.split)
-            P.wts[name] = wt
+            return G.Weights(m, 'conv', taps=taps, split=P.split, flop_scale=9 / 16)
+        wt = P.derived(name, (conv.weight,), build)
         y = P.act(name + '.out', og, conv.out_channels, f32=True)
         G.igemm(s2d, wt, P.err, split=P.split, bias=conv.bias.detach(), out=y)
         return y
@@ -286,14 +288,13 @@ class Decoder(_BlockNet):
         materialised.  The one-pixel ring of the image, where the conv's zero padding changes the weights, is then
         re-evaluated exactly with per-class weights."""
         co = self.output_layer.out_channels
-        st = P.wts.get('final')
-        if st is None:
+        def build():
             wc, bias = G.compose_upblock_conv(ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias)
             dev = ub.upblock.weight.device
             w_int = wc[4].reshape(4 * co, wc.shape[3], 3, 3).contiguous().to(dev)          # phase-major output channels
-            st = dict(wt=G.Weights(w_int, 'conv', split=P.split), b_int=bias[4].repeat(4).contiguous().to(dev),
-                      wc=wc.contiguous().to(dev), bias=bias.contiguous().to(dev))
-            P.wts['final'] = st
+            return dict(wt=G.Weights(w_int, 'conv', split=P.split), b_int=bias[4].repeat(4).contiguous().to(dev),
+                        wc=wc.contiguous().to(dev), bias=bias.contiguous().to(dev))
+        st = P.derived('final', (ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias), build)
         G.igemm(x, st['wt'], P.err, split=P.split, bias=st['b_int'], up=2, phase_cols=co, out_nchw=img, nchw_c=co)
         G.border_phase_conv(x, st['wc'], st['bias'], co, img)
 
@@ -316,6 +317,13 @@ class Decoder(_BlockNet):
 
     def _run(self, x, want_feats, sinks=None):
         P = self._plan_for(x)
+        G.poll_error(x.device)
+        with G.nested():
+            res = self._run_body(P, x, want_feats, sinks)
+        G.post_error_check(x.device)
+        return res
+
+    def _run_body(self, P, x, want_feats, sinks):
         n, c, h, w = x.shape
         g = G.Geom(n, h, w, True)
         xin = P.act('in', g, c, f32=False)

@@ -12,10 +12,16 @@ import torch
 from . import _lib
 
 _PAD = {'zeros': 0, 'border': 1}
+# how `2 * v / max(size - 1, 1)` is rounded: 'cuda' = the reference's own device path (ATen's CUDA true-divide kernel turns a
+# Python-scalar divisor into a multiplication by the fp32 reciprocal), 'cpu' = ATen's CPU kernel (a true division).  Measured
+# on the B200 against F.grid_sample on both devices: profiles/r02_flow_h3.json.
+_COORD = {'cpu': 0, 'cuda': 1}
+DEFAULT_COORD_FORM = 'cuda'
 
 
-def flow_warp(x, flow, interp_mode='bilinear', padding_mode='zeros', align_corners=True):
-    """x: f32[n, c, h, w]; flow: f32[n, h, w, 2] (dx, dy in pixels) -> f32[n, c, h, w]."""
+def flow_warp(x, flow, interp_mode='bilinear', padding_mode='zeros', align_corners=True, coord_form=None):
+    """x: f32[n, c, h, w]; flow: f32[n, h, w, 2] (dx, dy in pixels) -> f32[n, c, h, w].
+    coord_form (not a BasicSR argument): which device's rounding of the coordinate normalisation to reproduce."""
     assert x.size()[-2:] == flow.size()[1:3]      # same assertion as BasicSR
     if interp_mode != 'bilinear':
         raise NotImplementedError(f'interp_mode={interp_mode!r}: only bilinear is built (the reference uses no other)')
@@ -31,6 +37,7 @@ def flow_warp(x, flow, interp_mode='bilinear', padding_mode='zeros', align_corne
     x = x.contiguous()
     flow = flow.contiguous()
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().gpemsr_flow_warp(_lib.ptr(x), _lib.ptr(flow), n, c, h, w, _PAD[padding_mode],
-                                           int(bool(align_corners)), _lib.ptr(out), _lib.stream_ptr()))
+    _lib.check(_lib.lib().gpemsr_flow_warp_ex(_lib.ptr(x), _lib.ptr(flow), n, c, h, w, _PAD[padding_mode],
+                                              int(bool(align_corners)), _COORD[coord_form or DEFAULT_COORD_FORM], _lib.ptr(out),
+                                              _lib.stream_ptr()))
     return out

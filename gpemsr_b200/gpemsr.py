@@ -83,13 +83,6 @@ class ThreeDA(nn.Module):                                        # parameter hol
         self.spatial_attn_add1, self.spatial_attn_add2 = _conv(nf, nf, 1, 1, 0), _conv(nf, nf, 1, 1, 0)
 
 
-class _Bias:
-    """Stand-in for a module whose weight / bias were rebuilt on the host (Kronecker-expanded Conv3d)."""
-
-    def __init__(self, weight, bias):
-        self.weight, self.bias = weight, bias
-
-
 class GPEMSR(SRTail):
     def __init__(self, ref_path_G=None, ref_path_Indexer=None, argref=None, nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10,
                  w_ref=True, ref_fusion_feat_RBs=3, align_mode='POD', fusion_mode='ThreeDA', mode='16to1', scale=16,
@@ -128,6 +121,7 @@ class GPEMSR(SRTail):
         for p in self.parameters():
             p.requires_grad = False
         self.debug = None                 # set to a dict to collect NCHW copies of intermediate tensors (tests)
+        self.strict_errors = False        # True: every forward waits for its own pipeline-error read-back (one host sync per call)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         """Accepts the reference model's ``state_dict()``: the parameters of modules that never run in inference
@@ -135,17 +129,13 @@ class GPEMSR(SRTail):
         return super().load_state_dict({k: v for k, v in state_dict.items() if not k.startswith(DEAD_PREFIXES)}, strict=strict, **kw)
 
     def check(self):
-        """Synchronise and raise if any GEMM pipeline of the last forward timed out (tests / smoke)."""
+        """Synchronise and raise if any GEMM pipeline timed out since the last check (all plans of a device share one flag)."""
         for P in self._plans.values():
             G.check_pipeline(P.err)
-        for m in (self.refmodel.indexer, self.refmodel.decoder, self.vgg, self.align_module.spynet):
-            m.check()
 
     # ------------------------------------------------------------------ helpers
-    def _c(self, P, name, mod, x, out, act=G.ACT_NONE, weight=None, **kw):
-        wt = P.wts.get(name)
-        if wt is None:
-            wt = P.wts[name] = G.Weights(mod.weight if weight is None else weight, 'conv', split=P.split)
+    def _c(self, P, name, mod, x, out, act=G.ACT_NONE, **kw):
+        wt = P.weights(name, mod.weight, 'conv')
         G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
 
     def _s2conv(self, P, name, mod, x, out, act=G.ACT_NONE, **kw):
@@ -154,18 +144,19 @@ class GPEMSR(SRTail):
         og = G.Geom(g.n, (g.h + 1) // 2, (g.w + 1) // 2, True)
         s2d = P.act(name + '.s2d', og, 4 * x.c, f32=False)
         G.space_to_depth(x, s2d)
-        wt = P.wts.get(name)
-        if wt is None:
+        def build():
             m, taps = G.down_conv_weight(mod.weight.detach())
-            wt = P.wts[name] = G.Weights(m, 'conv', taps=taps, split=P.split)
+            return G.Weights(m, 'conv', taps=taps, split=P.split, flop_scale=9 / 16)
+        wt = P.derived(name, (mod.weight,), build)
         G.igemm(s2d, wt, P.err, split=P.split, bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
 
     def _convT(self, P, name, mod, x, out, **kw):
         """lrelu(ConvTranspose2d(k3, s2, p1, op1)) as ONE GEMM over the four output-parity phases (:335-340)."""
-        wt = P.wts.get(name)
-        if wt is None:
-            wt = P.wts[name] = G.Weights(G.convT_merged_weight(mod.weight.detach()), 'conv', taps='offsets01', split=P.split)
+        def build():
+            wt = G.Weights(G.convT_merged_weight(mod.weight.detach()), 'conv', taps='offsets01', split=P.split, flop_scale=9 / 16)
             wt.bias4 = mod.bias.detach().repeat(4).contiguous()
+            return wt
+        wt = P.derived(name, (mod.weight, mod.bias), build)
         G.igemm(x, wt, P.err, split=P.split, bias=wt.bias4, act=G.ACT_LRELU, slope=LRELU_SLOPE, out=out, up=2,
                 phase_cols=mod.weight.shape[1], **kw)
 
@@ -217,11 +208,18 @@ class GPEMSR(SRTail):
         if H % 4 or W % 4 or min(H, W) < 16:
             raise _lib.GpemsrError(-1, 'GPEMSR: H and W must be multiples of 4 and >= 16 (the POD pyramid halves them twice and '
                                        'SpyNet needs a 64-pixel input at x4)')
+        # a pipeline time-out of an EARLIER call (bounded mbarrier waits: preemption, a debugger, a bug) raises here; this call's
+        # own flag is read back asynchronously below and raises at the next call, in check(), or in the volume driver's sync
+        G.poll_error(x.device)
         outs, refs = [], []
-        for b in range(B):                                       # windows are independent (output_GPEMSR.py runs B = 1)
-            o, r = self._forward_window(x[b].float().contiguous())
-            outs.append(o)
-            refs.append(r.view(1, N, 1, H * self.scale, W * self.scale))
+        with G.nested():
+            for b in range(B):                                   # windows are independent (output_GPEMSR.py runs B = 1)
+                o, r = self._forward_window(x[b].float().contiguous())
+                outs.append(o)
+                refs.append(r.view(1, N, 1, H * self.scale, W * self.scale))
+        G.post_error_check(x.device)
+        if self.strict_errors and not torch.cuda.is_current_stream_capturing():
+            G.poll_error(x.device, wait=True)                    # synchronous: the outputs are known good when this returns
         return (outs[0], refs[0]) if B == 1 else (torch.cat(outs), torch.cat(refs))
 
     def _plan(self, kind, n, H, W, dev):
@@ -292,12 +290,10 @@ class GPEMSR(SRTail):
             kin = 64 * j + 64 + (64 << j)
             conv = getattr(self, f'reffusionconv{j + 1}')
             wname = f'reffusionconv{j + 1}'
-            if wname not in P.wts:                               # reference input order (LR feat, decoder, carried) -> buffer order
-                w = conv.weight.detach()
-                d = 64 << j
-                P.wts[wname] = G.Weights(torch.cat([w[:, 64 + d:], w[:, :64], w[:, 64:64 + d]], dim=1).contiguous(), 'conv', split=P.split)
+            def build(w=conv.weight.detach(), d=64 << j):          # reference input order (LR feat, decoder, carried) -> buffer order
+                return G.Weights(torch.cat([w[:, 64 + d:], w[:, :64], w[:, 64:64 + d]], dim=1).contiguous(), 'conv', split=P.split)
             r = P.act(f'fus.r{g.key()}', g, nf, f32=True)
-            self._c(P, wname, conv, self._view(U[j], 64, kin), r)
+            G.igemm(self._view(U[j], 64, kin), P.derived(wname, (conv.weight,), build), P.err, split=P.split, bias=conv.bias.detach(), out=r)
             r = self._rbs(P, f'ffb{j}', getattr(self, f'fusion_fea_block{j + 1}'), r, g)
             gc = g.c
             _lib.check(L.gpemsr_cells_mul_mask(_lib.ptr(r.f32), C.byref(gc), nf, _lib.ptr(mask), hm, wm, g.h // hm, 1, 0, None,
@@ -369,6 +365,7 @@ class GPEMSR(SRTail):
         if H % 4 or W % 4 or min(H, W) < 16:
             raise _lib.GpemsrError(-1, 'GPEMSR: H and W must be multiples of 4 and >= 16')
         vol = vol.float().contiguous()
+        G.poll_error(vol.device)
         N, nf, dev, sc = self.nframes, self.nf, vol.device, self.scale
         if out is None:
             out = torch.empty(hi - lo, 1, sc * H, sc * W, dtype=torch.float32, device=dev)
@@ -380,6 +377,17 @@ class GPEMSR(SRTail):
         gB = [G.Geom(nfr, H, W, True), G.Geom(nfr, H // 2, W // 2, True), G.Geom(nfr, H // 4, W // 4, True)]
         bank = [Pb.act(f'bank{k}', gB[k], nf, f32=True) for k in range(3)]
         fb = frames_per_batch
+        with G.nested():
+            self._volume_body(vol, lo, hi, out, f_lo, f_hi, fb, bank, gB)
+        G.post_error_check(dev)
+        if self.strict_errors:
+            G.poll_error(dev, wait=True)
+        return out
+
+    def _volume_body(self, vol, lo, hi, out, f_lo, f_hi, fb, bank, gB):
+        from .volume import window_indices
+        S, _, H, W = vol.shape
+        N, nf, dev = self.nframes, self.nf, vol.device
         for s0 in range(f_lo, f_hi, fb):
             idx = [min(s0 + t, f_hi - 1) for t in range(fb)]     # the last batch repeats its last slice (one plan shape)
             frames = vol[s0:s0 + fb] if idx[-1] == s0 + fb - 1 else vol[torch.tensor(idx, device=dev)]
@@ -396,7 +404,6 @@ class GPEMSR(SRTail):
             win = window_indices(i, S, N)
             xw = vol[win[0]:win[0] + N] if win == list(range(win[0], win[0] + N)) else vol[torch.tensor(win, device=dev)]
             out[i - lo] = self._fuse_window(xw, [(bank, w - f_lo) for w in win])[0]
-        return out
 
     # ------------------------------------------------------------------ POD.forward (:99-150), N (neighbour, centre) pairs at once
     def _pod(self, P, x, catL, gL, t64):
@@ -492,13 +499,14 @@ class GPEMSR(SRTail):
         f3 = []
         for i, (c3, cf) in enumerate(((td.conv3D_1, td.conv3D_fusion_1), (td.conv3D_2, td.conv3D_fusion_2))):
             kname = f'tda.c3d{i}'
-            k3 = P.bufs.get(kname)
-            if k3 is None:                                       # Conv3d(t, t, k=1) over [b, t, c, h, w] = 1x1 conv with W (x) I_c
+            def build(c3=c3):                                    # Conv3d(t, t, k=1) over [b, t, c, h, w] = 1x1 conv with W (x) I_c
                 w = c3.weight.detach().reshape(N, N).float()
                 eye = torch.eye(nf, device=w.device)
-                k3 = P.bufs[kname] = _Bias(torch.kron(w, eye).reshape(N * nf, N * nf, 1, 1).contiguous(),
-                                           c3.bias.detach().float().repeat_interleave(nf).contiguous())
-            self._c(P, kname, k3, al, t3d, act=lre, out_f32=False)
+                wt = G.Weights(torch.kron(w, eye).reshape(N * nf, N * nf, 1, 1).contiguous(), 'conv', split=P.split)
+                wt.bias_k = c3.bias.detach().float().repeat_interleave(nf).contiguous()
+                return wt
+            k3 = P.derived(kname, (c3.weight, c3.bias), build)
+            G.igemm(al, k3, P.err, split=P.split, bias=k3.bias_k, act=lre, slope=LRELU_SLOPE, out=t3d, out_f32=False)
             if i == 0:                                           # feat = feat + fea_3d1 (:211): the residual epilogue
                 self._c(P, f'tda.c3dfus{i}', cf, t3d, feat, act=lre, residual=feat0.f32)
                 f3.append(None)

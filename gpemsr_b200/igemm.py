@@ -43,6 +43,92 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def cached(cache, name, params, build):
+    """Packed / derived weights are cached per plan, keyed on the live parameters they were built from: a parameter that was
+    reloaded (``load_state_dict`` copies in place: ``_version`` changes), moved (``.to()``: new storage) or updated in place is
+    re-packed on the next call, like the reference nn.Module, which always reads the live parameters."""
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ent = cache.get(name)
+    if ent is None or ent[0] != key:
+        ent = cache[name] = (key, build())
+    return ent[1]
+
+
+# ---- the device-side pipeline error flag (every mbarrier wait is bounded; a time-out sets it and the kernel drains)
+_ERR = {}
+
+
+class _ErrState:
+    def __init__(self, device):
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.host = None                   # pinned mirror, allocated by the first read-back
+        self.event = None
+
+
+def _err_state(device):
+    key = (device.type, device.index if device.index is not None or device.type != 'cuda' else torch.cuda.current_device())
+    st = _ERR.get(key)
+    if st is None:
+        st = _ERR[key] = _ErrState(device)
+    return st
+
+
+def err_flag(device):
+    """ONE flag per device, shared by every plan of every module, so a forward needs one 4-byte read-back to know."""
+    return _err_state(device).flag
+
+
+def _raise_pipeline_error(st, code):
+    st.flag.zero_()                       # otherwise every later launch would abort after its first 1024 probes
+    if st.host is not None:
+        st.host.zero_()
+    st.event = None
+    raise _lib.GpemsrError(-4, f'a GEMM pipeline timed out at wait site {code} (preemption / time-slicing longer than the bounded '
+                               'mbarrier waits, or a pipeline bug): the outputs of that call are INVALID; the flag has been reset')
+
+
+_nested = [0]
+
+
+class nested:
+    """Inside a composite forward (GPEMSR calling its sub-modules' public methods) only the outermost call posts the read-back."""
+
+    def __enter__(self):
+        _nested[0] += 1
+
+    def __exit__(self, *a):
+        _nested[0] -= 1
+
+
+def post_error_check(device):
+    """Queue an asynchronous read-back of the flag behind the kernels launched so far (no host sync).  Called at the end of every
+    public forward; skipped while a CUDA graph is being captured."""
+    if _nested[0] or torch.cuda.is_current_stream_capturing():
+        return
+    st = _err_state(device)
+    if st.host is None:
+        st.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    st.host.copy_(st.flag, non_blocking=True)
+    st.event = torch.cuda.Event()
+    st.event.record()
+
+
+def poll_error(device, wait=False):
+    """Raise if a finished read-back shows a time-out.  wait=True synchronises on the read-back first (used where the caller
+    synchronises anyway: the volume driver's D2H, ``check()``)."""
+    st = _err_state(device)
+    if st.event is None or torch.cuda.is_current_stream_capturing():
+        return
+    if wait:
+        st.event.synchronize()
+    elif not st.event.query():
+        return
+    st.event = None
+    code = int(st.host[0])
+    if code:
+        _raise_pipeline_error(st, code)
+
+
 class Geom:
     """Row geometry of a flattened image batch (mirrors gpemsr_geom_t)."""
 
@@ -85,9 +171,15 @@ class Act:
 class Weights:
     """B-operand planes [taps][k_pad/8][b_rows][8] packed once from a reference-layout parameter."""
 
-    def __init__(self, w, kind, taps=None, split=3, block_rows=256, min_rows=0, pixel_shuffle=False, plain=False):
+    def __init__(self, w, kind, taps=None, split=3, block_rows=256, min_rows=0, pixel_shuffle=False, plain=False, flop_scale=1.0):
         """kind: 'conv' [co, ci, kh, kw] | 'convT' [ci, co, kh, kw] | 'linear' [n, k].
-        taps: list of (src_index, dy, dx); default = all kh*kw taps of a 'same' convolution."""
+        taps: list of (src_index, dy, dx); default = all kh*kw taps of a 'same' convolution.
+        flop_scale: algorithmic FLOPs of the reference layer / FLOPs of the launched tap grid (9/16 for the merged
+        ConvTranspose phases and the space-to-depth stride-2 convs); bookkeeping for bench.py only."""
+        self.flop_scale = flop_scale
+        self.split = split
+        if not w.is_cuda:
+            raise _lib.GpemsrError(-3, f'weights live on {w.device}: move the module to the GPU first (there is no CPU fallback)')
         w = w.detach().contiguous().float()
         dev = w.device
         if kind == 'conv':
@@ -242,7 +334,11 @@ def border_phase_conv(x, wc, bias, cout, out):
 
 
 def _p(t):
-    return None if t is None else t if isinstance(t, int) else t.data_ptr()
+    if t is None or isinstance(t, int):
+        return t
+    if not t.is_cuda:
+        raise _lib.GpemsrError(-3, f'expected a CUDA tensor, got one on {t.device}: there is no CPU fallback')
+    return t.data_ptr()
 
 
 def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row=False, act=ACT_NONE, slope=0.0,
@@ -363,7 +459,7 @@ def add_bilinear_base(x_center, scale, out):
 
 
 def check_pipeline(err):
-    """Synchronises and raises if any GEMM pipeline timed out (tests / smoke only; the hot path never syncs)."""
+    """Synchronises and raises if any GEMM pipeline timed out."""
     code = int(err.item())
     if code:
-        raise _lib.GpemsrError(-4, f'GEMM pipeline timed out at wait site {code}')
+        _raise_pipeline_error(_err_state(err.device), code)

@@ -56,6 +56,7 @@ class _Indexer(_BlockNet):
     def _trunk(self, x):
         """output_layer(feat_extract(input_layer(x))) in the internal format (model/indexer.py:52 / 99)."""
         P = self._plan_for(x)
+        G.poll_error(x.device)
         n, c, h, w = x.shape
         g = G.Geom(n, h, w, True)
         xin = P.act('in', g, c, f32=False)
@@ -85,6 +86,7 @@ class _Indexer(_BlockNet):
         last = self.output_layer[self.num_output_resblck]
         G.igemm(cur, P.weights('output_layer.last', last.weight, 'conv'), P.err, split=P.split, bias=last.bias.detach(),
                 out_nchw=feat, nchw_c=self.latent_dim)
+        G.post_error_check(x.device)
         return feat
 
     @torch.no_grad()
@@ -103,6 +105,7 @@ class _Indexer(_BlockNet):
         G.igemm(feat, P.weights('embedding', self.embedding.weight, 'linear'), P.err, split=P.split,
                 bias=self.embedding.bias.detach(), out_rowmajor=buf, ld=k)
         logits = buf.view(g.n, g.r_img, k)[:, :(g.h + 2) * (g.w + 2)].view(g.n, g.h + 2, g.w + 2, k)[:, 1:-1, 1:-1]
+        G.post_error_check(x.device)
         return logits.contiguous()
 
 

@@ -84,15 +84,20 @@ class SpyNet(nn.Module):
         key = (n, h, w, device.index)
         P = self._plans.get(key)
         if P is None:
-            P = dict(err=torch.zeros(1, dtype=torch.int32, device=device), levels=[], two=torch.full((2,), 2.0, device=device),
-                     mean=self.mean.reshape(3).float().contiguous(), std=self.std.reshape(3).float().contiguous())
+            P = dict(err=G.err_flag(device), levels=[], two=torch.full((2,), 2.0, device=device), cache={})
             for lv in range(6):
                 s = 5 - lv
                 g = G.Geom(n, h >> s, w >> s, padded=3)
                 acts = [G.Act(g, c, device, f32=False, split=self.split) for c in (8, 32, 64, 32, 16)]
-                wts = [G.Weights(self.basic_module[lv].basic_module[2 * i].weight, 'conv', split=self.split) for i in range(5)]
-                P['levels'].append(dict(g=g, acts=acts, wts=wts))
+                P['levels'].append(dict(g=g, acts=acts))
             self._plans[key] = P
+        # packed forms follow the live parameters / buffers (igemm.cached)
+        P['mean'], P['std'] = G.cached(P['cache'], 'norm', (self.mean, self.std), lambda: (
+            self.mean.reshape(3).float().contiguous(), self.std.reshape(3).float().contiguous()))
+        for lv in range(6):
+            mods = self.basic_module[lv].basic_module
+            P['levels'][lv]['wts'] = [G.cached(P['cache'], (lv, i), (mods[2 * i].weight,),
+                                               lambda m=mods[2 * i]: G.Weights(m.weight, 'conv', split=self.split)) for i in range(5)]
         return P
 
     @torch.no_grad()
@@ -140,6 +145,7 @@ class SpyNet(nn.Module):
         """spynet_arch.py SpyNet.forward: resize to multiples of 32, process, resize the flow back and rescale it."""
         if not ref.is_cuda:
             raise _lib.GpemsrError(-3, 'SpyNet needs CUDA tensors: there is no CPU fallback')
+        G.poll_error(ref.device)
         ref, supp = ref.float().contiguous(), supp.float().contiguous()
         n, c, h, w = ref.shape
         wf, hf = int(math.floor(math.ceil(w / 32.0) * 32.0)), int(math.floor(math.ceil(h / 32.0) * 32.0))
@@ -151,7 +157,9 @@ class SpyNet(nn.Module):
         if scale is None:                                      # flow[:, 0] *= w / wf ; flow[:, 1] *= h / hf
             scale = self._plans[key] = torch.tensor([float(w) / float(wf), float(h) / float(hf)], dtype=torch.float32,
                                                     device=ref.device)
-        return resize_bilinear(flow, h, w, False, mul=scale)
+        out = resize_bilinear(flow, h, w, False, mul=scale)
+        G.post_error_check(ref.device)
+        return out
 
     def check(self):
         G.check_pipeline(self._last_err)

@@ -47,6 +47,7 @@ class SRTail(nn.Module):
         if not fea.is_cuda:
             from ._lib import GpemsrError
             raise GpemsrError(-3, 'SRTail needs CUDA tensors: there is no CPU fallback')
+        G.poll_error(fea.device)
         n, c, h, w = fea.shape
         key = (n, h, w, fea.device.index)
         P = self._plans.get(key)
@@ -57,7 +58,9 @@ class SRTail(nn.Module):
         g = G.Geom(n, h, w, True)
         cur = P.act('in', g, c, f32=True)
         G.pack_nchw(fea.float(), cur)
-        return self._tail(P, cur, x_center)
+        out = self._tail(P, cur, x_center)
+        G.post_error_check(fea.device)
+        return out
 
     def _tail(self, P, cur, x_center):
         """The tail from an activation already in the internal format (fp32 master + planes): used by ``forward`` and by the

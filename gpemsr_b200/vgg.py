@@ -54,12 +54,13 @@ class VGG19Slice1(nn.Module):
         if P is None:
             g = G.Geom(n, h, w, True)
             P = dict(g=g, c1=G.Act(g, 64, device, f32=False, split=self.split), ref=G.Act(g, 64, device, f32=True, planes=False),
-                     err=torch.zeros(1, dtype=torch.int32, device=device))
-            w0 = self.slice1[0].weight.detach().float()
-            P['w1'] = w0.sum(1).reshape(64, 9).contiguous()           # the 3 input channels are copies of one image
-            P['b1'] = self.slice1[0].bias.detach().float().contiguous()
-            P['w2'] = G.Weights(self.slice1[2].weight, 'conv', split=self.split)
+                     err=G.err_flag(device), wts={})
             self._plans[key] = P
+        c0, c2 = self.slice1[0], self.slice1[2]                      # packed forms follow the live parameters (igemm.cached)
+        # the 3 input channels are copies of one image: their weights are summed
+        P['w1'], P['b1'] = G.cached(P['wts'], 'c1', (c0.weight, c0.bias), lambda: (
+            c0.weight.detach().float().sum(1).reshape(64, 9).contiguous(), c0.bias.detach().float().contiguous()))
+        P['w2'] = G.cached(P['wts'], 'c2', (c2.weight,), lambda: G.Weights(c2.weight, 'conv', split=self.split))
         return P
 
     def _conv1(self, P, img):
@@ -105,6 +106,7 @@ class VGG19Slice1(nn.Module):
         mask = torch.empty(n, 1, h // ksize, w // ksize, dtype=torch.float32, device=ref_img.device)
         _lib.check(_lib.lib().gpemsr_patch_cosine(_lib.ptr(sums), npatch, 1e-12, _lib.ptr(mask), _lib.stream_ptr()))
         self._last_err = P['err']
+        G.post_error_check(ref_img.device)
         return mask
 
     @torch.no_grad()

@@ -48,6 +48,10 @@ def super_resolve_volume(model, vol, rank=0, world_size=1, dist=None, gather=Tru
     the HR slices are all-gathered once (the only collective).  Returns [S, 1, sH, sW] (or the local block if not gather)."""
     lo, hi = shard_range(vol.shape[0], world_size, rank)
     local = model.forward_volume(vol, lo, hi)
-    if not gather:
-        return local
-    return gather_slices(local, vol.shape[0], world_size, rank, dist)
+    out = gather_slices(local, vol.shape[0], world_size, rank, dist) if gather else local
+    if local.is_cuda:
+        # a volume is a unit of work whose result leaves the GPU next: wait for the pipeline-error read-back here (one host
+        # sync per volume) so a timed-out GEMM pipeline raises instead of returning invalid slices
+        from . import igemm as G
+        G.poll_error(local.device, wait=True)
+    return out

@@ -45,6 +45,12 @@ extern "C" {
 
 #define GPEMSR_PAD_ZEROS   0
 #define GPEMSR_PAD_BORDER  1
+/* how `2 * v / max(size - 1, 1)` of BasicSR's flow_warp is rounded: ATen's CPU kernel divides; ATen's CUDA kernel
+ * (BinaryDivTrueKernel.cu, CPU-scalar divisor) multiplies by the fp32 reciprocal 1.0f / b.  The reference runs on CUDA
+ * (output_GPEMSR.py:44), so RECIP is what its own path computes; DIV reproduces a CPU run of the same code. */
+#define GPEMSR_COORD_DIV     0
+#define GPEMSR_COORD_RECIP   1
+#define GPEMSR_COORD_DEFAULT GPEMSR_COORD_RECIP
 
 /* activation fused into a convolution epilogue */
 #define GPEMSR_ACT_NONE    0
@@ -66,6 +72,9 @@ GPEMSR_API int64_t     gpemsr_kernel_launches(void);          /* kernels launche
  * Coordinates are evaluated with the reference's sequence of separately rounded fp32 ops. */
 GPEMSR_API int gpemsr_flow_warp(const float* x, const float* flow, int n, int c, int h, int w,
                      int padding_mode, int align_corners, float* out, gpemsr_stream_t stream);
+/* same with the coordinate rounding form chosen explicitly (GPEMSR_COORD_*); gpemsr_flow_warp uses GPEMSR_COORD_DEFAULT */
+GPEMSR_API int gpemsr_flow_warp_ex(const float* x, const float* flow, int n, int c, int h, int w,
+                     int padding_mode, int align_corners, int coord_form, float* out, gpemsr_stream_t stream);
 
 /* ---- a-1: Codebook.forward  (model/codebook.py:15-32) ---------------------------------
  * z [b,d,hw] (NCHW with hw = H*W), emb [k,d]  ->  zq [b,d,hw], idx [b*hw] (row order b,h,w),

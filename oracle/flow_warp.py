@@ -43,11 +43,13 @@ def flow_warp_torch(x, flow, interp_mode='bilinear', padding_mode='zeros', align
                          padding_mode=padding_mode, align_corners=align_corners)
 
 
-def source_coords(flow, h, w, padding_mode='zeros', align_corners=True, dtype=np.float32):
+def source_coords(flow, h, w, padding_mode='zeros', align_corners=True, dtype=np.float32, recip=False):
     """Pixel-space sampling coordinates exactly as BasicSR + ATen derive them.
 
     Each line is one separately-rounded elementwise op of the reference
-    (no fused multiply-add across them).
+    (no fused multiply-add across them).  ``recip``: ``tensor / python_scalar`` the way ATen's CUDA kernel evaluates it
+    (aten/src/ATen/native/cuda/BinaryDivTrueKernel.cu: a CPU-scalar divisor b becomes a multiplication by ``1.0f / b``);
+    False = ATen's CPU kernel (a true division).  The reference runs on CUDA (output_GPEMSR.py:44).
     """
     f = dtype
     flow = np.asarray(flow, dtype=f)
@@ -55,8 +57,12 @@ def source_coords(flow, h, w, padding_mode='zeros', align_corners=True, dtype=np
     gy = np.arange(h, dtype=f)[None, :, None]
     vx = gx + flow[..., 0]
     vy = gy + flow[..., 1]
-    nx = (f(2.0) * vx) / f(max(w - 1, 1)) - f(1.0)
-    ny = (f(2.0) * vy) / f(max(h - 1, 1)) - f(1.0)
+    if recip:
+        nx = (f(2.0) * vx) * (f(1.0) / f(max(w - 1, 1))) - f(1.0)
+        ny = (f(2.0) * vy) * (f(1.0) / f(max(h - 1, 1))) - f(1.0)
+    else:
+        nx = (f(2.0) * vx) / f(max(w - 1, 1)) - f(1.0)
+        ny = (f(2.0) * vy) / f(max(h - 1, 1)) - f(1.0)
 
     def unnormalize(c, size):
         if align_corners:                       # ((c + 1) / 2) * (size - 1)
@@ -74,7 +80,7 @@ def source_coords(flow, h, w, padding_mode='zeros', align_corners=True, dtype=np
 
 
 def flow_warp_numpy(x, flow, interp_mode='bilinear', padding_mode='zeros', align_corners=True,
-                    dtype=np.float32):
+                    dtype=np.float32, recip=False):
     """x: [n, c, h, w]; flow: [n, h, w, 2] -> [n, c, h, w]."""
     if interp_mode != 'bilinear':
         raise NotImplementedError(interp_mode)
@@ -82,7 +88,7 @@ def flow_warp_numpy(x, flow, interp_mode='bilinear', padding_mode='zeros', align
     x = np.asarray(x, dtype=f)
     n, c, h, w = x.shape
     assert flow.shape == (n, h, w, 2)
-    ix, iy = source_coords(flow, h, w, padding_mode, align_corners, dtype)
+    ix, iy = source_coords(flow, h, w, padding_mode, align_corners, dtype, recip)
     x0 = np.floor(ix)
     y0 = np.floor(iy)
     x1 = x0 + f(1.0)

@@ -55,7 +55,7 @@ def _spynet(sd, prefix):
     net = basicsr_shim.SpyNet()
     own = net.state_dict()
     net.load_state_dict({k: sd[prefix + k] for k in own}, strict=True)
-    return net.eval()
+    return net.eval().to(sd[prefix + next(iter(own))].device)      # CPU, or the GPU-eager run of oracle/gpu_eager.py
 
 
 def pod(nbr_fea_l, ref_fea_l, nbr, ref, sd, spynet, taps=None, tag=''):

@@ -9,9 +9,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5      # north_star: warped features within 1e-5 max-abs of the reference
 
 
-def _run(x, flow, pm, ac=True):
+def _run(x, flow, pm, ac=True, form='cpu'):
+    """form='cpu': the rounding of ATen's CPU kernels (what the CPU oracle and the fixtures hold); 'cuda': ATen's CUDA form."""
     import gpemsr_b200
-    out = gpemsr_b200.flow_warp(torch.from_numpy(x).cuda(), torch.from_numpy(flow).cuda(), 'bilinear', pm, ac)
+    out = gpemsr_b200.flow_warp(torch.from_numpy(x).cuda(), torch.from_numpy(flow).cuda(), 'bilinear', pm, ac, coord_form=form)
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -37,9 +38,12 @@ def test_vs_oracle_seeded(shape, pm, cuda_dev):
     got = _run(x, flow, pm)
     err = np.abs(got - want).max()
     assert err <= TOL, err
-    # and against ATen on CPU (what the reference executes)
+    # and against ATen on CPU (the reference's code on the CPU device)
     ref = flow_warp_torch(torch.from_numpy(x), torch.from_numpy(flow), 'bilinear', pm).numpy()
     assert np.abs(got - ref).max() <= TOL
+    # the library default reproduces ATen's CUDA rounding of the normalisation (reciprocal multiply)
+    want_c = flow_warp_numpy(x, flow, 'bilinear', pm, recip=True)
+    assert np.abs(_run(x, flow, pm, form='cuda') - want_c).max() <= TOL
 
 
 def test_align_corners_false(cuda_dev):
@@ -101,6 +105,9 @@ def test_full_size_properties(cuda_dev):
     assert torch.allclose(sh[:, :, 2:, :-3], x[:, :, :-2, 3:], atol=5e-3)
     # a CPU-oracle spot check on a crop-free subsample of channels
     sub = x[:, :2].contiguous()
-    want = flow_warp_numpy(sub.cpu().numpy(), flow.cpu().numpy(), 'bilinear', 'border')
+    want = flow_warp_numpy(sub.cpu().numpy(), flow.cpu().numpy(), 'bilinear', 'border', recip=True)
     got = gpemsr_b200.flow_warp(sub, flow, 'bilinear', 'border').cpu().numpy()
+    assert np.abs(got - want).max() <= TOL
+    want = flow_warp_numpy(sub.cpu().numpy(), flow.cpu().numpy(), 'bilinear', 'border')
+    got = gpemsr_b200.flow_warp(sub, flow, 'bilinear', 'border', coord_form='cpu').cpu().numpy()
     assert np.abs(got - want).max() <= TOL

@@ -15,6 +15,19 @@ STAGES = ['L1_fea0', 'fusion.r0', 'fusion.r1', 'fusion.r2', 'fusion.r3', 'L1_fea
           'pod.o2', 'pod.fea2', 'pod.o1', 'pod.fea1', 'pod.off', 'aligned', 'tda.feat', 'tda.f2', 'tda.attn', 'tda.add', 'fea']
 
 
+def _record_index_parity(key, rec):
+    import json, os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, 'r02_index_parity.json')
+        old = json.load(open(path)) if os.path.exists(path) else {}
+        old[key] = rec
+        json.dump(old, open(path, 'w'), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 def _stage_report(model, sd, x, scale):
     model.debug = {}
     out, ref_img = model(x.cuda())
@@ -145,8 +158,12 @@ def test_full_size_windows(cuda_dev, scale, lr):
     flips = int((top.indices != idx).sum())
     print(f'x{scale} {lr}x{lr}: {flips} of {idx.numel()} indices differ from the oracle arg-max, max logit regret {float(regret.max()):.2e}, '
           f'logit range {float(lg.max() - lg.min()):.2f}')
-    assert float(regret.max()) <= 1e-3 * float(lg.max() - lg.min())
-    assert flips <= idx.numel() // 200
+    _record_index_parity(f'x{scale}_{lr}x{lr}_vs_cpu_oracle', dict(latents=int(idx.numel()), flips=flips, max_regret=float(regret.max()),
+                                                                   logit_range=float(lg.max() - lg.min())))
+    # 10x what was measured against the GPU-eager reference (tests/test_gpu_eager_parity_gpu.py, profiles/r02_index_parity.json:
+    # 1 flip of 32 000, regret 2.8e-5); the un-overridden comparison on the frames without flips lives in that test
+    assert float(regret.max()) <= 3e-4
+    assert flips <= 10
     assert tuple(out.shape) == (1, 1, scale * lr, scale * lr)
     e, er = float((out.cpu() - want).abs().max()), float((ref_img.cpu() - want_ref).abs().max())
     print(f'out err {e:.3e}, ref_img err {er:.3e}')

@@ -77,3 +77,18 @@ def test_reffusion_channel_permutation():
     wp = torch.cat([w[:, 64 + d:], w[:, :64], w[:, 64:64 + d]], dim=1)
     got = F.conv2d(torch.cat((car, lr, dec), 1), wp, None, 1, 1)
     assert (got - want).abs().max().item() < 1e-4
+
+
+def test_cached_follows_parameter_identity_and_version():
+    """igemm.cached: derived weights are rebuilt when the parameter is updated in place (load_state_dict) or replaced (.to())."""
+    import torch
+    from gpemsr_b200 import igemm as G
+    p = torch.nn.Parameter(torch.zeros(4))
+    cache, builds = {}, []
+    get = lambda: G.cached(cache, 'w', (p,), lambda: builds.append(1) or float(p.sum()))
+    assert get() == 0.0 and get() == 0.0 and len(builds) == 1
+    with torch.no_grad():
+        p.copy_(torch.ones(4))                                     # what load_state_dict does
+    assert get() == 4.0 and len(builds) == 2
+    p.data = torch.full((4,), 2.0)                                 # what .to(device) does
+    assert get() == 8.0 and len(builds) == 3

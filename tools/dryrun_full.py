@@ -37,6 +37,11 @@ _lib._lib = Fake()
 _lib.stream_ptr = lambda: None
 torch.Tensor.is_cuda = property(lambda self: True)
 torch.cuda.current_device = lambda: 0
+torch.cuda.current_stream = lambda device=None: type('S', (), {'cuda_stream': 0})()
+
+from gpemsr_b200 import igemm as _G  # noqa: E402
+_G.post_error_check = lambda device: None          # (the read-back of the device error flag needs a real device)
+_G.poll_error = lambda device, wait=False: None
 
 from full_model_util import build  # noqa: E402
 
