@@ -37,6 +37,11 @@ struct EpiConv {
   const float* patch_other;   // fp32 cells in the output geometry: the tensor the stored values are correlated with
   float* patch_sums;          // [n][h / patch][w / patch][3] = (sum v*o, sum v*v, sum o*o) per patch x patch block of pixels
   int patch_size;
+  // softmax fused into the attention GEMMs (model/blocks.py:74-79): rows = queries, columns = keys
+  float* row_max_out;         // pre-pass: only the per-row maximum of v over the valid columns is produced (atomic max)
+  const float* row_max;       // GPEMSR_ACT_EXP: v = exp(v - row_max[row])
+  float* row_sum;             // per-row sum of the stored v over the columns (atomicAdd once per CTA column sweep)
+  const float* row_div;       // v = acc / row_div[row]  (the deferred softmax normalisation of P v^T)
 
   static constexpr int WARPS = BLOCK_N >= 64 ? 8 : 4;
   struct State {
@@ -46,6 +51,7 @@ struct EpiConv {
     long long orow = 0;        // output row of (up*y + py, up*x + px) in the blocked outputs
     long long nchw0 = 0;       // offset of (img, channel 0, Y, X) in out_nchw
     float p_ab = 0.f, p_aa = 0.f, p_bb = 0.f;      // patch-correlation partial sums of this row (patch_sums)
+    float r_max = -3.0e38f, r_sum = 0.f, r_sub = 0.f, r_inv = 1.f;     // fused softmax: running max / sum, subtrahend, 1 / divisor
   };
 
   // one cell = 8 consecutive output channels of one output pixel; (dy, dx) only differ from 0 under PixelShuffle
@@ -129,16 +135,36 @@ struct EpiConv {
       for (int j = 0; j < CHUNK; ++j)
         f[j] = fmaf(scale, __uint_as_float(r[j]), (bias && col0 + j < n_cols) ? __ldg(bias + col0 + j) : 0.f);
     }
+    if (row_max_out) {                   // softmax pre-pass: nothing is stored
+      float m = st.r_max;
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) if (full || col0 + j < n_cols) m = fmaxf(m, f[j]);
+      st.r_max = m;
+      return;
+    }
+    if (row_div) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) f[j] *= st.r_inv;
+    }
     if (act == GPEMSR_ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] = fmaxf(f[j], 0.f);
     } else if (act == GPEMSR_ACT_LRELU) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
+    } else if (act == GPEMSR_ACT_EXP) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) f[j] = expf(f[j] - st.r_sub);
     }
     if (!full) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (col0 + j >= n_cols) f[j] = 0.f;
+    }
+    if (row_sum) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) a += f[j];
+      st.r_sum += a;
     }
     if (gn_sums) {                       // all 32 lanes take part; rows outside the image contribute zeros
       if (!st.valid) {
@@ -213,7 +239,7 @@ struct EpiConv {
     }
   }
 
-  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int, int row, int part) const {
+  __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int part) const {
     const long long rel = m_tile * gemm::BLOCK_M + row;
     if (!st.init) {
       st.init = true;
@@ -224,6 +250,8 @@ struct EpiConv {
         st.orow = place_row(og, st.img, Y, X);
         const long long Wo = (long long)up * ag.w, Ho = (long long)up * ag.h;
         st.nchw0 = ((long long)st.img * nchw_c * Ho + Y) * Wo + X;
+        if (row_max) st.r_sub = __ldg(row_max + rel);
+        if (row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
       }
     }
     constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
@@ -246,6 +274,15 @@ struct EpiConv {
       if ((st.valid || gn_sums) && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
     }
     if (patch_sums) flush_patch(st);
+    // fused softmax statistics: one atomic per row once this CTA has swept its last column tile of the row tile
+    if ((row_max_out || row_sum) && st.valid && n_tile + (int)gridDim.y >= n_tiles) {
+      if (row_max_out) {                 // float max through the ordered-integer trick (the buffer starts at -1.7e38)
+        if (st.r_max >= 0.f) atomicMax(reinterpret_cast<int*>(row_max_out + rel), __float_as_int(st.r_max));
+        else atomicMin(reinterpret_cast<unsigned*>(row_max_out + rel), __float_as_uint(st.r_max));
+      } else {
+        atomicAdd(row_sum + rel, st.r_sum);
+      }
+    }
   }
 
   // The 32 lanes of a warp are 32 consecutive flat rows: pixels of the same patch row form contiguous runs.  A segmented
@@ -283,6 +320,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   e.pair_off = 0;
   const int sms = gpemsr::num_sms();
   const bool clustered = BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters();
@@ -331,6 +369,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -373,6 +412,7 @@ int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_dyfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -935,6 +975,15 @@ int gpemsr_igemm(const gpemsr_igemm_desc_t* dp, gpemsr_stream_t stream) {
     if ((rc = check_geom(d.o_geom, "igemm(patch)")) != GPEMSR_OK) return rc;
     GPEMSR_CUDA_OK(cudaMemsetAsync(d.patch_sums, 0, (size_t)d.a_geom.n * (d.a_geom.h / ps) * (d.a_geom.w / ps) * 3 * sizeof(float),
                                    (cudaStream_t)stream));
+  }
+
+  if (d.act == GPEMSR_ACT_EXP && !d.row_max) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: GPEMSR_ACT_EXP needs row_max");
+  if (d.row_max_out || d.row_sum) {
+    if (d.row_max_out && d.row_sum) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: row_max_out (pre-pass) excludes row_sum");
+    if (d.up != 1 || d.pixel_shuffle || d.phase_cols) return set_error(GPEMSR_ERR_BAD_SHAPE, "igemm: row statistics need a same-resolution output");
+    const size_t rows = (size_t)d.a_geom.n * d.a_geom.r_img;
+    if (d.row_max_out) GPEMSR_CUDA_OK(cudaMemsetAsync(d.row_max_out, 0xFE, rows * sizeof(float), (cudaStream_t)stream));   // -1.7e38
+    else GPEMSR_CUDA_OK(cudaMemsetAsync(d.row_sum, 0, rows * sizeof(float), (cudaStream_t)stream));
   }
 
   const int block_n = pick_block_n(d);

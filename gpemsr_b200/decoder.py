@@ -57,7 +57,8 @@ class _Plan:
     """Packed weights + activation buffers for one input shape (built lazily, reused across calls)."""
 
     def __init__(self, dec, n, h, w, device):
-        self.split = 3 if dec.precision == 'fp32' else 1
+        self.prec = G.Precision(dec.precision)
+        self.split = self.prec.planes()          # activations carry lo planes whenever some launch is fp32-faithful
         self.device = device
         self.err = G.err_flag(device)           # one flag per device, read back once per forward (igemm.post_error_check)
         self.n, self.h, self.w = n, h, w
@@ -73,10 +74,14 @@ class _Plan:
             self.bufs[key] = a
         return a
 
+    def sp(self, name):
+        """The split (1 | 3) layer `name` runs at (igemm.Precision)."""
+        return self.prec.split(name)
+
     def weights(self, name, param, kind, taps=None, min_rows=0, split=None):
         """Packed B operand of `param`, re-packed whenever the live parameter changes (igemm.cached)."""
         return G.cached(self.wts, name, (param,),
-                        lambda: G.Weights(param, kind, taps=taps, split=split or self.split, min_rows=min_rows))
+                        lambda: G.Weights(param, kind, taps=taps, split=split or self.sp(name), min_rows=min_rows))
 
     def derived(self, name, params, build):
         """Anything computed on the host from parameters (merged phases, composed layers, Kronecker weights), same caching."""
@@ -95,8 +100,7 @@ class _BlockNet(nn.Module):
     """Runs the reference's building blocks (model/blocks.py) on the implicit-GEMM kernels; shared by Decoder and Indexer*."""
 
     def _init_runner(self, precision):
-        assert precision in ('fp32', 'bf16')
-        self.precision = precision
+        self.precision = G.Precision(precision)
         self._plans = {}
 
     def _plan_for(self, x):
@@ -119,7 +123,7 @@ class _BlockNet(nn.Module):
     # ------------------------------------------------------------------ building blocks
     def _conv(self, P, name, mod, x, out, **kw):
         wt = P.weights(name, mod.weight, 'conv')
-        G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), out=out, **kw)
+        G.igemm(x, wt, P.err, split=P.sp(name), bias=mod.bias.detach(), out=out, **kw)
 
     def _res_block(self, P, name, rb, x, nchw_out=None, planes_into=None):
         """x + ReLU(GN(conv(ReLU(GN(conv(x))))))  (model/blocks.py:25-29); x carries fp32 master + planes.
@@ -163,17 +167,17 @@ class _BlockNet(nn.Module):
         if cout % 32 == 0 and cout <= 64:
             # narrow up-blocks are bound by memory traffic: run the four phases as ONE GEMM with 4*cout columns
             def build():
-                wt = G.Weights(G.convT_merged_weight(ub.upblock.weight.detach()), 'conv', taps='offsets01', split=P.split,
+                wt = G.Weights(G.convT_merged_weight(ub.upblock.weight.detach()), 'conv', taps='offsets01', split=P.sp(name),
                                flop_scale=9 / 16)
                 wt.bias4 = ub.upblock.bias.detach().repeat(4).contiguous()
                 return wt
             wt = P.derived(name + '.merged', (ub.upblock.weight, ub.upblock.bias), build)
-            G.igemm(x, wt, P.err, split=P.split, bias=wt.bias4, out=y, up=2, phase_cols=cout, out_f32=need_f32)
+            G.igemm(x, wt, P.err, split=P.sp(name), bias=wt.bias4, out=y, up=2, phase_cols=cout, out_f32=need_f32)
             return y
         for py in (0, 1):
             for px in (0, 1):
                 wt = P.weights(f'{name}.p{py}{px}', ub.upblock.weight, 'convT', taps=G.convT_phase_taps(py, px))
-                G.igemm(x, wt, P.err, split=P.split, bias=ub.upblock.bias.detach(), out=y, up=2, py=py, px=px,
+                G.igemm(x, wt, P.err, split=P.sp(name), bias=ub.upblock.bias.detach(), out=y, up=2, py=py, px=px,
                         out_f32=need_f32)
         return y
 
@@ -186,10 +190,10 @@ class _BlockNet(nn.Module):
         G.space_to_depth(x, s2d)
         def build():
             m, taps = G.down_conv_weight(conv.weight.detach())
-            return G.Weights(m, 'conv', taps=taps, split=P.split, flop_scale=9 / 16)
+            return G.Weights(m, 'conv', taps=taps, split=P.sp(name), flop_scale=9 / 16)
         wt = P.derived(name, (conv.weight,), build)
         y = P.act(name + '.out', og, conv.out_channels, f32=True)
-        G.igemm(s2d, wt, P.err, split=P.split, bias=conv.bias.detach(), out=y)
+        G.igemm(s2d, wt, P.err, split=P.sp(name), bias=conv.bias.detach(), out=y)
         return y
 
     def _non_local(self, P, name, nl, x):
@@ -204,8 +208,8 @@ class _BlockNet(nn.Module):
         q = P.act(name + '.q', cg, c, f32=False)
         k = P.act(name + '.k', cg, c, f32=False)
         o = P.act(name + '.o', cg, c, f32=False)
-        G.igemm(hn, P.weights(name + '.q', nl.q.weight, 'conv'), P.err, split=P.split, bias=nl.q.bias.detach(), out=q, out_f32=False)
-        G.igemm(hn, P.weights(name + '.k', nl.k.weight, 'conv'), P.err, split=P.split, bias=nl.k.bias.detach(), out=k, out_f32=False)
+        G.igemm(hn, P.weights(name + '.q', nl.q.weight, 'conv'), P.err, split=P.sp(name + '.q'), bias=nl.q.bias.detach(), out=q, out_f32=False)
+        G.igemm(hn, P.weights(name + '.k', nl.k.weight, 'conv'), P.err, split=P.sp(name + '.k'), bias=nl.k.bias.detach(), out=k, out_f32=False)
         # v^T [tokens/8][channels][8]: weights as the A operand, tokens as columns, bias per row
         wv = P.weights(name + '.v', nl.v.weight, 'conv', min_rows=128)      # used as the A operand: >= one 128-row tile
         c_rows = G._round_up(wv.b_rows, 128)
@@ -218,37 +222,41 @@ class _BlockNet(nn.Module):
             vt = (torch.zeros(shape, dtype=torch.bfloat16, device=P.device),
                   torch.zeros(shape, dtype=torch.bfloat16, device=P.device) if P.split == 3 else None)
             P.bufs[name + '.vt'] = vt
-            sg = G.Geom(1, g.h, g.w, padded=False, r_img=t_pad, m0=0)             # scores: rows = queries, cells = 8 keys
-            P.bufs[name + '.s'] = _View(None, None, sg)
-            P.bufs[name + '.s'].f32 = torch.zeros(t_pad // 8, sg.rows_alloc, 8, dtype=torch.float32, device=P.device)
-            P.bufs[name + '.stats'] = torch.zeros(2 * t_pad * 17, dtype=torch.float32, device=P.device)
+            # the softmax is fused into the two attention GEMMs: no fp32 score matrix.  rmax / rsum: per-query statistics;
+            # p: the unnormalised probabilities exp(s - rmax) as (hi, lo) operand planes [t_pad/8][t_pad][8] (zero-initialised:
+            # padding rows / key columns are never written), shared by the images of the batch (stream order)
+            P.bufs[name + '.rmax'] = torch.zeros(t_pad, dtype=torch.float32, device=P.device)
+            P.bufs[name + '.rsum'] = torch.zeros(t_pad, dtype=torch.float32, device=P.device)
             pshape = (t_pad // 8, t_pad, 8)
             P.bufs[name + '.p'] = (torch.zeros(pshape, dtype=torch.bfloat16, device=P.device),
                                    torch.zeros(pshape, dtype=torch.bfloat16, device=P.device) if P.split == 3 else None)
-        s_buf, stats = P.bufs[name + '.s'], P.bufs[name + '.stats']
+        rmax, rsum = P.bufs[name + '.rmax'], P.bufs[name + '.rsum']
         p_hi, p_lo = P.bufs[name + '.p']
+        pg = G.Geom(1, g.h, g.w, padded=False, r_img=t_pad, m0=0, rows_alloc=t_pad)
+        pa = _View(p_hi, p_lo, pg)
         row_bytes = 16                                                # one 8 x bf16 cell
+        sm_scale = float(int(c) ** (-0.5))
         for i in range(g.n):
             vt_geom = G.Geom(1, 1, c, padded=False, r_img=wgeom.r_img, m0=0, rows_alloc=c_rows)
             vt_i = _View(vt[0][i], vt[1][i] if vt[1] is not None else None, vt_geom)
-            G.igemm(wa, None, P.err, split=P.split, bias=nl.v.bias.detach(), bias_per_row=True, out=vt_i, out_f32=False,
+            G.igemm(wa, None, P.err, split=P.sp(name + '.v'), bias=nl.v.bias.detach(), bias_per_row=True, out=vt_i, out_f32=False,
                     n_cols=t, b_hi=hn.hi.data_ptr() + i * t_pad * row_bytes,
                     b_lo=(hn.lo.data_ptr() + i * t_pad * row_bytes) if hn.lo is not None else None,
                     b_rows=cg.rows_alloc, k_pad=hn.c_pad)
-            # scores = q_i^T k_i / sqrt(c)  -> fp32 [t_pad, t_pad]
-            G.igemm(q, None, P.err, split=P.split, scale=float(int(c) ** (-0.5)), a_geom=cg.sample(i), n_cols=t,
-                    b_hi=k.hi.data_ptr() + i * t_pad * row_bytes,
-                    b_lo=(k.lo.data_ptr() + i * t_pad * row_bytes) if k.lo is not None else None,
-                    b_rows=cg.rows_alloc, k_pad=k.c_pad, out=s_buf, out_planes=False)
-            G.softmax_cells_blocked(s_buf.f32, t, s_buf.geom.rows_alloc, t_pad, stats, p_hi, p_lo)
-            # o_i = P v_i^T
-            pg = G.Geom(1, g.h, g.w, padded=False, r_img=t_pad, m0=0, rows_alloc=t_pad)
-            pa = _View(p_hi, p_lo, pg)
-            G.igemm(pa, None, P.err, split=P.split, n_cols=c, b_hi=vt_i.hi.data_ptr(),
+            k_hi = k.hi.data_ptr() + i * t_pad * row_bytes
+            k_lo = (k.lo.data_ptr() + i * t_pad * row_bytes) if k.lo is not None else None
+            # 1. row maxima of q_i^T k_i / sqrt(c) from ONE bf16 pass (a stabiliser only: any value near the maximum will do)
+            G.igemm(q, None, P.err, split=1, scale=sm_scale, a_geom=cg.sample(i), n_cols=t, b_hi=k_hi, b_rows=cg.rows_alloc,
+                    k_pad=k.c_pad, row_max_out=rmax)
+            # 2. scores in the fp32-faithful split; the epilogue stores exp(s - max) as operand planes and sums the rows
+            G.igemm(q, None, P.err, split=P.sp(name + '.scores'), scale=sm_scale, a_geom=cg.sample(i), n_cols=t, b_hi=k_hi, b_lo=k_lo,
+                    b_rows=cg.rows_alloc, k_pad=k.c_pad, act=G.ACT_EXP, row_max=rmax, row_sum=rsum, out=pa, out_f32=False)
+            # 3. o_i = (P v_i^T) / row sum
+            G.igemm(pa, None, P.err, split=P.sp(name + '.pv'), n_cols=c, b_hi=vt_i.hi.data_ptr(),
                     b_lo=vt_i.lo.data_ptr() if vt_i.lo is not None else None, b_rows=c_rows, k_pad=t_pad,
-                    out=o, o_geom=cg.sample(i), out_f32=False)
+                    out=o, o_geom=cg.sample(i), out_f32=False, row_div=rsum)
         y = P.act(name + '.out', g, c, f32=True)
-        G.igemm(o, P.weights(name + '.proj_out', nl.proj_out.weight, 'conv'), P.err, split=P.split,
+        G.igemm(o, P.weights(name + '.proj_out', nl.proj_out.weight, 'conv'), P.err, split=P.sp(name + '.proj_out'),
                 bias=nl.proj_out.bias.detach(), residual=x.f32, out=y)
         return y
 
@@ -292,10 +300,10 @@ class Decoder(_BlockNet):
             wc, bias = G.compose_upblock_conv(ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias)
             dev = ub.upblock.weight.device
             w_int = wc[4].reshape(4 * co, wc.shape[3], 3, 3).contiguous().to(dev)          # phase-major output channels
-            return dict(wt=G.Weights(w_int, 'conv', split=P.split), b_int=bias[4].repeat(4).contiguous().to(dev),
+            return dict(wt=G.Weights(w_int, 'conv', split=P.sp('final')), b_int=bias[4].repeat(4).contiguous().to(dev),
                         wc=wc.contiguous().to(dev), bias=bias.contiguous().to(dev))
         st = P.derived('final', (ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias), build)
-        G.igemm(x, st['wt'], P.err, split=P.split, bias=st['b_int'], up=2, phase_cols=co, out_nchw=img, nchw_c=co)
+        G.igemm(x, st['wt'], P.err, split=P.sp('final'), bias=st['b_int'], up=2, phase_cols=co, out_nchw=img, nchw_c=co)
         G.border_phase_conv(x, st['wc'], st['bias'], co, img)
 
     # ------------------------------------------------------------------ reference API
@@ -359,7 +367,7 @@ class Decoder(_BlockNet):
                 cur = self._up_block(P, name, mod, cur, need_f32=not last)
         img = torch.empty(n, self.output_layer.out_channels, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x.device)
         wt = P.weights('output_layer', self.output_layer.weight, 'conv')
-        G.igemm(cur, wt, P.err, split=P.split, bias=self.output_layer.bias.detach(), out_nchw=img,
+        G.igemm(cur, wt, P.err, split=P.sp('output_layer'), bias=self.output_layer.bias.detach(), out_nchw=img,
                 nchw_c=self.output_layer.out_channels)
         return feats, img
 

@@ -44,11 +44,13 @@ def _conv(cin, cout, k=3, s=1, p=1):
 class POD(nn.Module):                                            # parameter holder for model/GPEMSR.py:64-97
     def __init__(self, nf=64, groups=8, precision='fp32'):
         super().__init__()
-        self.spynet = SpyNet(precision=precision)
+        prec = G.Precision(precision)
+        one = lambda name: 'fp32' if prec.split(name) == 3 else 'bf16'      # modules that run at ONE split
+        self.spynet = SpyNet(precision=one('spynet'))
         self.flowdsconv0_1, self.flowdsconv0_2 = _conv(2, 16, 3, 4, 1), _conv(2, 16, 3, 4, 1)
         self.flowdsconv1_1, self.flowdsconv1_2 = _conv(16, 16, 3, 2, 1), _conv(16, 16, 3, 2, 1)
         self.flowdsconv2_1, self.flowdsconv2_2 = _conv(16, 16, 3, 2, 1), _conv(16, 16, 3, 2, 1)
-        dcn = lambda: DCNv2Pack(nf, nf, 3, stride=1, padding=1, dilation=1, deformable_groups=groups, precision=precision)
+        dcn = lambda: DCNv2Pack(nf, nf, 3, stride=1, padding=1, dilation=1, deformable_groups=groups, precision=one('pod.dcn'))
         self.L3_offset_conv1, self.L3_offset_conv2 = _conv(nf * 2 + 34, nf), _conv(nf, nf)
         self.L3_dcnpack = dcn()
         self.L2_offset_conv1, self.L2_offset_conv2, self.L2_offset_conv3 = _conv(nf * 2 + 34, nf), _conv(nf * 2, nf), _conv(nf, nf)
@@ -98,7 +100,8 @@ class GPEMSR(SRTail):
         self.center, self.w_ref, self.align_mode, self.fusion_mode, self.mode, self.nframes = nframes // 2, w_ref, align_mode, fusion_mode, mode, nframes
         self.conv_first = _conv(1, nf)
         self.feature_extraction = nn.Sequential(*[ResidualBlockNoBN(nf) for _ in range(front_RBs)])
-        self.vgg = VGG19Slice1(precision=precision)
+        prec = G.Precision(precision)
+        self.vgg = VGG19Slice1(precision='fp32' if prec.split('vgg') == 3 else 'bf16')
         self.refmaskconv1, self.refmaskconv2, self.refmaskconv3 = _conv(1, nf), _conv(nf, nf), _conv(nf, 1)
         for k in (2, 3, 4):
             setattr(self, f'reffea_L{k}_conv1', nn.ConvTranspose2d(nf, nf, 3, 2, 1, 1, bias=True))
@@ -108,7 +111,7 @@ class GPEMSR(SRTail):
         for j in (1, 2, 3):
             setattr(self, f'down_fea_conv{j}', _conv(nf * j, nf * j, 3, 2, 1))
         self.reduce_dim_conv = _conv((5 if scale == 16 else 4) * nf, nf, 1, 1, 0)
-        self.refmodel = (lrGenerator16 if scale == 16 else lrGenerator8)(argref, precision=precision)
+        self.refmodel = (lrGenerator16 if scale == 16 else lrGenerator8)(argref, precision=prec)
         if ref_path_G:
             self.refmodel.load_state_dict({k: v for k, v in torch.load(ref_path_G, map_location='cpu').items()
                                            if not k.startswith('encoder.')}, strict=False)
@@ -116,7 +119,7 @@ class GPEMSR(SRTail):
             self.refmodel.indexer.load_state_dict(torch.load(ref_path_Indexer, map_location='cpu'), strict=True)
         self.fea_L2_conv1, self.fea_L2_conv2 = _conv(nf, nf, 3, 2, 1), _conv(nf, nf)
         self.fea_L3_conv1, self.fea_L3_conv2 = _conv(nf, nf, 3, 2, 1), _conv(nf, nf)
-        self.align_module = POD(nf=nf, groups=groups, precision=precision)
+        self.align_module = POD(nf=nf, groups=groups, precision=prec)
         self.ThreeDA = ThreeDA(num_feat=nf, num_frame=nframes, center_frame_idx=self.center)
         for p in self.parameters():
             p.requires_grad = False
@@ -136,7 +139,7 @@ class GPEMSR(SRTail):
     # ------------------------------------------------------------------ helpers
     def _c(self, P, name, mod, x, out, act=G.ACT_NONE, **kw):
         wt = P.weights(name, mod.weight, 'conv')
-        G.igemm(x, wt, P.err, split=P.split, bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
+        G.igemm(x, wt, P.err, split=P.sp(name), bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
 
     def _s2conv(self, P, name, mod, x, out, act=G.ACT_NONE, **kw):
         """Conv2d(k3, s2, p1) = space-to-depth + 2x2 taps (model/GPEMSR.py:257,260,263,288,290)."""
@@ -146,18 +149,18 @@ class GPEMSR(SRTail):
         G.space_to_depth(x, s2d)
         def build():
             m, taps = G.down_conv_weight(mod.weight.detach())
-            return G.Weights(m, 'conv', taps=taps, split=P.split, flop_scale=9 / 16)
+            return G.Weights(m, 'conv', taps=taps, split=P.sp(name), flop_scale=9 / 16)
         wt = P.derived(name, (mod.weight,), build)
-        G.igemm(s2d, wt, P.err, split=P.split, bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
+        G.igemm(s2d, wt, P.err, split=P.sp(name), bias=mod.bias.detach(), act=act, slope=LRELU_SLOPE, out=out, **kw)
 
     def _convT(self, P, name, mod, x, out, **kw):
         """lrelu(ConvTranspose2d(k3, s2, p1, op1)) as ONE GEMM over the four output-parity phases (:335-340)."""
         def build():
-            wt = G.Weights(G.convT_merged_weight(mod.weight.detach()), 'conv', taps='offsets01', split=P.split, flop_scale=9 / 16)
+            wt = G.Weights(G.convT_merged_weight(mod.weight.detach()), 'conv', taps='offsets01', split=P.sp(name), flop_scale=9 / 16)
             wt.bias4 = mod.bias.detach().repeat(4).contiguous()
             return wt
         wt = P.derived(name, (mod.weight, mod.bias), build)
-        G.igemm(x, wt, P.err, split=P.split, bias=wt.bias4, act=G.ACT_LRELU, slope=LRELU_SLOPE, out=out, up=2,
+        G.igemm(x, wt, P.err, split=P.sp(name), bias=wt.bias4, act=G.ACT_LRELU, slope=LRELU_SLOPE, out=out, up=2,
                 phase_cols=mod.weight.shape[1], **kw)
 
     def _rbs(self, P, name, blocks, cur, g):
@@ -258,12 +261,12 @@ class GPEMSR(SRTail):
         xin = P.act('x', g1, 1, f32=False)
         G.pack_nchw(x, xin)
         f0 = P.act('conv_first', g1, nf, f32=True)
-        self._c(P, 'conv_first', self.conv_first, xin, f0, act=lre)
-        L1 = self._rbs(P, 'fe', self.feature_extraction, f0, g1)
+        self._c(P, 'enc.conv_first', self.conv_first, xin, f0, act=lre)
+        L1 = self._rbs(P, 'enc.fe', self.feature_extraction, f0, g1)
         self._tap('L1_fea0', L1)
         self._copy(L1, 0, nf, U[J - 1], 64 + 64 * (J - 1))
         for j in range(J - 2, -1, -1):                           # lrelu(reffea_L{k}_conv1): level j from level j + 1
-            self._convT(P, f'reffea{j}', getattr(self, f'reffea_L{J - j}_conv1'), self._view(U[j + 1], 64 + 64 * (j + 1), nf),
+            self._convT(P, f'enc.reffea{j}', getattr(self, f'reffea_L{J - j}_conv1'), self._view(U[j + 1], 64 + 64 * (j + 1), nf),
                         U[j], c_off=64 + 64 * j, out_f32=False)
 
         # ---- generative-prior features of every frame (:342 / 385) and the similarity mask (:344-357 / 387-400)
@@ -276,12 +279,12 @@ class GPEMSR(SRTail):
         gm = G.Geom(N, hm, wm, True)
         ma, mb, mc = P.act('mask.in', gm, 1, f32=False), P.act('mask.a', gm, nf, f32=False), P.act('mask.b', gm, nf, f32=False)
         G.pack_nchw(m0, ma)
-        self._c(P, 'refmaskconv1', self.refmaskconv1, ma, mb, act=lre, out_f32=False)
-        self._c(P, 'refmaskconv2', self.refmaskconv2, mb, mc, act=lre, out_f32=False)
+        self._c(P, 'enc.mask.conv1', self.refmaskconv1, ma, mb, act=lre, out_f32=False)
+        self._c(P, 'enc.mask.conv2', self.refmaskconv2, mb, mc, act=lre, out_f32=False)
         mask = P.bufs.get('mask.out')
         if mask is None:
             mask = P.bufs['mask.out'] = torch.empty(N, 1, hm, wm, dtype=torch.float32, device=dev)
-        self._c(P, 'refmaskconv3', self.refmaskconv3, mc, None, act=lre, out_nchw=mask, nchw_c=1)      # sigmoid: in mul_mask
+        self._c(P, 'enc.mask.conv3', self.refmaskconv3, mc, None, act=lre, out_nchw=mask, nchw_c=1)      # sigmoid: in mul_mask
         self._tap('mask_logit', mask)
 
         # ---- reference-feature fusion, finest level first (:360-378 / 403-417)
@@ -289,12 +292,12 @@ class GPEMSR(SRTail):
             g = geo[j]
             kin = 64 * j + 64 + (64 << j)
             conv = getattr(self, f'reffusionconv{j + 1}')
-            wname = f'reffusionconv{j + 1}'
+            wname = f'enc.reffusionconv{j + 1}'
             def build(w=conv.weight.detach(), d=64 << j):          # reference input order (LR feat, decoder, carried) -> buffer order
-                return G.Weights(torch.cat([w[:, 64 + d:], w[:, :64], w[:, 64:64 + d]], dim=1).contiguous(), 'conv', split=P.split)
+                return G.Weights(torch.cat([w[:, 64 + d:], w[:, :64], w[:, 64:64 + d]], dim=1).contiguous(), 'conv', split=P.sp(wname))
             r = P.act(f'fus.r{g.key()}', g, nf, f32=True)
-            G.igemm(self._view(U[j], 64, kin), P.derived(wname, (conv.weight,), build), P.err, split=P.split, bias=conv.bias.detach(), out=r)
-            r = self._rbs(P, f'ffb{j}', getattr(self, f'fusion_fea_block{j + 1}'), r, g)
+            G.igemm(self._view(U[j], 64, kin), P.derived(wname, (conv.weight,), build), P.err, split=P.sp(wname), bias=conv.bias.detach(), out=r)
+            r = self._rbs(P, f'enc.ffb{j}', getattr(self, f'fusion_fea_block{j + 1}'), r, g)
             gc = g.c
             _lib.check(L.gpemsr_cells_mul_mask(_lib.ptr(r.f32), C.byref(gc), nf, _lib.ptr(mask), hm, wm, g.h // hm, 1, 0, None,
                                                _lib.ptr(U[j].hi), _lib.ptr(U[j].lo), st()))
@@ -304,16 +307,16 @@ class GPEMSR(SRTail):
                                                    _lib.ptr(dbg.f32), None, None, st()))
                 self._tap(f'fusion.r{j}', dbg)
             if j < J - 1:
-                self._s2conv(P, f'down_fea_conv{j + 1}', getattr(self, f'down_fea_conv{j + 1}'), self._view(U[j], 0, 64 * (j + 1)),
+                self._s2conv(P, f'enc.down_fea_conv{j + 1}', getattr(self, f'down_fea_conv{j + 1}'), self._view(U[j], 0, 64 * (j + 1)),
                              U[j + 1], c_off=64, out_f32=False)
         # L1_fea = reduce_dim_conv(cat(R, carried, L1)) (:377-378 / 416-417), then the alignment pyramid (:421-425)
         gL = [g1, G.Geom(N, H // 2, W // 2, True), G.Geom(N, H // 4, W // 4, True)]
         encL = [P.act(f'encL{k}', gL[k], nf, f32=True) for k in range(3)]
-        self._c(P, 'reduce_dim_conv', self.reduce_dim_conv, self._view(U[J - 1], 0, 128 + 64 * (J - 1)), encL[0])
+        self._c(P, 'enc.reduce_dim_conv', self.reduce_dim_conv, self._view(U[J - 1], 0, 128 + 64 * (J - 1)), encL[0])
         for k in (1, 2):
             t = P.act(f'enc.t{k}', gL[k], nf, f32=False)
-            self._s2conv(P, f'fea_L{k + 1}_conv1', getattr(self, f'fea_L{k + 1}_conv1'), encL[k - 1], t, act=lre, out_f32=False)
-            self._c(P, f'fea_L{k + 1}_conv2', getattr(self, f'fea_L{k + 1}_conv2'), t, encL[k], act=lre)
+            self._s2conv(P, f'enc.fea_L{k + 1}_conv1', getattr(self, f'fea_L{k + 1}_conv1'), encL[k - 1], t, act=lre, out_f32=False)
+            self._c(P, f'enc.fea_L{k + 1}_conv2', getattr(self, f'fea_L{k + 1}_conv2'), t, encL[k], act=lre)
         self._tap('L1_fea', encL[0]); self._tap('L2_fea', encL[1]); self._tap('L3_fea', encL[2])
         return P, ref_img
 
@@ -444,35 +447,35 @@ class GPEMSR(SRTail):
         nbr_f32 = lambda k: catL[k].f32                          # channels 0..63 of the level operand = the neighbour features
 
         # L3 (:112-115)
-        self._c(P, 'L3_offset_conv1', am.L3_offset_conv1, catL[2], t64[2], act=lre, out_f32=False)
-        self._c(P, 'L3_offset_conv2', am.L3_offset_conv2, t64[2], oa[2], act=lre)
-        am.L3_dcnpack.run_acts(P, 'L3_dcn', nbr_f32(2), gL[2], oa[2], fe[2], P.err, act=lre, slope=LRELU_SLOPE, out_planes=False)
+        self._c(P, 'pod.L3_offset_conv1', am.L3_offset_conv1, catL[2], t64[2], act=lre, out_f32=False)
+        self._c(P, 'pod.L3_offset_conv2', am.L3_offset_conv2, t64[2], oa[2], act=lre)
+        am.L3_dcnpack.run_acts(P, 'pod.L3_dcn', nbr_f32(2), gL[2], oa[2], fe[2], P.err, act=lre, slope=LRELU_SLOPE, out_planes=False)
         self._tap('pod.o3', oa[2]); self._tap('pod.fea3', fe[2])
         # L2 (:117-124)
-        self._c(P, 'L2_offset_conv1', am.L2_offset_conv1, catL[1], cat2[1], act=lre, out_f32=False)
+        self._c(P, 'pod.L2_offset_conv1', am.L2_offset_conv1, catL[1], cat2[1], act=lre, out_f32=False)
         self._up2(oa[2].f32, gL[2], nf, cat2[1], c_off=nf, mul=2.0)
-        self._c(P, 'L2_offset_conv2', am.L2_offset_conv2, cat2[1], t64[1], act=lre, out_f32=False)
-        self._c(P, 'L2_offset_conv3', am.L2_offset_conv3, t64[1], oa[1], act=lre)
-        am.L2_dcnpack.run_acts(P, 'L2_dcn', nbr_f32(1), gL[1], oa[1], cat2[1], P.err, out_f32=False)
+        self._c(P, 'pod.L2_offset_conv2', am.L2_offset_conv2, cat2[1], t64[1], act=lre, out_f32=False)
+        self._c(P, 'pod.L2_offset_conv3', am.L2_offset_conv3, t64[1], oa[1], act=lre)
+        am.L2_dcnpack.run_acts(P, 'pod.L2_dcn', nbr_f32(1), gL[1], oa[1], cat2[1], P.err, out_f32=False)
         self._up2(fe[2].f32, gL[2], nf, cat2[1], c_off=nf)
-        self._c(P, 'L2_fea_conv', am.L2_fea_conv, cat2[1], fe[1], act=lre, out_planes=False)
+        self._c(P, 'pod.L2_fea_conv', am.L2_fea_conv, cat2[1], fe[1], act=lre, out_planes=False)
         self._tap('pod.o2', oa[1]); self._tap('pod.fea2', fe[1])
         # L1 (:126-133)
-        self._c(P, 'L1_offset_conv1', am.L1_offset_conv1, catL[0], cat2[0], act=lre, out_f32=False)
+        self._c(P, 'pod.L1_offset_conv1', am.L1_offset_conv1, catL[0], cat2[0], act=lre, out_f32=False)
         self._up2(oa[1].f32, gL[1], nf, cat2[0], c_off=nf, mul=2.0)
-        self._c(P, 'L1_offset_conv2', am.L1_offset_conv2, cat2[0], t64[0], act=lre, out_f32=False)
-        self._c(P, 'L1_offset_conv3', am.L1_offset_conv3, t64[0], oa[0], act=lre)
-        am.L1_dcnpack.run_acts(P, 'L1_dcn', nbr_f32(0), gL[0], oa[0], cat2[0], P.err, out_f32=False)
+        self._c(P, 'pod.L1_offset_conv2', am.L1_offset_conv2, cat2[0], t64[0], act=lre, out_f32=False)
+        self._c(P, 'pod.L1_offset_conv3', am.L1_offset_conv3, t64[0], oa[0], act=lre)
+        am.L1_dcnpack.run_acts(P, 'pod.L1_dcn', nbr_f32(0), gL[0], oa[0], cat2[0], P.err, out_f32=False)
         self._up2(fe[1].f32, gL[1], nf, cat2[0], c_off=nf)
         catC = P.act('catC', gL[0], 2 * nf, f32=True)            # [L1_fea | centre features] (:135)
-        self._c(P, 'L1_fea_conv', am.L1_fea_conv, cat2[0], catC)
+        self._c(P, 'pod.L1_fea_conv', am.L1_fea_conv, cat2[0], catC)
         self._tap('pod.o1', oa[0]); self._tap('pod.fea1', catC, nf)
         # cascading (:135-138)
         self._copy(catL[0], 64, nf, catC, 64)
-        self._c(P, 'cas_offset_conv1', am.cas_offset_conv1, catC, t64[0], act=lre, out_f32=False)
-        self._c(P, 'cas_offset_conv2', am.cas_offset_conv2, t64[0], oa[0], act=lre)
+        self._c(P, 'pod.cas_offset_conv1', am.cas_offset_conv1, catC, t64[0], act=lre, out_f32=False)
+        self._c(P, 'pod.cas_offset_conv2', am.cas_offset_conv2, t64[0], oa[0], act=lre)
         self._tap('pod.off', oa[0])
-        am.cas_dcnpack.run_acts(P, 'cas_dcn', catC.f32, gL[0], oa[0], fe[0], P.err, act=lre, slope=LRELU_SLOPE)
+        am.cas_dcnpack.run_acts(P, 'pod.cas_dcn', catC.f32, gL[0], oa[0], fe[0], P.err, act=lre, slope=LRELU_SLOPE)
         return fe[0]
 
     # ------------------------------------------------------------------ ThreeDA.forward (:181-234)
@@ -502,11 +505,11 @@ class GPEMSR(SRTail):
             def build(c3=c3):                                    # Conv3d(t, t, k=1) over [b, t, c, h, w] = 1x1 conv with W (x) I_c
                 w = c3.weight.detach().reshape(N, N).float()
                 eye = torch.eye(nf, device=w.device)
-                wt = G.Weights(torch.kron(w, eye).reshape(N * nf, N * nf, 1, 1).contiguous(), 'conv', split=P.split)
+                wt = G.Weights(torch.kron(w, eye).reshape(N * nf, N * nf, 1, 1).contiguous(), 'conv', split=P.sp(kname))
                 wt.bias_k = c3.bias.detach().float().repeat_interleave(nf).contiguous()
                 return wt
             k3 = P.derived(kname, (c3.weight, c3.bias), build)
-            G.igemm(al, k3, P.err, split=P.split, bias=k3.bias_k, act=lre, slope=LRELU_SLOPE, out=t3d, out_f32=False)
+            G.igemm(al, k3, P.err, split=P.sp(kname), bias=k3.bias_k, act=lre, slope=LRELU_SLOPE, out=t3d, out_f32=False)
             if i == 0:                                           # feat = feat + fea_3d1 (:211): the residual epilogue
                 self._c(P, f'tda.c3dfus{i}', cf, t3d, feat, act=lre, residual=feat0.f32)
                 f3.append(None)

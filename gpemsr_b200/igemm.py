@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_EXP = 0, 1, 2, 3
 
 
 class GeomC(C.Structure):
@@ -36,7 +36,8 @@ class IgemmDesc(C.Structure):
                 ('out_rowmajor', C.c_void_p), ('ld', C.c_int64),
                 ('gn_sums', C.c_void_p), ('gn_cpg', C.c_int32),
                 ('patch_other', C.c_void_p), ('patch_sums', C.c_void_p), ('patch_size', C.c_int32),
-                ('err_flag', C.c_void_p)]
+                ('err_flag', C.c_void_p),
+                ('row_max_out', C.c_void_p), ('row_max', C.c_void_p), ('row_sum', C.c_void_p), ('row_div', C.c_void_p)]
 
 
 def _round_up(v, m):
@@ -52,6 +53,43 @@ def cached(cache, name, params, build):
     if ent is None or ent[0] != key:
         ent = cache[name] = (key, build())
     return ent[1]
+
+
+class Precision:
+    """Which arithmetic every GEMM launch runs: 3 = the fp32-faithful split (hi*hi + lo*hi + hi*lo on the bf16 tensor pipe),
+    1 = one bf16 pass.  spec: 'fp32' (3 everywhere) | 'bf16' (1 everywhere) | {layer-name prefix: 1 | 3, 'default': 3}
+    (longest matching prefix wins; layer names are the plan keys of the host mirrors, e.g. 'tail.up', 'vgg', 'tda.')."""
+
+    def __init__(self, spec='fp32'):
+        if isinstance(spec, Precision):
+            self.table, self.default = dict(spec.table), spec.default
+        elif isinstance(spec, dict):
+            self.table = {k: int(v) for k, v in spec.items() if k != 'default'}
+            self.default = int(spec.get('default', 3))
+        elif spec in ('fp32', 'bf16'):
+            self.table, self.default = {}, 3 if spec == 'fp32' else 1
+        else:
+            raise ValueError(f'precision must be "fp32", "bf16" or a {{prefix: split}} dict, got {spec!r}')
+        if any(v not in (1, 3) for v in list(self.table.values()) + [self.default]):
+            raise ValueError('precision: splits are 1 (one bf16 pass) or 3 (fp32-faithful)')
+
+    def split(self, name):
+        best, val = -1, self.default
+        for k, v in self.table.items():
+            if name.startswith(k) and len(k) > best:
+                best, val = len(k), v
+        return val
+
+    def planes(self):
+        """3 when any launch may need the lo planes of the activations, else 1."""
+        return 3 if self.default == 3 or 3 in self.table.values() else 1
+
+    def sub(self, prefix):
+        """The precision of a sub-module whose layer names live under `prefix` + '.' in this table."""
+        pre = prefix + '.'
+        t = {k[len(pre):]: v for k, v in self.table.items() if k.startswith(pre)}
+        t['default'] = self.split(prefix)
+        return Precision(t)
 
 
 # ---- the device-side pipeline error flag (every mbarrier wait is bounded; a time-out sets it and the kernel drains)
@@ -345,7 +383,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
           residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, phase_cols=0, c_off=0,
           out_f32=True, out_planes=True, out_nchw=None, nchw_c=0, out_rowmajor=None, ld=0,
           b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None, gn_sums=None, gn_cpg=0,
-          patch_other=None, patch_sums=None, patch_size=0):
+          patch_other=None, patch_sums=None, patch_size=0, row_max_out=None, row_max=None, row_sum=None, row_div=None):
     """One fused implicit-GEMM launch.  `a`: Act (A operand); `w`: Weights or None when b_* are given explicitly;
     `out`: Act receiving fp32 master / planes (whichever it owns and the flags allow)."""
     d = IgemmDesc()
@@ -379,6 +417,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
     d.gn_sums, d.gn_cpg = _p(gn_sums), gn_cpg
     d.patch_other, d.patch_sums, d.patch_size = _p(patch_other), _p(patch_sums), patch_size
     d.err_flag = _p(err)
+    d.row_max_out, d.row_max, d.row_sum, d.row_div = _p(row_max_out), _p(row_max), _p(row_sum), _p(row_div)
     _lib.check(_lib.lib().gpemsr_igemm(C.byref(d), _lib.stream_ptr()))
 
 

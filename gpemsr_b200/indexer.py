@@ -84,7 +84,7 @@ class _Indexer(_BlockNet):
         g = cur.geom
         feat = torch.empty(g.n, self.latent_dim, g.h, g.w, dtype=torch.float32, device=x.device)
         last = self.output_layer[self.num_output_resblck]
-        G.igemm(cur, P.weights('output_layer.last', last.weight, 'conv'), P.err, split=P.split, bias=last.bias.detach(),
+        G.igemm(cur, P.weights('output_layer.last', last.weight, 'conv'), P.err, split=P.sp('output_layer.last'), bias=last.bias.detach(),
                 out_nchw=feat, nchw_c=self.latent_dim)
         G.post_error_check(x.device)
         return feat
@@ -96,13 +96,13 @@ class _Indexer(_BlockNet):
         g = cur.geom
         last = self.output_layer[self.num_output_resblck]
         feat = P.act('output_layer.last.out', g, self.latent_dim, f32=False)
-        G.igemm(cur, P.weights('output_layer.last', last.weight, 'conv'), P.err, split=P.split, bias=last.bias.detach(),
+        G.igemm(cur, P.weights('output_layer.last', last.weight, 'conv'), P.err, split=P.sp('output_layer.last'), bias=last.bias.detach(),
                 out=feat, out_f32=False)
         # the Linear over channels: rows = padded pixel rows, columns = codes; gather the interior rows afterwards
         k = self.embedding.out_features
         rows = g.n * g.r_img
         buf = torch.empty(rows, k, dtype=torch.float32, device=x.device)
-        G.igemm(feat, P.weights('embedding', self.embedding.weight, 'linear'), P.err, split=P.split,
+        G.igemm(feat, P.weights('embedding', self.embedding.weight, 'linear'), P.err, split=P.sp('embedding'),
                 bias=self.embedding.bias.detach(), out_rowmajor=buf, ld=k)
         logits = buf.view(g.n, g.r_img, k)[:, :(g.h + 2) * (g.w + 2)].view(g.n, g.h + 2, g.w + 2, k)[:, 1:-1, 1:-1]
         G.post_error_check(x.device)
@@ -128,8 +128,9 @@ class _LrGenerator(nn.Module):
 
     def __init__(self, args, precision='fp32'):
         super().__init__()
-        self.indexer = self.indexer_cls(args[self.key], precision=precision)
-        self.decoder = Decoder(args['Decoder'], precision=precision)
+        prec = G.Precision(precision)
+        self.indexer = self.indexer_cls(args[self.key], precision=prec.sub('indexer'))
+        self.decoder = Decoder(args['Decoder'], precision=prec.sub('decoder'))
         self.codebook = Codebook(args['Codebook'])
 
     @torch.no_grad()

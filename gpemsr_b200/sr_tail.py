@@ -30,7 +30,7 @@ class SRTail(nn.Module):
         super().__init__()
         assert scale in (8, 16)
         self.nf, self.scale = nf, scale
-        self.precision = precision
+        self.precision = G.Precision(precision)
         self.recon_trunk = nn.Sequential(*[ResidualBlockNoBN(nf) for _ in range(back_RBs)])
         self.upconv1 = nn.Conv2d(nf, nf * 4, 3, 1, 1, bias=True)
         self.upconv2 = nn.Conv2d(nf, 64 * 4, 3, 1, 1, bias=True)
@@ -65,30 +65,29 @@ class SRTail(nn.Module):
     def _tail(self, P, cur, x_center):
         """The tail from an activation already in the internal format (fp32 master + planes): used by ``forward`` and by the
         whole-model mirror ``gpemsr_b200.GPEMSR``."""
-        sp = P.split
         g = cur.geom
         n = g.n
         t = P.act('trunk.t', g, self.nf, f32=False)
         pp = [P.act('trunk.a', g, self.nf, f32=True), P.act('trunk.b', g, self.nf, f32=True)]
         for i, rb in enumerate(self.recon_trunk):          # x + conv2(relu(conv1(x)))
-            G.igemm(cur, P.weights(f'rt{i}.1', rb.conv1.weight, 'conv'), P.err, split=sp, bias=rb.conv1.bias.detach(),
+            G.igemm(cur, P.weights(f'tail.rt{i}.1', rb.conv1.weight, 'conv'), P.err, split=P.sp('tail.rt'), bias=rb.conv1.bias.detach(),
                     act=G.ACT_RELU, out=t, out_f32=False)
             nxt = pp[i % 2]
-            G.igemm(t, P.weights(f'rt{i}.2', rb.conv2.weight, 'conv'), P.err, split=sp, bias=rb.conv2.bias.detach(),
+            G.igemm(t, P.weights(f'tail.rt{i}.2', rb.conv2.weight, 'conv'), P.err, split=P.sp('tail.rt'), bias=rb.conv2.bias.detach(),
                     residual=cur.f32, out=nxt)
             cur = nxt
         ups = [self.upconv1, self.upconv2, self.upconv3] + ([self.upconv4] if self.scale == 16 else [])
         for i, conv in enumerate(ups):                     # lrelu(pixel_shuffle(conv(x)))
             og = G.Geom(n, cur.geom.h * 2, cur.geom.w * 2, True)
             out = P.act(f'up{i}', og, 64, f32=False)
-            G.igemm(cur, P.weights(f'up{i}', conv.weight, 'conv'), P.err, split=sp, bias=conv.bias.detach(), act=G.ACT_LRELU,
+            G.igemm(cur, P.weights(f'tail.up{i}', conv.weight, 'conv'), P.err, split=P.sp(f'tail.up{i}'), bias=conv.bias.detach(), act=G.ACT_LRELU,
                     slope=LRELU_SLOPE, out=out, up=2, pixel_shuffle=True, out_f32=False)
             cur = out
         hr = P.act('hr', cur.geom, 64, f32=False)
-        G.igemm(cur, P.weights('hr', self.HRconv.weight, 'conv'), P.err, split=sp, bias=self.HRconv.bias.detach(),
+        G.igemm(cur, P.weights('tail.hr', self.HRconv.weight, 'conv'), P.err, split=P.sp('tail.hr'), bias=self.HRconv.bias.detach(),
                 act=G.ACT_LRELU, slope=LRELU_SLOPE, out=hr, out_f32=False)
         out = torch.empty(n, 1, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x_center.device)
-        G.igemm(hr, P.weights('last', self.conv_last.weight, 'conv'), P.err, split=sp, bias=self.conv_last.bias.detach(),
+        G.igemm(hr, P.weights('tail.last', self.conv_last.weight, 'conv'), P.err, split=P.sp('tail.last'), bias=self.conv_last.bias.detach(),
                 out_nchw=out, nchw_c=1)
         G.add_bilinear_base(x_center.float(), self.scale, out)
         self._last_plan = P

@@ -56,6 +56,7 @@ extern "C" {
 #define GPEMSR_ACT_NONE    0
 #define GPEMSR_ACT_RELU    1
 #define GPEMSR_ACT_LRELU   2   /* slope passed separately */
+#define GPEMSR_ACT_EXP     3   /* exp(v - row_max[row]): the softmax numerator, see gpemsr_igemm_desc_t.row_max */
 
 typedef void* gpemsr_stream_t;
 
@@ -160,6 +161,17 @@ typedef struct gpemsr_igemm_desc {
                                                and over all n_cols channels, (sum v*o, sum v*v, sum o*o) of the stored values v;
                                                zeroed by the call; needs up == 1 and h, w divisible by patch_size */
   int32_t* err_flag;                        /* device int: set when the pipeline times out (never hangs) */
+  /* softmax fused into the attention GEMMs (model/blocks.py:74-79; rows = queries, columns = keys; the rows of a launch are
+   * indexed from 0 at a_geom.m0).  Three launches replace bmm -> scale -> softmax -> bmm without a fp32 score matrix:
+   *   1. pre-pass (split 1): row_max_out[row] = max over the valid columns of v           (nothing else is stored)
+   *   2. scores:  act = GPEMSR_ACT_EXP, row_max = that buffer, row_sum: v = exp(v - row_max[row]) is stored as operand planes
+   *      (the unnormalised probabilities, zero beyond n_cols) and summed per row into row_sum[row]
+   *   3. P v^T:   row_div = that buffer: v = acc / row_div[row]
+   * row_max_out / row_sum are initialised by the call. */
+  float* row_max_out;
+  const float* row_max;
+  float* row_sum;
+  const float* row_div;
 } gpemsr_igemm_desc_t;
 
 GPEMSR_API int gpemsr_igemm(const gpemsr_igemm_desc_t* desc, gpemsr_stream_t stream);
