@@ -356,9 +356,12 @@ def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
 
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    # halo: the 2 boundary slices' features come from the neighbour ranks (GPEMSR_HALO=recompute: encoded again locally, round 1)
+    exchange = world > 1 and os.environ.get('GPEMSR_HALO', 'exchange') == 'exchange'
+
     def one_pass():
         vol = vol_host.to(dev, non_blocking=True)
-        model.forward_volume(vol, lo, hi, out=out_dev)
+        model.forward_volume(vol, lo, hi, out=out_dev, halo_exchange=(dist, rank, world) if exchange else None)
         g0.record()
         if world > 1:
             gather_slices(out_dev, n_slices, world, rank, dist)
@@ -381,9 +384,10 @@ def volume_bench(dev, rank, world, dist, passes=2, n_slices=VOL_SLICES):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / passes
-    halo = (min(hi + NFRAMES // 2, n_slices) - max(lo - NFRAMES // 2, 0)) - (hi - lo)
+    halo = 0 if exchange else (min(hi + NFRAMES // 2, n_slices) - max(lo - NFRAMES // 2, 0)) - (hi - lo)
     return {'value': n_slices * hr * hr / 1e6 / (ms / 1e3), 'unit': UNIT, 'ms_per_volume': ms, 'ms_per_slice': ms / n_slices * world,
-            'slices_rank0': hi - lo, 'halo_slices_encoded_rank0': halo, 'gather_ms_rank0': g0.elapsed_time(g1) if world > 1 else 0.0,
+            'slices_rank0': hi - lo, 'halo_slices_encoded_rank0': halo,
+            'halo': 'exchanged with the neighbour ranks (P2P, 17 MB of features per slice)' if exchange else 'recomputed locally' if world > 1 else 'none', 'gather_ms_rank0': g0.elapsed_time(g1) if world > 1 else 0.0,
             'workload': f'{n_slices} slices x{VOL_SCALE}, {VOL_LR}^2 LR -> {hr}^2 HR, windows of output_GPEMSR.py:54-128, every slice '
                         f'encoded once (per-frame cache), slice blocks over {world} GPU(s), HR slices all-gathered',
             'h2d_bytes': vol_host.numel() * 4, 'd2h_bytes': out_host.numel() * 4, 'scaling': 'strong',
@@ -422,7 +426,9 @@ def config_block(world, lr=LR):
                         f'{NFRAMES}-slice window {LR}x{LR} LR -> {SCALE * LR}x{SCALE * LR} HR, random-init weights' + crop,
             'lr': lr, 'cpu_crop': lr != LR, 'n_frames': NFRAMES, 'scale': SCALE, 'units_per_step': 'one output slice per GPU',
             'parallelism': f'slice-sharded x{world}, outputs all-gathered', 'l2': 'working set per step (>2 GB of activations) '
-            'exceeds the 126 MB L2; no explicit flush', 'precision': 'bf16 x3 split (fp32-faithful) on tcgen05'}
+            'exceeds the 126 MB L2; no explicit flush',
+            'precision': 'default precision plan (gpemsr_b200.gpemsr.DEFAULT_PLAN, profiles/r02_precision_plan.json): bf16 x3 split '
+                         '(fp32-faithful) on tcgen05 everywhere except the VGG similarity branch and SpyNet (one bf16 pass)'}
 
 
 def main():

@@ -63,6 +63,7 @@ SIGNATURES = {
     'gpemsr_cells_copy': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
     'gpemsr_temporal_attn_scale': (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     'gpemsr_threeda_combine': (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    'gpemsr_tap_gather_sum': (_i, [_p, _p, _i, _i, _i, _p, _i, _f, _p, _i, _i, _i, _p, _p]),
     'gpemsr_conv3x3_direct': (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     'gpemsr_selftest_gemm_workspace_bytes': (_sz, [_i64, _i, _i]),
     'gpemsr_selftest_gemm': (_i, [_p, _p, _i64, _i, _i, _i, _i, _p, _p, _sz, _p]),

@@ -35,6 +35,7 @@ struct EpiConv {
   int pair_off;               // > 0: the accumulator is split over two column ranges (c, c + pair_off): the paired-N MMAs of the
                               // tap-fused / dy-fused kernels keep a_hi * w_lo apart from a_hi * w_hi + a_lo * w_hi; summed here
   const float* patch_other;   // fp32 cells in the output geometry: the tensor the stored values are correlated with
+  int patch_other_bf16;       // 1: patch_other points at bf16 cells (the hi plane of that tensor) instead
   float* patch_sums;          // [n][h / patch][w / patch][3] = (sum v*o, sum v*v, sum o*o) per patch x patch block of pixels
   int patch_size;
   // softmax fused into the attention GEMMs (model/blocks.py:74-79): rows = queries, columns = keys
@@ -179,9 +180,17 @@ struct EpiConv {
       for (int g = 0; g < CHUNK / 8; ++g) {
         if (col0 + 8 * g >= n_cols) break;
         const size_t cell = ((size_t)((c_off + col0 + 8 * g) >> 3) * og.rows_alloc + st.orow) * 8;
-        const float4 o0 = __ldg(reinterpret_cast<const float4*>(patch_other + cell));
-        const float4 o1 = __ldg(reinterpret_cast<const float4*>(patch_other + cell + 4));
-        const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        float o[8];
+        if (patch_other_bf16) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(patch_other) + cell));
+          const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { o[2 * j] = __uint_as_float(w4[j] << 16); o[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u); }
+        } else {
+          const float4 o0 = __ldg(reinterpret_cast<const float4*>(patch_other + cell));
+          const float4 o1 = __ldg(reinterpret_cast<const float4*>(patch_other + cell + 4));
+          o[0] = o0.x; o[1] = o0.y; o[2] = o0.z; o[3] = o0.w; o[4] = o1.x; o[5] = o1.y; o[6] = o1.z; o[7] = o1.w;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float a = f[8 * g + j];
@@ -319,7 +328,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
-  e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   e.pair_off = 0;
   const int sms = gpemsr::num_sms();
@@ -368,7 +377,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
-  e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
@@ -411,7 +420,7 @@ int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t
   e.out_f32 = d.out_f32; e.out_hi = (__nv_bfloat16*)d.out_hi; e.out_lo = (__nv_bfloat16*)d.out_lo;
   e.out_nchw = d.out_nchw; e.nchw_c = d.nchw_c; e.out_rowmajor = d.out_rowmajor; e.ld = d.ld;
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
-  e.patch_other = d.patch_other; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
+  e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_dyfuse_kernel<BLOCK_N, SPLIT, Epi>;

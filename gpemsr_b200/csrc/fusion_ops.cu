@@ -206,6 +206,58 @@ __global__ void conv3x3_direct_kernel(const float* __restrict__ x, int n, int ci
 
 inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
+
+// 3x3 convolutions with very few output channels (conv_last 64 -> 1, refmaskconv3 64 -> 1, the composed last decoder stage
+// 64 -> 4 phases): on the tensor pipe an M = 128 MMA costs the same ~60 cycles for N = 16 as for N = 64, and the nine taps make
+// it nine of them per k-step -- 1.4 % of peak.  Instead the nine taps become nine OUTPUT COLUMNS of ONE 1x1 GEMM
+//     D[row, tap * n_out + o] = sum_c x[row, c] * w[o, c, tap]          (gpemsr_igemm, fp32 cells; ring rows stay zero)
+// and this kernel finishes the convolution with a nine-point shifted sum on CUDA cores:
+//     out[o](y, x) = act(bias[o] + sum_tap D[(y + dy_tap, x + dx_tap), tap * n_out + o])   (+ the bilinear base image, :452-455)
+// up == 2: column o = phase * co + ch is channel ch of output pixel (2y + phase / 2, 2x + phase % 2) (the composed up-block).
+__global__ void tap_gather_sum_kernel(const float* __restrict__ d, Geom g, int n_out, int up, int co, const float* __restrict__ bias,
+                                      int act, float slope, const float* __restrict__ base, int bh, int bw, int bscale,
+                                      float* __restrict__ out) {
+  const long long hw = (long long)g.h * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)g.n * hw) return;
+  const int img = (int)(t / hw), y = (int)((t % hw) / g.w), x = (int)(t % g.w);
+  const long long row = place_row(g, img, y, x);
+  const int wp = g.wp();
+  float acc[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = (bias && o < n_out) ? __ldg(bias + o) : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const long long r = row + (long long)(tap / 3 - 1) * wp + (tap % 3 - 1);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (o < n_out) {
+        const int col = tap * n_out + o;
+        acc[o] += __ldg(d + ((size_t)(col >> 3) * g.rows_alloc + r) * 8 + (col & 7));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = apply_act(acc[o], act, slope);
+  if (up == 1) {
+    float b = 0.f;
+    if (base) {                                  // ATen upsample_bilinear2d(x_center, scale_factor, align_corners=False)
+      const float rs = 1.0f / (float)bscale;
+      const Lerp ly = lerp_src(y, rs, bh), lx = lerp_src(x, rs, bw);
+      const float* p = base + (long long)img * bh * bw;
+      b = ly.l0 * (lx.l0 * __ldg(p + (long long)ly.i0 * bw + lx.i0) + lx.l1 * __ldg(p + (long long)ly.i0 * bw + lx.i1)) +
+          ly.l1 * (lx.l0 * __ldg(p + (long long)ly.i1 * bw + lx.i0) + lx.l1 * __ldg(p + (long long)ly.i1 * bw + lx.i1));
+    }
+    for (int o = 0; o < n_out; ++o) out[((long long)img * n_out + o) * hw + (long long)y * g.w + x] = acc[o] + b;
+  } else {
+    const long long Wo = 2LL * g.w, plane = 4 * hw;
+    for (int o = 0; o < n_out; ++o) {
+      const int ph = o / co, ch = o - ph * co;
+      out[((long long)img * co + ch) * plane + (long long)(2 * y + (ph >> 1)) * Wo + 2 * x + (ph & 1)] = acc[o];
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -325,6 +377,23 @@ int gpemsr_conv3x3_direct(const float* x, int n, int cin, int h, int w, const fl
   const long long total = (long long)n * cout * ho * wo;
   conv3x3_direct_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(x, n, cin, h, w, wgt, bias, cout, stride, ho, wo, out);
   GPEMSR_LAUNCH_OK("conv3x3_direct_kernel");
+  return GPEMSR_OK;
+}
+
+int gpemsr_tap_gather_sum(const float* taps_f32, const gpemsr_geom_t* g, int n_out, int up, int co, const float* bias,
+                          int act, float slope, const float* base, int base_h, int base_w, int base_scale, float* out_nchw, gpemsr_stream_t stream) {
+  using namespace gpemsr;
+  int rc = check_device_current();
+  if (rc != GPEMSR_OK) return rc;
+  if (!taps_f32 || !g || !out_nchw || n_out < 1 || n_out > 4 || (up != 1 && up != 2) || !g->padded ||
+      (up == 2 && (co < 1 || n_out != 4 * co || base)) || (base && (base_h * base_scale != g->h || base_w * base_scale != g->w)))
+    return set_error(GPEMSR_ERR_BAD_SHAPE, "tap_gather_sum: n_out in 1..4 on a ringed geometry; up = 2 needs n_out == 4 * co; the base image "
+                     "must be (h / scale) x (w / scale)");
+  if ((rc = check_geom(*g, "tap_gather_sum")) != GPEMSR_OK) return rc;
+  const long long total = (long long)g->n * g->h * g->w;
+  tap_gather_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(taps_f32, to_geom(*g), n_out, up, co, bias, act, slope, base,
+                                                                                         base_h, base_w, base_scale, out_nchw);
+  GPEMSR_LAUNCH_OK("tap_gather_sum_kernel");
   return GPEMSR_OK;
 }
 

@@ -300,10 +300,18 @@ class Decoder(_BlockNet):
             wc, bias = G.compose_upblock_conv(ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias)
             dev = ub.upblock.weight.device
             w_int = wc[4].reshape(4 * co, wc.shape[3], 3, 3).contiguous().to(dev)          # phase-major output channels
-            return dict(wt=G.Weights(w_int, 'conv', split=P.sp('final')), b_int=bias[4].repeat(4).contiguous().to(dev),
-                        wc=wc.contiguous().to(dev), bias=bias.contiguous().to(dev))
+            few = 4 * co <= 4            # nine taps as GEMM columns + a nine-point sum instead of nine N = 16 tensor-pipe tiles
+            return dict(wt=G.Weights(G.taps_as_columns(w_int) if few else w_int, 'conv', split=P.sp('final')), few=few,
+                        b_int=bias[4].repeat(4).contiguous().to(dev), wc=wc.contiguous().to(dev), bias=bias.contiguous().to(dev))
         st = P.derived('final', (ub.upblock.weight, ub.upblock.bias, self.output_layer.weight, self.output_layer.bias), build)
-        G.igemm(x, st['wt'], P.err, split=P.sp('final'), bias=st['b_int'], up=2, phase_cols=co, out_nchw=img, nchw_c=co)
+        if st['few']:
+            key = f'final.taps{x.geom.key()}'
+            taps = P.bufs.get(key)
+            if taps is None:
+                taps = P.bufs[key] = G.TapCells(x.geom, 4 * co, P.device)
+            G.conv3x3_few_outputs(x, st['wt'], taps, P.err, P.sp('final'), st['b_int'], img, 4 * co, up=2, co=co)
+        else:
+            G.igemm(x, st['wt'], P.err, split=P.sp('final'), bias=st['b_int'], up=2, phase_cols=co, out_nchw=img, nchw_c=co)
         G.border_phase_conv(x, st['wc'], st['bias'], co, img)
 
     # ------------------------------------------------------------------ reference API

@@ -37,7 +37,8 @@ class IgemmDesc(C.Structure):
                 ('gn_sums', C.c_void_p), ('gn_cpg', C.c_int32),
                 ('patch_other', C.c_void_p), ('patch_sums', C.c_void_p), ('patch_size', C.c_int32),
                 ('err_flag', C.c_void_p),
-                ('row_max_out', C.c_void_p), ('row_max', C.c_void_p), ('row_sum', C.c_void_p), ('row_div', C.c_void_p)]
+                ('row_max_out', C.c_void_p), ('row_max', C.c_void_p), ('row_sum', C.c_void_p), ('row_div', C.c_void_p),
+                ('patch_other_bf16', C.c_int32)]
 
 
 def _round_up(v, m):
@@ -383,7 +384,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
           residual=None, out=None, a_geom=None, o_geom=None, up=1, py=0, px=0, pixel_shuffle=False, phase_cols=0, c_off=0,
           out_f32=True, out_planes=True, out_nchw=None, nchw_c=0, out_rowmajor=None, ld=0,
           b_hi=None, b_lo=None, b_rows=None, k_pad=None, taps=None, gn_sums=None, gn_cpg=0,
-          patch_other=None, patch_sums=None, patch_size=0, row_max_out=None, row_max=None, row_sum=None, row_div=None):
+          patch_other=None, patch_sums=None, patch_size=0, row_max_out=None, row_max=None, row_sum=None, row_div=None, patch_other_bf16=False):
     """One fused implicit-GEMM launch.  `a`: Act (A operand); `w`: Weights or None when b_* are given explicitly;
     `out`: Act receiving fp32 master / planes (whichever it owns and the flags allow)."""
     d = IgemmDesc()
@@ -415,7 +416,7 @@ def igemm(a, w, err, *, n_cols=None, split=3, scale=1.0, bias=None, bias_per_row
     d.out_nchw, d.nchw_c = _p(out_nchw), nchw_c
     d.out_rowmajor, d.ld = _p(out_rowmajor), ld
     d.gn_sums, d.gn_cpg = _p(gn_sums), gn_cpg
-    d.patch_other, d.patch_sums, d.patch_size = _p(patch_other), _p(patch_sums), patch_size
+    d.patch_other, d.patch_sums, d.patch_size, d.patch_other_bf16 = _p(patch_other), _p(patch_sums), patch_size, int(patch_other_bf16)
     d.err_flag = _p(err)
     d.row_max_out, d.row_max, d.row_sum, d.row_div = _p(row_max_out), _p(row_max), _p(row_sum), _p(row_div)
     _lib.check(_lib.lib().gpemsr_igemm(C.byref(d), _lib.stream_ptr()))
@@ -489,6 +490,34 @@ def group_norm_act(x, gamma, beta, scratch, out, act=ACT_NONE, slope=0.0, residu
 def softmax_cells_blocked(s_cells, t, rows_alloc, t_pad, scratch, p_hi, p_lo):
     _lib.check(_lib.lib().gpemsr_softmax_cells_blocked(_lib.ptr(s_cells), t, rows_alloc, t_pad, _lib.ptr(scratch), _lib.ptr(p_hi),
                                                        _lib.ptr(p_lo), _lib.stream_ptr()))
+
+
+def taps_as_columns(w):
+    """Conv2d weight [n_out, ci, 3, 3] -> the 1x1 weight [9 * n_out, ci, 1, 1] whose column tap * n_out + o is tap (ky, kx) of
+    output o (tap = ky * 3 + kx): the GEMM half of ``conv3x3_few_outputs``."""
+    n_out, ci = w.shape[0], w.shape[1]
+    return w.detach().float().permute(2, 3, 0, 1).reshape(9 * n_out, ci, 1, 1).contiguous()
+
+
+class TapCells:
+    """fp32 cells [ceil(9 * n_out / 8)][rows_alloc][8] receiving the per-tap partial products (zero ring: never written)."""
+
+    def __init__(self, geom, n_out, device):
+        self.geom, self.c = geom, 9 * n_out
+        self.f32 = torch.zeros((self.c + 7) // 8, geom.rows_alloc, 8, dtype=torch.float32, device=device)
+        self.hi = self.lo = None
+
+
+def conv3x3_few_outputs(x, wt, taps, err, split, bias, out_nchw, n_out, up=1, co=0, act=ACT_NONE, slope=0.0, base=None,
+                        base_scale=1):
+    """3x3 convolution with <= 4 output columns: ONE 1x1 GEMM producing the nine per-tap partial products as fp32 cells of
+    `taps` (a TapCells), then the nine-point shifted sum (+ bias, activation, + bilinear base image) on CUDA cores.
+    wt = Weights(taps_as_columns(w), 'conv')."""
+    igemm(x, wt, err, split=split, out=taps, out_planes=False)
+    g = x.geom.c
+    bh, bw = (base.shape[2], base.shape[3]) if base is not None else (0, 0)
+    _lib.check(_lib.lib().gpemsr_tap_gather_sum(_lib.ptr(taps.f32), C.byref(g), n_out, up, co, _lib.ptr(bias), act, slope,
+                                                _lib.ptr(base), bh, bw, base_scale, _lib.ptr(out_nchw), _lib.stream_ptr()))
 
 
 def add_bilinear_base(x_center, scale, out):

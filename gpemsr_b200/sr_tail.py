@@ -87,9 +87,16 @@ class SRTail(nn.Module):
         G.igemm(cur, P.weights('tail.hr', self.HRconv.weight, 'conv'), P.err, split=P.sp('tail.hr'), bias=self.HRconv.bias.detach(),
                 act=G.ACT_LRELU, slope=LRELU_SLOPE, out=hr, out_f32=False)
         out = torch.empty(n, 1, cur.geom.h, cur.geom.w, dtype=torch.float32, device=x_center.device)
-        G.igemm(hr, P.weights('tail.last', self.conv_last.weight, 'conv'), P.err, split=P.sp('tail.last'), bias=self.conv_last.bias.detach(),
-                out_nchw=out, nchw_c=1)
-        G.add_bilinear_base(x_center.float(), self.scale, out)
+        # conv_last (64 -> 1) + the bilinear base image (:450-455): nine taps as the columns of one 1x1 GEMM, then a nine-point
+        # shifted sum on CUDA cores (an N = 16 tensor-pipe tile per tap ran at 1.4 % of peak)
+        sp = P.sp('tail.last')
+        wt = P.derived('tail.last', (self.conv_last.weight,), lambda: G.Weights(G.taps_as_columns(self.conv_last.weight), 'conv', split=sp))
+        key = f'tail.last.taps{cur.geom.key()}'
+        taps = P.bufs.get(key)
+        if taps is None:
+            taps = P.bufs[key] = G.TapCells(cur.geom, 1, x_center.device)
+        G.conv3x3_few_outputs(hr, wt, taps, P.err, sp, self.conv_last.bias.detach(), out, 1, base=x_center.float().contiguous(),
+                              base_scale=self.scale)
         self._last_plan = P
         return out
 

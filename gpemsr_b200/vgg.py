@@ -53,8 +53,10 @@ class VGG19Slice1(nn.Module):
         P = self._plans.get(key)
         if P is None:
             g = G.Geom(n, h, w, True)
-            P = dict(g=g, c1=G.Act(g, 64, device, f32=False, split=self.split), ref=G.Act(g, 64, device, f32=True, planes=False),
-                     err=G.err_flag(device), wts={})
+            # fp32-faithful: the first image's features are kept as fp32 cells; one-pass bf16: as a bf16 plane (what the bf16
+            # branch resolves anyway) -- half the bytes of the largest tensor of the forward, written once and read once
+            P = dict(g=g, c1=G.Act(g, 64, device, f32=False, split=self.split),
+                     ref=G.Act(g, 64, device, f32=self.split == 3, planes=self.split == 1, split=1), err=G.err_flag(device), wts={})
             self._plans[key] = P
         c0, c2 = self.slice1[0], self.slice1[2]                      # packed forms follow the live parameters (igemm.cached)
         # the 3 input channels are copies of one image: their weights are summed
@@ -96,13 +98,14 @@ class VGG19Slice1(nn.Module):
         P = self._plan(n, h, w, ref_img.device)
         b2 = self.slice1[2].bias.detach()
         G.igemm(self._conv1(P, ref_img), P['w2'], P['err'], split=self.split, bias=b2, act=G.ACT_RELU, out=P['ref'],
-                out_planes=False)
+                out_planes=self.split == 1, out_f32=self.split == 3)
         npatch = n * (h // ksize) * (w // ksize)
         sums = P.get('sums')
         if sums is None:
             sums = P['sums'] = torch.empty(npatch, 3, dtype=torch.float32, device=ref_img.device)
         G.igemm(self._conv1(P, other_img), P['w2'], P['err'], split=self.split, bias=b2, act=G.ACT_RELU, o_geom=P['g'],
-                patch_other=P['ref'].f32, patch_sums=sums, patch_size=ksize)
+                patch_other=P['ref'].f32 if self.split == 3 else P['ref'].hi, patch_other_bf16=self.split == 1, patch_sums=sums,
+                patch_size=ksize)
         mask = torch.empty(n, 1, h // ksize, w // ksize, dtype=torch.float32, device=ref_img.device)
         _lib.check(_lib.lib().gpemsr_patch_cosine(_lib.ptr(sums), npatch, 1e-12, _lib.ptr(mask), _lib.stream_ptr()))
         self._last_err = P['err']

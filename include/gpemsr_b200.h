@@ -154,7 +154,7 @@ typedef struct gpemsr_igemm_desc {
   double* gn_sums; int32_t gn_cpg;          /* optional fused GroupNorm statistics of the stored values: [n][n_cols/gn_cpg][2]
                                                doubles (sum, sum of squares per image and group of gn_cpg channels), zeroed by
                                                the call; gn_cpg in {1,2,4,8,16,32} */
-  const float* patch_other; float* patch_sums; int32_t patch_size;
+  const void* patch_other; float* patch_sums; int32_t patch_size;
                                             /* optional fused patch correlation (the VGG relu1_2 similarity mask,
                                                model/GPEMSR.py:345-353): patch_other = fp32 cells of a second tensor in the
                                                output geometry; patch_sums [n][h/ps][w/ps][3] receives, per ps x ps pixel block
@@ -172,6 +172,8 @@ typedef struct gpemsr_igemm_desc {
   const float* row_max;
   float* row_sum;
   const float* row_div;
+  int32_t patch_other_bf16;                 /* 1: patch_other points at bf16 cells (the hi operand plane of the second tensor: what a
+                                               one-pass bf16 branch keeps of it anyway) instead of fp32 cells */
 } gpemsr_igemm_desc_t;
 
 GPEMSR_API int gpemsr_igemm(const gpemsr_igemm_desc_t* desc, gpemsr_stream_t stream);
@@ -298,6 +300,16 @@ GPEMSR_API int gpemsr_threeda_combine(const float* feat, const float* attn, cons
                            gpemsr_stream_t stream);
 GPEMSR_API int gpemsr_conv3x3_direct(const float* x, int n, int cin, int h, int w, const float* wgt, const float* bias, int cout,
                           int stride, float* out, gpemsr_stream_t stream);
+
+/* 3x3 convolutions with <= 4 output columns (model/GPEMSR.py:450 conv_last, :356 refmaskconv3, the composed last stage of
+ * model/decoder.py:31,33) as ONE 1x1 GEMM whose columns are the nine taps (gpemsr_igemm writing fp32 cells, column
+ * tap * n_out + o, tap = ky * 3 + kx) followed by this nine-point shifted sum on CUDA cores:
+ *   out[o](y, x) = act(bias[o] + sum_tap taps[(y + ky - 1, x + kx - 1), tap * n_out + o])  (+ bilinear x`base_scale` of `base` [n, 1, h/s, w/s],
+ *   align_corners=False: the base image of :452-455).  up == 2: column o = phase * co + ch is channel ch of output pixel
+ *   (2y + phase / 2, 2x + phase % 2), out_nchw [n, co, 2h, 2w]; up == 1: out_nchw [n, n_out, h, w]. */
+GPEMSR_API int gpemsr_tap_gather_sum(const float* taps_f32, const gpemsr_geom_t* g, int n_out, int up, int co, const float* bias,
+                          int act, float slope, const float* base, int base_h, int base_w, int base_scale, float* out_nchw, gpemsr_stream_t stream);
+
 
 /* ---- self-test of the tcgen05 GEMM core (used by tests/, not by the product path) ------
  * D[m,n] = A[m,k] * B[n,k]^T, fp32 row-major; split = 1 (single bf16 pass) or 3 (hi/lo bf16,

@@ -21,10 +21,11 @@ def network_kwargs(scale, nframes=5):
                 align_mode='POD', fusion_mode='ThreeDA', mode='16to1' if scale == 16 else '8to1', scale=scale)
 
 
-def build(scale, seed=None, device=None, nframes=5):
-    """(mirror module with the fixture's synthetic parameters loaded, the same parameters as a CPU state dict)."""
+def build(scale, seed=None, device=None, nframes=5, precision='plan'):
+    """(mirror module with the fixture's synthetic parameters loaded, the same parameters as a CPU state dict).
+    precision: 'plan' = the default precision plan (what a user gets), 'fp32' = every GEMM in the fp32-faithful split."""
     import gpemsr_b200
-    m = gpemsr_b200.GPEMSR(None, None, **network_kwargs(scale, nframes))
+    m = gpemsr_b200.GPEMSR(None, None, precision=precision, **network_kwargs(scale, nframes))
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     sd = W.fill_state(shapes, seed=900 + scale if seed is None else seed)
     m.load_state_dict(sd, strict=True)

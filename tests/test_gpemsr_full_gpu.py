@@ -29,6 +29,8 @@ def _record_index_parity(key, rec):
 
 
 def _stage_report(model, sd, x, scale):
+    """Stage-by-stage comparison: for the all-split-3 model (precision='fp32'); the default precision plan is judged on the
+    outputs only (HR image / reference images <= 1e-3), which is BASELINE.json's criterion."""
     model.debug = {}
     out, ref_img = model(x.cuda())
     model.check()
@@ -59,7 +61,7 @@ def _stage_report(model, sd, x, scale):
 @pytest.mark.parametrize('scale', [8, 16])
 def test_full_model_golden_and_stages(golden, cuda_dev, scale):
     g = golden(f'full_x{scale}')
-    model, sd = build(scale, device=cuda_dev)
+    model, sd = build(scale, device=cuda_dev, precision='fp32')
     x = T(g['x'])
     out, ref_img, want_out, want_ref, bad, rows = _stage_report(model, sd, x, scale)
     assert not bad, (bad, rows)
@@ -72,11 +74,17 @@ def test_full_model_golden_and_stages(golden, cuda_dev, scale):
     model(torch.rand(1, 5, 1, 16, 16, device='cuda'))
     out2, _ = model(x.cuda())
     assert float((out - out2).abs().max()) <= 1e-4
+    # the default precision plan (VGG branch and SpyNet in one bf16 pass) against the same golden outputs
+    plan, _ = build(scale, device=cuda_dev)
+    out_p, ref_p = plan(x.cuda())
+    plan.check()
+    assert float(np.abs(out_p.cpu().numpy() - g['out']).max()) <= 1e-3
+    assert float(np.abs(ref_p[0, :, 0, ::4, ::4].cpu().numpy() - g['ref_img_sub']).max()) <= 1e-3
 
 
 def test_config1_x8_window_32(cuda_dev):
     """BASELINE configs[0]: x8 on a 5-frame 32 x 32 LR window -> 256 x 256, vs the oracle on the same parameters."""
-    model, sd = build(8, seed=77, device=cuda_dev)
+    model, sd = build(8, seed=77, device=cuda_dev, precision='fp32')
     x = torch.rand(1, 5, 1, 32, 32, generator=torch.Generator().manual_seed(78))
     out, ref_img, want_out, want_ref, bad, rows = _stage_report(model, sd, x, 8)
     assert not bad, (bad, rows)
@@ -87,7 +95,7 @@ def test_config1_x8_window_32(cuda_dev):
 
 def test_x16_non_square_window(cuda_dev):
     """x16 on a 20 x 24 window (sizes that are not powers of two: SpyNet resizes 80 x 96 -> 96 x 96 internally)."""
-    model, sd = build(16, seed=79, device=cuda_dev)
+    model, sd = build(16, seed=79, device=cuda_dev, precision='fp32')
     x = torch.rand(1, 5, 1, 20, 24, generator=torch.Generator().manual_seed(80))
     out, ref_img, want_out, want_ref, bad, rows = _stage_report(model, sd, x, 16)
     assert not bad, (bad, rows)

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gpemsr_b200.volume import gather_slices, shard_range, super_resolve_volume, window_indices
+from gpemsr_b200.volume import exchange_halo, gather_slices, shard_range, super_resolve_volume, window_indices
 
 
 def test_shard_range_partitions():
@@ -43,11 +43,31 @@ def _worker(rank, world, port, n_units):
 
 
 class _FakeModel:
-    """Stands in for gpemsr_b200.GPEMSR on CPU: slice i of the output is a known function of its window's slice indices."""
+    """Stands in for gpemsr_b200.GPEMSR on CPU with the same two-phase structure as ``forward_volume``: every needed slice is
+    "encoded" once into a feature bank (here: 10 * slice value + 1, in a strided bank like the real [cells][rows][8] planes), each
+    output slice is a known function of its window's BANK entries.  With ``halo_exchange`` the rank encodes its own block only
+    and the halo entries must arrive from the neighbours (gpemsr_b200.volume.exchange_halo) -- a missing or misplaced halo
+    shows up as a wrong output."""
 
-    def forward_volume(self, vol, lo=0, hi=None):
-        hi = vol.shape[0] if hi is None else hi
-        rows = [sum(float(vol[j, 0, 0, 0]) * (k + 1) for k, j in enumerate(window_indices(i, vol.shape[0]))) for i in range(lo, hi)]
+    def __init__(self):
+        self.encoded = []
+
+    def forward_volume(self, vol, lo=0, hi=None, halo_exchange=None):
+        S = vol.shape[0]
+        hi = S if hi is None else hi
+        f_lo, f_hi = max(lo - 2, 0), min(hi + 2, S)
+        e_lo, e_hi = (lo, hi) if halo_exchange else (f_lo, f_hi)
+        bank = torch.full((3, f_hi - f_lo, 2), float('nan'))           # [planes][slots][..]: slot views are strided
+        for s_ in range(e_lo, e_hi):
+            bank[:, s_ - f_lo] = 10.0 * vol[s_, 0, 0, 0] + 1.0
+            self.encoded.append(s_)
+        if halo_exchange:
+            dist_, rank, world = halo_exchange
+            sl = lambda a, n: [bank[:, a - f_lo:a - f_lo + n]]
+            down, up = lo > 0, hi < S
+            exchange_halo(sl(lo, 2) if down else [], sl(lo - 2, 2) if down else [], sl(hi - 2, 2) if up else [],
+                          sl(hi, 2) if up else [], rank, world, dist_)
+        rows = [sum(float(bank[0, j - f_lo, 0]) * (k + 1) for k, j in enumerate(window_indices(i, S))) for i in range(lo, hi)]
         return torch.tensor(rows).view(-1, 1, 1, 1) * torch.ones(1, 1, 2, 2)
 
 
@@ -55,17 +75,24 @@ def _volume_worker(rank, world, port, n_slices):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     vol = torch.arange(n_slices, dtype=torch.float32).view(-1, 1, 1, 1) * torch.ones(1, 1, 4, 4)
-    full = super_resolve_volume(_FakeModel(), vol, rank, world, dist)
     want = _FakeModel().forward_volume(vol)
-    assert full.shape == want.shape and torch.equal(full, want)
+    lo, hi = shard_range(n_slices, world, rank)
+    for halo in ('exchange', 'recompute'):
+        m = _FakeModel()
+        full = super_resolve_volume(m, vol, rank, world, dist, halo=halo)
+        assert full.shape == want.shape and torch.equal(full, want), halo
+        # exchange: a rank encodes exactly its own block; recompute: its block plus the 2-slice halo
+        assert m.encoded == (list(range(lo, hi)) if halo == 'exchange' else list(range(max(lo - 2, 0), min(hi + 2, n_slices))))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_super_resolve_volume_two_ranks_gloo():
-    """N > 1 path of the volume driver: contiguous slice blocks per rank, one all_gather, no other collective."""
+@pytest.mark.parametrize('world', [2, 3])
+def test_super_resolve_volume_gloo(world):
+    """N > 1 path of the volume driver: contiguous slice blocks per rank, the halo exchanged between neighbours (a middle rank has
+    two) or recomputed, one all_gather."""
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_volume_worker, args=(2, port, 9), nprocs=2, join=True)
+    mp.spawn(_volume_worker, args=(world, port, 11), nprocs=world, join=True)
 
 
 def test_gather_two_ranks_gloo():

@@ -85,12 +85,57 @@ def measure(scale, sd, x, table, ref, idx0, steps):
     return res, idx, (out, ref_img)
 
 
+def errors_only(scale, sd, x, table, ref, idx0):
+    m = build(scale, sd, table)
+    out, ref_img = m(x)
+    m.check()
+    idx = m.refmodel.codebook.last_idx.clone()
+    res = dict(flips=int((idx != idx0).sum()) if idx0 is not None else 0)
+    if ref is not None:
+        res['out_err'] = float((out - ref[0]).abs().max())
+        res['out_mean_abs'] = float((out - ref[0]).abs().mean())
+        res['ref_img_err'] = float((ref_img - ref[1]).abs().max())
+    del m
+    torch.cuda.empty_cache()
+    return res, idx
+
+
+def verify(cands):
+    """The candidate groups (alone and accumulated) on several parameter / input seeds and both shapes: a plan must hold on every one."""
+    rep = {}
+    for scale, lr, seeds in ((16, 80, (1, 11, 101, 21)), (8, 156, (2, 93, 12, 22)), (8, 16, (400 + 8, 5)), (16, 16, (400 + 16, 6))):
+        for seed in seeds:
+            probe = gpemsr_b200.GPEMSR(None, None, **network_kwargs(scale))
+            sd = W.fill_state({k: tuple(v.shape) for k, v in probe.state_dict().items()}, seed=seed)
+            del probe
+            x = torch.rand(1, 5, 1, lr, lr, generator=torch.Generator().manual_seed(1000 + seed)).cuda()
+            _, idx0 = errors_only(scale, sd, x, {}, None, None)
+            sd_dev = GE.to_device(sd)
+            ref = GE.forward(x, sd_dev, scale, idx_override=idx0)
+            key = f'x{scale}_{lr}_seed{seed}'
+            rep[key] = {'all_split3': errors_only(scale, sd, x, {}, ref, idx0)[0]}
+            acc = {}
+            for g in cands:
+                rep[key][g] = errors_only(scale, sd, x, {p: 1 for p in GROUPS[g]}, ref, idx0)[0]
+                acc.update({p: 1 for p in GROUPS[g]})
+                rep[key]['+'.join(cands[:cands.index(g) + 1])] = errors_only(scale, sd, x, acc, ref, idx0)[0]
+            print(key, json.dumps(rep[key]), flush=True)
+            del sd_dev, ref
+            torch.cuda.empty_cache()
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, 'gpurun_out', 'r02_precision_verify.json'), 'w'), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--budget', type=float, default=3e-4)
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--quick', action='store_true')
+    ap.add_argument('--verify', default='', help='comma-separated groups: errors only, on several seeds and both shapes')
     a = ap.parse_args()
+    if a.verify:
+        verify(a.verify.split(','))
+        return
     report = {'budget_hr_max_abs': a.budget, 'criterion': 'HR image vs PyTorch eager on the same GPU (TF32 off) following the same codebook '
               'indices; tolerance of BASELINE.json: 1e-3 max-abs, PSNR delta < 0.01 dB, indices unchanged'}
     scale, lr = 16, 80
