@@ -39,15 +39,25 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 
 // decode a row of geometry g (relative to g.m0) into (image, y, x); false for ring / tail rows
 __device__ __forceinline__ bool decode_row(const Geom& g, long long rel, int& img, int& y, int& x) {
-  img = (int)(rel / g.r_img);
-  const long long q = rel - (long long)img * g.r_img;
+  // every epilogue thread decodes its row once per tile: 32-bit divisions whenever the numbers fit (always, for real shapes) --
+  // a 64-bit division is ~100 dependent instructions and the narrow-tile epilogues are latency bound
+  long long q;
+  if ((((unsigned long long)rel | (unsigned long long)g.r_img) >> 31) == 0) {
+    const unsigned r32 = (unsigned)rel, ri = (unsigned)g.r_img;
+    img = (int)(r32 / ri);
+    q = (long long)(r32 - (unsigned)img * ri);
+  } else {
+    img = (int)(rel / g.r_img);
+    q = rel - (long long)img * g.r_img;
+  }
   if (g.padded) {
-    const int wp = g.w + 2 * g.padded;
-    const int yp = (int)(q / wp), xp = (int)(q - (long long)yp * wp);
+    const unsigned wp = (unsigned)(g.w + 2 * g.padded), q32 = (unsigned)q;        // q < r_img < 2^31 here
+    const int yp = (int)(q32 / wp), xp = (int)(q32 - (unsigned)yp * wp);
     y = yp - g.padded; x = xp - g.padded;
     return img < g.n && y >= 0 && y < g.h && x >= 0 && x < g.w;
   }
-  y = (int)(q / g.w); x = (int)(q - (long long)y * g.w);
+  if (q >> 31) { y = (int)(q / g.w); x = (int)(q - (long long)y * g.w); }
+  else { const unsigned q32 = (unsigned)q, w32 = (unsigned)g.w; y = (int)(q32 / w32); x = (int)(q32 - (unsigned)y * w32); }
   return img < g.n && q < (long long)g.h * g.w;
 }
 __device__ __forceinline__ long long place_row(const Geom& g, int img, int y, int x) {
@@ -59,6 +69,7 @@ int check_geom(const gpemsr_geom_t& g, const char* what) {
   if (g.n <= 0 || g.h <= 0 || g.w <= 0 || g.r_img <= 0 || (g.r_img % kRowTile) != 0)
     return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: bad geometry n=%d h=%d w=%d r_img=%lld", what, g.n, g.h, g.w, (long long)g.r_img);
   if (g.padded < 0 || g.padded > 3) return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: ring width %d (0..3 supported)", what, g.padded);
+  if (g.r_img >= (1LL << 31)) return set_error(GPEMSR_ERR_BAD_SHAPE, "%s: more than 2^31 rows per image", what);
   const long long need = (long long)(g.h + 2 * g.padded) * (g.w + 2 * g.padded);
   const long long margin = g.padded ? (long long)g.padded * (g.w + 2 * g.padded) + g.padded : 0;     // largest tap shift
   if (g.r_img < need || g.m0 < margin || g.rows_alloc < g.m0 + (long long)g.n * g.r_img + margin)

@@ -14,7 +14,10 @@
 
 namespace {
 
-template <int BLOCK_N>
+// PAIR: the accumulator is split over the column ranges (c, c + BLOCK_N) -- the paired-N MMAs of the tap-fused / dy-fused kernels in
+// the fp32-faithful split keep a_hi * w_lo apart from a_hi * w_hi + a_lo * w_hi; the epilogue sums them.  A compile-time property
+// of the launch: the kernels that never pair (the streaming kernel, every single-pass launch) carry no second TMEM load.
+template <int BLOCK_N, bool PAIR = false>
 struct EpiConv {
   Geom ag, og;
   int n_cols;
@@ -32,8 +35,7 @@ struct EpiConv {
   long long ld;
   double* gn_sums;
   int gn_cpg;
-  int pair_off;               // > 0: the accumulator is split over two column ranges (c, c + pair_off): the paired-N MMAs of the
-                              // tap-fused / dy-fused kernels keep a_hi * w_lo apart from a_hi * w_hi + a_lo * w_hi; summed here
+  static constexpr int pair_off = PAIR ? BLOCK_N : 0;      // column distance of the two partial accumulators (see PAIR above)
   const float* patch_other;   // fp32 cells in the output geometry: the tensor the stored values are correlated with
   int patch_other_bf16;       // 1: patch_other points at bf16 cells (the hi plane of that tensor) instead
   float* patch_sums;          // [n][h / patch][w / patch][3] = (sum v*o, sum v*v, sum o*o) per patch x patch block of pixels
@@ -44,7 +46,13 @@ struct EpiConv {
   float* row_sum;             // per-row sum of the stored v over the columns (atomicAdd once per CTA column sweep)
   const float* row_div;       // v = acc / row_div[row]  (the deferred softmax normalisation of P v^T)
 
-  static constexpr int WARPS = BLOCK_N >= 64 ? 8 : 4;
+  // epilogue warps: (WARPS / 4) warps share a TMEM lane quarter and split the tile's columns.  The narrow tiles are EPILOGUE bound
+  // (ncu source view, 64 -> 64 conv @ 5 x 640^2 with 8 warps: the epilogue warps are busy 92 % of the time at 10 cycles per
+  // instruction, half of it long-scoreboard stalls on bias / residual / constant loads that two warps per scheduler cannot hide,
+  // tile period 7900 cycles against 5000 of MMA time), so N = 64 runs 16 epilogue warps and N = 32 runs 8: -7 % / -14 % on the
+  // split-3 / single-pass 64-channel convs.  (Measured and dropped: 16 warps on the N >= 128 tiles -- the 112-register cap spills and the
+  // wide kernels get 2-4 % slower.)
+  static constexpr int WARPS = BLOCK_N == 64 ? 16 : BLOCK_N >= 128 ? 8 : BLOCK_N == 32 ? 8 : 4;
   struct State {
     bool init = false, valid = false;
     int img = 0, y = 0, x = 0;
@@ -116,26 +124,32 @@ struct EpiConv {
     }
   }
 
+  // the bias of a chunk's columns: loaded BEFORE the chunk's TMEM loads are issued, so the two latencies overlap (the epilogue
+  // warps stall on exactly these loads: ncu source view)
   template <int CHUNK>
-  __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], int col0, long long rel) const {
-    float f[CHUNK];
-    const bool full = col0 + CHUNK <= n_cols;
-    // v = scale * acc + bias  (flag tests are hoisted out of the column loops: they are uniform for the launch)
+  __device__ __forceinline__ void load_bias(const State& st, float (&bv)[CHUNK], int col0) const {
     if (bias_per_row) {
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), st.row_bias);
-    } else if (bias && full) {
+      for (int j = 0; j < CHUNK; ++j) bv[j] = st.row_bias;
+    } else if (bias && col0 + CHUNK <= n_cols) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-        f[j] = fmaf(scale, __uint_as_float(r[j]), b4.x); f[j + 1] = fmaf(scale, __uint_as_float(r[j + 1]), b4.y);
-        f[j + 2] = fmaf(scale, __uint_as_float(r[j + 2]), b4.z); f[j + 3] = fmaf(scale, __uint_as_float(r[j + 3]), b4.w);
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j)
-        f[j] = fmaf(scale, __uint_as_float(r[j]), (bias && col0 + j < n_cols) ? __ldg(bias + col0 + j) : 0.f);
+      for (int j = 0; j < CHUNK; ++j) bv[j] = (bias && col0 + j < n_cols) ? __ldg(bias + col0 + j) : 0.f;
     }
+  }
+
+  template <int CHUNK>
+  __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], const float (&bv)[CHUNK], int col0, long long rel) const {
+    float f[CHUNK];
+    const bool full = col0 + CHUNK <= n_cols;
+    // v = scale * acc + bias
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), bv[j]);
     if (row_max_out) {                   // softmax pre-pass: nothing is stored
       float m = st.r_max;
 #pragma unroll
@@ -154,8 +168,11 @@ struct EpiConv {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
     } else if (act == GPEMSR_ACT_EXP) {
+      // exp(v - max) = 2^(v * log2(e) - max * log2(e)): one FFMA + MUFU.EX2 per element (relative error ~2^-22; the arguments are
+      // <= ~0, so no overflow; expf() costs ~4x the instructions and this epilogue is what bounds the scores GEMM)
+      const float sub2 = st.r_sub * 1.4426950408889634f;
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) f[j] = expf(f[j] - st.r_sub);
+      for (int j = 0; j < CHUNK; ++j) f[j] = exp2f(fmaf(f[j], 1.4426950408889634f, -sub2));
     }
     if (!full) {
 #pragma unroll
@@ -263,14 +280,19 @@ struct EpiConv {
         if (row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
       }
     }
-    constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
     constexpr int SPAN = BLOCK_N / (WARPS / 4);          // columns this warp covers
+    constexpr int CHUNK = SPAN >= 32 ? 32 : 16;
+    const bool row_stats = (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
 #pragma unroll 1
     for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
+      const int col0 = n_tile * BLOCK_N + c0;
+      const bool work = (st.valid || gn_sums) && col0 < n_cols;
+      float bv[CHUNK];
+      if (work) load_bias<CHUNK>(st, bv, col0);
       uint32_t r[CHUNK];
       if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + c0, r);
       else sm100::tmem_ld_32x16(tmem_acc + c0, r);
-      if (pair_off) {
+      if constexpr (PAIR) {
         uint32_t r2[CHUNK];
         if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + pair_off + c0, r2);
         else sm100::tmem_ld_32x16(tmem_acc + pair_off + c0, r2);
@@ -279,12 +301,11 @@ struct EpiConv {
         for (int j = 0; j < CHUNK; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
       }
       sm100::tmem_ld_wait();
-      const int col0 = n_tile * BLOCK_N + c0;
-      if ((st.valid || gn_sums) && col0 < n_cols) chunk<CHUNK>(st, r, col0, rel);
+      if (work) chunk<CHUNK>(st, r, bv, col0, rel);
     }
     if (patch_sums) flush_patch(st);
     // fused softmax statistics: one atomic per row once this CTA has swept its last column tile of the row tile
-    if ((row_max_out || row_sum) && st.valid && n_tile + (int)gridDim.y >= n_tiles) {
+    if (row_stats && st.valid) {
       if (row_max_out) {                 // float max through the ordered-integer trick (the buffer starts at -1.7e38)
         if (st.r_max >= 0.f) atomicMax(reinterpret_cast<int*>(row_max_out + rel), __float_as_int(st.r_max));
         else atomicMin(reinterpret_cast<unsigned*>(row_max_out + rel), __float_as_uint(st.r_max));
@@ -330,7 +351,6 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
-  e.pair_off = 0;
   const int sms = gpemsr::num_sms();
   const bool clustered = BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters();
   // grid: gx persistent row-tile walkers x gy column-tile splitters.  Model: one CTA per SM, CTAs run in waves, a CTA's
@@ -369,7 +389,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
 
 template <int BLOCK_N, int SPLIT>
 int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
-  using Epi = EpiConv<BLOCK_N>;
+  using Epi = EpiConv<BLOCK_N, SPLIT == 3>;
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
@@ -379,7 +399,6 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
-  e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
@@ -412,7 +431,7 @@ size_t plan_dyfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n
 
 template <int BLOCK_N, int SPLIT>
 int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
-  using Epi = EpiConv<BLOCK_N>;
+  using Epi = EpiConv<BLOCK_N, SPLIT == 3>;
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
@@ -422,7 +441,6 @@ int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t
   e.gn_sums = d.gn_sums; e.gn_cpg = d.gn_cpg;
   e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
-  e.pair_off = SPLIT == 3 ? BLOCK_N : 0;
   auto kern = gemm::gemm_dyfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());

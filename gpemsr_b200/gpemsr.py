@@ -428,10 +428,10 @@ class GPEMSR(SRTail):
         from .volume import exchange_halo, window_indices
         S, _, H, W = vol.shape
         N, nf, dev = self.nframes, self.nf, vol.device
-        f_hi_needed, f_hi = f_hi, e_hi
+        f_hi = e_hi
         for s0 in range(e_lo, e_hi, fb):
-            idx = [min(s0 + t, f_hi - 1) for t in range(fb)]     # the last batch repeats its last slice (one plan shape)
-            frames = vol[s0:s0 + fb] if idx[-1] == s0 + fb - 1 else vol[torch.tensor(idx, device=dev)]
+            # a short last batch is encoded as its own (smaller) batch -- a second plan shape -- instead of repeating slices
+            frames = vol[s0:min(s0 + fb, f_hi)]
             Pe, _ = self._encode_frames(frames)
             nv = min(fb, f_hi - s0)
             for k in range(3):

@@ -96,9 +96,69 @@ def conv_bench(which=None):
     return out
 
 
+def conv_last_bench(iters=5):
+    """conv_last (64 -> 1 @ 1280^2) + bilinear base: nine taps as the columns of one 1x1 GEMM + the nine-point sum kernel."""
+    from gpemsr_b200 import igemm as G
+    s = 1280
+    g = G.Geom(1, s, s, True)
+    x = G.Act(g, 64, 'cuda', f32=False)
+    x.hi.normal_(); x.lo.normal_(std=0.004)
+    w = torch.randn(1, 64, 3, 3, device='cuda') * 0.05
+    b = torch.randn(1, device='cuda')
+    wt = G.Weights(G.taps_as_columns(w), 'conv')
+    taps = G.TapCells(g, 1, 'cuda')
+    base = torch.rand(1, 1, s // 16, s // 16, device='cuda')
+    out = torch.empty(1, 1, s, s, device='cuda')
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    fn = lambda: G.conv3x3_few_outputs(x, wt, taps, err, 3, b, out, 1, base=base, base_scale=16)
+    med, best = timeit(fn, iters=iters, warm=2)
+    return [dict(op='conv_last_1280', ms=med, ms_best=best, bytes_in=4.0 * 64 * s * s, gbs=(4.0 * 64 * s * s + 4.0 * s * s) / med / 1e6,
+                 note='64 -> 1 3x3 @ 1 x 1280^2 (+ bilinear base): round 1 ran this as nine N = 16 tensor-pipe tiles per k-step (~0.2 ms)')]
+
+
+def flow1_bench():
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    c, s = 64, 1250
+    x = torch.randn(1, c, s, s, device='cuda')
+    fl = torch.nn.functional.avg_pool2d(2.0 * torch.randn(1, 2, s, s, device='cuda'), 5, 1, 2).permute(0, 2, 3, 1).contiguous()
+    white = 4.0 * torch.randn(1, s, s, 2, device='cuda')
+    byt = 8 * c * s * s + 8 * s * s
+    med, best = timeit(lambda: gpemsr_b200.flow_warp(x, fl, 'bilinear', 'border'), flush=flush)
+    med_w, _ = timeit(lambda: gpemsr_b200.flow_warp(x, white, 'bilinear', 'border'), flush=flush)
+    from oracle.flow_warp import flow_warp_torch
+    med_t, _ = timeit(lambda: flow_warp_torch(x, fl, 'bilinear', 'border'), flush=flush)
+    return [dict(op='flow_warp', c=c, s=s, ms=med, ms_best=best, gbs=byt / med / 1e6, frac=byt / med / 1e6 / 6550.1, ms_white_noise_flow=med_w,
+                 gbs_white=byt / med_w / 1e6, frac_white=byt / med_w / 1e6 / 6550.1, torch_grid_sample_ms=med_t)]
+
+
+def attn_bench(n=1, c=512, hw=80, iters=5):
+    """One NonLocalBlock (model/blocks.py:61-83) at the decoder's shape: GroupNorm, q / k / v^T, row-max pre-pass, scores + exp,
+    P v^T / row sum, proj_out -- 7 GEMM launches per image + 3 GroupNorm helpers."""
+    from gpemsr_b200 import igemm as G
+    from gpemsr_b200.decoder import Decoder, NonLocalBlock, _Plan
+    dec = Decoder(dict(channel_list=[c, c], im_channel=1, num_resblock_per_scale=1, num_input_resblck=0, latent_dim=c, use_non_local=True)).cuda()
+    nl = [m for m in dec.feat_extract if isinstance(m, NonLocalBlock)][0]
+    P = _Plan(dec, n, hw, hw, torch.device('cuda'))
+    g = G.Geom(n, hw, hw, True)
+    x = G.Act(g, c, 'cuda', f32=True)
+    G.pack_nchw(torch.randn(n, c, hw, hw, device='cuda'), x)
+    fn = lambda: dec._non_local(P, 'nl', nl, x)
+    med, best = timeit(fn, iters=iters, warm=1)
+    t = hw * hw
+    fl = n * (4.0 * t * t * c + 8.0 * t * c * c)
+    return [dict(op='non_local_block', n=n, c=c, tokens=t, ms=med, ms_best=best, tflops=fl / med / 1e9,
+                 note='GroupNorm + q/k/v + fused-softmax attention + proj_out; algorithmic FLOPs 4 T^2 C + 8 T C^2 per image')]
+
+
 if __name__ == '__main__':
     torch.cuda.init()
     res = []
+    if 'attn' in sys.argv[1:]:
+        res += attn_bench()
+    if 'last' in sys.argv[1:]:
+        res += conv_last_bench()
+    if 'flow1' in sys.argv[1:]:
+        res += flow1_bench()
     if 'flow' in sys.argv[1:] or len(sys.argv) == 1:
         res += flow_warp_bench()
     if 'conv' in sys.argv[1:]:

@@ -29,6 +29,10 @@ def main(path):
             if w in hdr:
                 i = hdr.index(w)
                 print(f'   {w:72s} {r[i]:>16s} {units[i]}')
+        for i, h in enumerate(hdr):            # tensor-pipe / TMEM / shared-memory operand-fetch counters, whatever this ncu calls them
+            if h not in WANT and any(t in h for t in ('pipe_tensor', 'tc_wavefronts', 'tmem', 'data_pipe_lsu_wavefronts_mem_shared.sum',
+                                                      'shared_op_ld.sum', 'achieved_occupancy')):
+                print(f'   {h:72s} {r[i]:>16s} {units[i]}')
 
 
 if __name__ == '__main__':
