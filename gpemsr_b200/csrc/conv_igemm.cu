@@ -144,7 +144,8 @@ struct EpiConv {
   }
 
   template <int CHUNK>
-  __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], const float (&bv)[CHUNK], int col0, long long rel) const {
+  __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], const float (&bv)[CHUNK], const uint4 (&po)[CHUNK / 8],
+                                        int col0, long long rel) const {
     float f[CHUNK];
     const bool full = col0 + CHUNK <= n_cols;
     // v = scale * acc + bias
@@ -199,7 +200,7 @@ struct EpiConv {
         const size_t cell = ((size_t)((c_off + col0 + 8 * g) >> 3) * og.rows_alloc + st.orow) * 8;
         float o[8];
         if (patch_other_bf16) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(patch_other) + cell));
+          const uint4 raw = po[g];               // loaded ahead of the TMEM loads (tile()): this epilogue stalled on exactly this load
           const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) { o[2 * j] = __uint_as_float(w4[j] << 16); o[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u); }
@@ -288,7 +289,18 @@ struct EpiConv {
       const int col0 = n_tile * BLOCK_N + c0;
       const bool work = (st.valid || gn_sums) && col0 < n_cols;
       float bv[CHUNK];
-      if (work) load_bias<CHUNK>(st, bv, col0);
+      uint4 po[CHUNK / 8];
+      if (work) {
+        load_bias<CHUNK>(st, bv, col0);
+        if (patch_sums && patch_other_bf16 && st.valid) {
+#pragma unroll
+          for (int g = 0; g < CHUNK / 8; ++g) {
+            const size_t cell = ((size_t)((c_off + col0 + 8 * g) >> 3) * og.rows_alloc + st.orow) * 8;
+            po[g] = col0 + 8 * g < n_cols ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(patch_other) + cell))
+                                          : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
       uint32_t r[CHUNK];
       if constexpr (CHUNK == 32) sm100::tmem_ld_32x32(tmem_acc + c0, r);
       else sm100::tmem_ld_32x16(tmem_acc + c0, r);
@@ -301,7 +313,7 @@ struct EpiConv {
         for (int j = 0; j < CHUNK; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
       }
       sm100::tmem_ld_wait();
-      if (work) chunk<CHUNK>(st, r, bv, col0, rel);
+      if (work) chunk<CHUNK>(st, r, bv, po, col0, rel);
     }
     if (patch_sums) flush_patch(st);
     // fused softmax statistics: one atomic per row once this CTA has swept its last column tile of the row tile
