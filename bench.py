@@ -585,7 +585,7 @@ def main():
         name, (fl, tms, cnt) = max(agg.items(), key=lambda kv: kv[1][1])
         step_ms = ms_total / args.steps
         # DRAM bytes per launch of that kernel class: from the committed ncu pass over one eager step (profiles/README.md)
-        prof = os.path.join(ROOT, 'profiles', 'r01_full_traffic.json')
+        prof = os.path.join(ROOT, 'profiles', 'r02_full_traffic.json')
         traffic = None
         if os.path.exists(prof):
             ent = json.load(open(prof))['per_step'].get(name)
@@ -593,7 +593,7 @@ def main():
         roof = {'bound': 'tensor', 'kernel': name, 'achieved': fl / tms / 1e9, 'peak': peaks['tf'], 'unit': 'TFLOP/s',
                 'frac': fl / tms / 1e9 / peaks['tf'], 'traffic': traffic, 'launches_per_step': cnt,
                 'ms_per_launch': tms / cnt, 'share_of_step': tms / step_ms, 'peak_source': peaks['src'] + ' (bf16 sustained)',
-                'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_full_traffic.json)',
+                'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_full_traffic.json)',
                 'note': 'algorithmic FLOPs = 2*rows*cols*k*taps (one pass); the kernel issues 3 bf16 MMAs per product '
                         '(fp32-faithful split), so frac <= 1/3 by construction',
                 'by_kernel': {k: {'tflops': v[0] / v[1] / 1e9, 'ms': v[1], 'launches': v[2]} for k, v in agg.items()}}
