@@ -653,7 +653,7 @@ __global__ void pack_concat3_kernel(const float* __restrict__ a, int ca, const f
 __global__ void __launch_bounds__(256)
 conv3x3_c1_relu_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ bias, int co, Geom g,
                        uint4* __restrict__ out_hi, uint4* __restrict__ out_lo) {
-  __shared__ float sw[64 * 9 + 64];
+  __shared__ __align__(16) float sw[64 * 9 + 64];
   for (int i = threadIdx.x; i < co * 9; i += blockDim.x) sw[i] = w1[i];
   for (int i = threadIdx.x; i < co; i += blockDim.x) sw[64 * 9 + i] = bias[i];
   __syncthreads();
@@ -672,13 +672,17 @@ conv3x3_c1_relu_kernel(const float* __restrict__ x, const float* __restrict__ w1
     }
   const long long row = place_row(g, img, y, xx);
   for (int cc = 0; cc < co / 8; ++cc) {
+    // the 72 weights of a cell as 18 broadcast LDS.128 instead of 72 LDS.32 (the kernel is issue bound: 576 MACs per pixel)
+    float wv[72];
+    const float4* w4 = reinterpret_cast<const float4*>(sw + cc * 72);
+#pragma unroll
+    for (int q = 0; q < 18; ++q) { const float4 f4 = w4[q]; wv[4 * q] = f4.x; wv[4 * q + 1] = f4.y; wv[4 * q + 2] = f4.z; wv[4 * q + 3] = f4.w; }
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float* wj = sw + (cc * 8 + j) * 9;
       float a = sw[64 * 9 + cc * 8 + j];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(v[k], wj[k], a);
+      for (int k = 0; k < 9; ++k) a = fmaf(v[k], wv[j * 9 + k], a);
       o[j] = fmaxf(a, 0.f);
     }
     uint4 hi, lo;

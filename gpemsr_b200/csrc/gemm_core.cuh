@@ -531,6 +531,9 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1
     const uint32_t a_desc_lo = ((seg_bytes >> 4) & 0x3FFFu) << 16;           // LBO = one k-cell column of a segment
     const uint32_t b_desc_lo = (((uint32_t)PLANES * BLOCK_N * 16 >> 4) & 0x3FFFu) << 16;      // LBO: the next k-cell's [plane][n] block
+    // a full 3x3 tap grid in dy-major order: segments of BLOCK_M + 2 rows, tap (dy, dx) at segment dy, row dx
+    bool is3x3 = op.taps == 9 && op.n_seg == 3 && op.seg_len == BLOCK_M + 2;
+    for (int t = 0; t < 9 && is3x3; ++t) is3x3 = op.tap_seg[t] == t / 3 && op.tap_dx[t] == t % 3;
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
       ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
       if (!ok) break;
@@ -545,6 +548,25 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
           // thread -- the serial bottleneck of this loop -- does two adds per MMA, offsets come from a smem table
           const uint32_t a_lo0 = a_desc_lo + (sm100::smem_u32(stages + (size_t)stage * stage_bytes) >> 4);
           const uint32_t b_lo0 = b_desc_lo + ((sb0 + (uint32_t)(it * KCH) * (PLANES * BLOCK_N * 16)) >> 4);
+          if (is3x3) {
+            // The 3x3 case (every 64-channel convolution of the model): the nine start-address offsets are compile-time
+            // constants (segment dy at 2 * 130 cell rows, dx = one row), so the fully unrolled loop is an add-immediate per
+            // descriptor.  The ISSUING THREAD bounds these kernels (ncu source view: it never waits and needs ~108 cycles per MMA
+            // through the table-driven loop while the tensor pipe is busy ~49), so every instruction here counts.
+            const uint32_t b_tap16 = ((uint32_t)PLANES * b_tap_bytes) >> 4, a_pl16 = a_plane_bytes >> 4;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)((t / 3) * (KCH * (BLOCK_M + 2)) + t % 3), b_lo = b_lo0 + (uint32_t)t * b_tap16;
+              const uint64_t a_hi_d = ((uint64_t)kDescHi << 32) | a_lo, b_hi_d = ((uint64_t)kDescHi << 32) | b_lo;
+              if constexpr (SPLIT == 3) {
+                const uint64_t a_lo_d = ((uint64_t)kDescHi << 32) | (a_lo + a_pl16);
+                sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc_pair, (it | t) != 0);    // a_hi * [w_hi | w_lo]
+                sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);                  // a_lo * w_hi
+              } else {
+                sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
+              }
+            }
+          } else {
           for (int t = 0; t < op.taps; ++t) {
             const uint32_t a_lo = a_lo0 + tap_tab[2 * t], b_lo = b_lo0 + tap_tab[2 * t + 1];
             const uint64_t a_hi_d = ((uint64_t)kDescHi << 32) | a_lo, b_hi_d = ((uint64_t)kDescHi << 32) | b_lo;
@@ -555,6 +577,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
             } else {
               sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
             }
+          }
           }
           sm100::umma_commit(&bars->empty[stage]);
           if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
@@ -684,14 +707,26 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
           sm100::tc_fence_after();
           uint32_t a = a_lo_base + stage * (stage_bytes >> 4);
           uint32_t b = b_lo_base + stage * (stage_bytes >> 4);
-          for (int dx = 0; dx < op.n_dx; ++dx, ++a, b += b_tap) {                   // one row = one 16-byte unit
-            const uint64_t a_hi = ((uint64_t)kDescHi << 32) | a, b_hi = ((uint64_t)kDescHi << 32) | b;
+          // one tap = one 16-byte row of A and one weight block of B.  The issuing thread bounds the narrow kernels, so the two tap
+          // counts the model uses (3: the K > 64 3x3 convs, 7: SpyNet) are fully unrolled: add-immediate descriptors, no loop
+          auto issue = [&](int dx) {
+            const uint32_t ad = a + (uint32_t)dx, bd = b + (uint32_t)dx * b_tap;
+            const uint64_t a_hi = ((uint64_t)kDescHi << 32) | ad, b_hi = ((uint64_t)kDescHi << 32) | bd;
             if constexpr (SPLIT == 3) {
               sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc_pair, (it | dx) != 0);                               // a_hi * [w_hi | w_lo]
-              sm100::umma_bf16(tmem_acc, ((uint64_t)kDescHi << 32) | (a + a_pl), b_hi, idesc, true);            // a_lo * w_hi
+              sm100::umma_bf16(tmem_acc, ((uint64_t)kDescHi << 32) | (ad + a_pl), b_hi, idesc, true);           // a_lo * w_hi
             } else {
               sm100::umma_bf16(tmem_acc, a_hi, b_hi, idesc, (it | dx) != 0);
             }
+          };
+          if (op.n_dx == 3) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) issue(dx);
+          } else if (op.n_dx == 7) {
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) issue(dx);
+          } else {
+            for (int dx = 0; dx < op.n_dx; ++dx) issue(dx);
           }
           sm100::umma_commit(&bars->empty[stage]);
           if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
