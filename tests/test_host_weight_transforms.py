@@ -92,3 +92,22 @@ def test_cached_follows_parameter_identity_and_version():
     assert get() == 4.0 and len(builds) == 2
     p.data = torch.full((4,), 2.0)                                 # what .to(device) does
     assert get() == 8.0 and len(builds) == 3
+
+
+def test_precision_table_longest_prefix_and_submodules():
+    """igemm.Precision: 'fp32' / 'bf16' / {prefix: split}; longest prefix wins; sub() hands a sub-module its slice of the table."""
+    import pytest
+    from gpemsr_b200 import igemm as G
+    assert G.Precision('fp32').split('anything') == 3 and G.Precision('bf16').split('x') == 1
+    p = G.Precision({'vgg': 1, 'decoder': 3, 'decoder.feat_extract.0': 1, 'tail.up': 1, 'default': 3})
+    assert p.split('vgg') == 1 and p.split('enc.conv_first') == 3
+    assert p.split('decoder.feat_extract.0.q') == 1 and p.split('decoder.feat_extract.1.block.0') == 3
+    assert p.split('tail.up3') == 1 and p.split('tail.hr') == 3 and p.planes() == 3
+    d = p.sub('decoder')
+    assert d.split('feat_extract.0.scores') == 1 and d.split('input_layer.0') == 3
+    assert G.Precision({'default': 1}).planes() == 1
+    with pytest.raises(ValueError):
+        G.Precision({'vgg': 2})
+    from gpemsr_b200.gpemsr import DEFAULT_PLAN
+    q = G.Precision(DEFAULT_PLAN)
+    assert q.split('vgg') == 1 and q.split('spynet') == 1 and q.split('indexer.feat_extract.0') == 3 and q.split('enc.mask.conv3') == 3
