@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libgpemsr_b200.so')
+# GPEMSR_B200_LIB: another build of the same library (A/B timing, profiling builds of tools/ablate.py); default = the in-tree build
+LIB_PATH = os.path.abspath(os.environ['GPEMSR_B200_LIB']) if os.environ.get('GPEMSR_B200_LIB') else os.path.join(_HERE, 'lib', 'libgpemsr_b200.so')
 
 ERRORS = {0: 'OK', -1: 'BAD_SHAPE', -2: 'BAD_ALIGN', -3: 'UNSUPPORTED_ARCH', -4: 'CUDA', -5: 'WORKSPACE',
           -6: 'UNSUPPORTED'}
@@ -31,6 +32,7 @@ SIGNATURES = {
     'gpemsr_last_error_string': (C.c_char_p, []),
     'gpemsr_device_check': (_i, [_i]),
     'gpemsr_kernel_launches': (_i64, []),
+    'gpemsr_tensor_map_stats': (None, [_p, _p]),
     'gpemsr_flow_warp': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     'gpemsr_flow_warp_ex': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     'gpemsr_vq_workspace_bytes': (_sz, [_i64, _i, _i]),

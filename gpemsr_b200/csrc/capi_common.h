@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include "../../include/gpemsr_b200.h"
+#include "sm100.cuh"
 
 namespace gpemsr {
 
@@ -14,6 +15,17 @@ extern std::atomic<long long> g_launches;   // kernels launched by this library
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
 bool use_clusters();                      // GPEMSR_CLUSTER=0 disables the cluster-multicast kernels (A/B testing)
+bool use_tensor_maps();                   // GPEMSR_TMA=0: activation tiles by plain bulk copies instead of tensor-map TMA (A/B testing)
+
+using TensorMap = sm100::TensorMap;      // a CUtensorMap as an opaque kernel parameter
+// Tiled tensor map over K8-blocked activation cells, element type = 8 bytes (half a 16-byte cell: a 16-byte inner dimension
+// makes the TMA engine work cell by cell -- measured 1.35x slower than bulk copies -- while a run of seg_len cells exceeds the
+// 256-element box limit, so a run is described as 2 x (seg_len 8-byte elements)).  dims[0 .. rank-1] / strides_bytes[1 .. rank-1]
+// / box[] innermost first.  No swizzle, out-of-bounds elements read as zero.  false when the driver entry point is missing or
+// rejects the shape (callers then use the bulk-copy path; tensor_map_stats() counts both outcomes).
+bool encode_u64_map(TensorMap* out, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                    const unsigned* box);
+void tensor_map_stats(long long* built, long long* rejected);
 
 #define GPEMSR_CUDA_OK(expr)                                                              \
   do {                                                                                    \

@@ -399,6 +399,47 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   return GPEMSR_OK;
 }
 
+// Tensor maps of the A planes for the tap-fused kernel, in 8-byte elements (see encode_u64_map): a segment of seg_len cells of one
+// k-cell column is 2 x seg_len elements, so the map is {2 * rows, 2 (stride = half a segment), segments (stride = one padded image
+// row), k-cells} with box {seg_len, 2, n_seg, 2} -> shared memory [k-cell][segment][row][8 bf16].  The half-segment and segment
+// dimensions OVERLAP the row dimension (shifted views of the same cells; the driver accepts that); the rows extent is shortened
+// so the last segment stays inside the allocation.  use = 0 (bulk copies) when the segments are not evenly spaced, seg_len is
+// odd, the driver refuses the shape, or GPEMSR_TMA=0.
+void maps_tapfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
+  tm.use = 0;
+  if (!gpemsr::use_tensor_maps() || op.seg_len > 256 || (op.seg_len & 1)) return;
+  long long seg_stride = op.a_rows;                     // n_seg == 1: any valid stride
+  if (op.n_seg > 1) {
+    seg_stride = op.seg_row_off[1] - op.seg_row_off[0];
+    for (int i = 2; i < op.n_seg; ++i) if (op.seg_row_off[i] - op.seg_row_off[i - 1] != seg_stride) return;
+    if (seg_stride <= 0) return;
+  }
+  const long long rows = op.a_rows - (op.n_seg > 1 ? (op.n_seg - 1) * seg_stride : 0) - op.seg_len / 2;
+  if (rows <= 0 || op.a_row0 + op.seg_row_off[0] < 0 || 2 * (op.a_row0 + op.m_tiles * gemm::BLOCK_M + op.seg_row_off[0]) >= (1LL << 31)) return;
+  const unsigned long long dims[4] = {2ull * rows, 2, (unsigned long long)op.n_seg, (unsigned long long)(op.k / 8)};
+  const unsigned long long strides[4] = {0, (unsigned long long)op.seg_len * 8, (unsigned long long)seg_stride * 16, (unsigned long long)op.a_rows * 16};
+  const unsigned box[4] = {(unsigned)op.seg_len, 2, (unsigned)op.n_seg, 2u * (unsigned)op.kslabs};
+  const void* base[2] = {op.a_hi, op.a_lo};
+  for (int p = 0; p < planes; ++p)
+    if (!gpemsr::encode_u64_map(&tm.a[p], base[p], 4, dims, strides, box)) return;
+  tm.use = 1;
+}
+
+// dy-fused kernel: {2 * rows, 2, k-cells}, box {seg_len, 2, 2}
+void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
+  tm.use = 0;
+  if (!gpemsr::use_tensor_maps() || op.seg_len > 256 || (op.seg_len & 1)) return;
+  if (op.a_row0 + op.dy_row_off[0] < 0 || 2 * (op.a_row0 + op.m_tiles * gemm::BLOCK_M + op.dy_row_off[op.n_dy - 1]) >= (1LL << 31)) return;
+  const long long rows = op.a_rows - op.seg_len / 2;
+  const unsigned long long dims[3] = {2ull * rows, 2, (unsigned long long)(op.k / 8)};
+  const unsigned long long strides[3] = {0, (unsigned long long)op.seg_len * 8, (unsigned long long)op.a_rows * 16};
+  const unsigned box[3] = {(unsigned)op.seg_len, 2, 2};
+  const void* base[2] = {op.a_hi, op.a_lo};
+  for (int p = 0; p < planes; ++p)
+    if (!gpemsr::encode_u64_map(&tm.a[p], base[p], 3, dims, strides, box)) return;
+  tm.use = 1;
+}
+
 template <int BLOCK_N, int SPLIT>
 int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
   using Epi = EpiConv<BLOCK_N, SPLIT == 3>;
@@ -414,7 +455,9 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
   auto kern = gemm::gemm_tapfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
-  kern<<<(unsigned)gx, gemm::num_threads<Epi>(), smem_bytes, s>>>(op, e);
+  gemm::TmaMaps tm;
+  maps_tapfuse(tm, op, SPLIT == 3 ? 2 : 1);
+  kern<<<(unsigned)gx, gemm::num_threads<Epi>(), smem_bytes, s>>>(op, e, tm);
   GPEMSR_LAUNCH_OK("gemm_tapfuse_kernel<EpiConv>");
   return GPEMSR_OK;
 }
@@ -434,7 +477,7 @@ size_t plan_dyfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n
   op.n_dy = n_dy; op.n_dx = n_dx;
   op.seg_len = gemm::BLOCK_M + n_dx - 1;
   for (int i = 0; i < n_dy; ++i) op.dy_row_off[i] = (d.tap_dy[0] + i) * wp + d.tap_dx[0];
-  const size_t stage_bytes = (size_t)planes * (2 * (size_t)op.seg_len * 16 + (size_t)n_dx * 2 * block_n * 16);
+  const size_t stage_bytes = (size_t)planes * (((2 * (size_t)op.seg_len * 16 + 127) & ~(size_t)127) + (size_t)n_dx * 2 * block_n * 16);
   const size_t budget = 227 * 1024 - 1024;
   if (3 * stage_bytes > budget) return 0;
   op.nstage = (int)std::min<size_t>(8, budget / stage_bytes);
@@ -456,7 +499,9 @@ int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t
   auto kern = gemm::gemm_dyfuse_kernel<BLOCK_N, SPLIT, Epi>;
   GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const long long gx = std::min<long long>(op.m_tiles, gpemsr::num_sms());
-  kern<<<(unsigned)gx, gemm::num_threads<Epi>(), smem_bytes, s>>>(op, e);
+  gemm::TmaMaps tm;
+  maps_dyfuse(tm, op, SPLIT == 3 ? 2 : 1);
+  kern<<<(unsigned)gx, gemm::num_threads<Epi>(), smem_bytes, s>>>(op, e, tm);
   GPEMSR_LAUNCH_OK("gemm_dyfuse_kernel<EpiConv>");
   return GPEMSR_OK;
 }
@@ -478,8 +523,16 @@ size_t plan_tapfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_
   for (int i = 0; i < n_seg; ++i) op.seg_row_off[i] = dys[i] * wp + dx_min;
   for (int t = 0; t < d.taps; ++t) op.tap_dx[t] = d.tap_dx[t] - dx_min;
   const size_t b_bytes = ((size_t)planes * d.taps * (d.k_pad / 8) * block_n * 16 + 1023) & ~(size_t)1023;
-  const size_t stage_bytes = (size_t)planes * n_seg * 2 * op.seg_len * 16;
   const size_t budget = 227 * 1024 - 1024;
+  // k-slabs per stage: as many as leave room for three stages (fewer ring hand-shakes per tile; the single-plane 64-channel
+  // layers fit a whole tile -- 4 slabs -- per stage, the (hi, lo) ones one slab)
+  size_t stage_bytes = 0;
+  for (int ks = 4; ks >= 1; ks >>= 1) {
+    if ((d.k_pad / 16) % ks) continue;
+    stage_bytes = (size_t)planes * (((size_t)ks * n_seg * 2 * op.seg_len * 16 + 127) & ~(size_t)127);
+    op.kslabs = ks;
+    if (b_bytes + 3 * stage_bytes <= budget) break;
+  }
   if (b_bytes + 3 * stage_bytes > budget) return 0;
   op.nstage = (int)std::min<size_t>(8, (budget - b_bytes) / stage_bytes);
   return b_bytes + (size_t)op.nstage * stage_bytes + 1024;

@@ -22,6 +22,35 @@
 #pragma once
 #include "sm100.cuh"
 
+// Profiling builds only (tools/ablate.py): bit 1 = no epilogue work, 2 = A tiles loaded once, 4 = no MMAs, in the tap-fused
+// kernel.  The shipped library is built with 0 and none of the branches exist in it.
+#ifndef GPEMSR_ABLATE
+#define GPEMSR_ABLATE 0
+#endif
+#ifndef GPEMSR_L2_PREFETCH
+#define GPEMSR_L2_PREFETCH 1
+#endif
+
+// bit 8: per-role cycle accounting (clock64 around every barrier wait), printed by CTA 0 and CTA 77 at kernel end
+#if GPEMSR_ABLATE & 8
+#include <cstdio>
+__device__ __forceinline__ unsigned long long prof_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GPEMSR_PROF_DECL long long prof_w[2] = {0, 0}, prof_work = 0, prof_t0 = 0, prof_t1 = clock64(), prof_n = 0; const long long prof_start = prof_t1; \
+    const unsigned long long prof_ns0 = prof_ns();
+#define GPEMSR_PROF_T0 prof_t0 = clock64();
+#define GPEMSR_PROF_WAIT(i) prof_t1 = clock64(); prof_w[i] += prof_t1 - prof_t0;
+#define GPEMSR_PROF_WORK prof_work += clock64() - prof_t1; ++prof_n;
+#define GPEMSR_PROF_PRINT(a, b, c) if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) \
+    printf("cta %3d warp %2d  total %8lld cycles in %7llu ns, %5lld trips | %s %8lld | %s %8lld | %s %8lld\n", (int)blockIdx.x, warp, \
+           clock64() - prof_start, prof_ns() - prof_ns0, prof_n, a, prof_w[0], b, prof_w[1], c, prof_work);
+#else
+#define GPEMSR_PROF_DECL
+#define GPEMSR_PROF_T0
+#define GPEMSR_PROF_WAIT(i)
+#define GPEMSR_PROF_WORK
+#define GPEMSR_PROF_PRINT(a, b, c)
+#endif
+
 namespace gemm {
 
 constexpr int BLOCK_M = 128;
@@ -54,6 +83,7 @@ struct Operands {
   int tap_seg[MAX_TAPS];       // segment of tap t
   int tap_dx[MAX_TAPS];        // row offset of tap t inside its segment (dx - dx_min)
   int nstage;                  // smem stages that fit next to the resident B
+  int kslabs;                  // 16-wide k-slabs per stage (1, 2 or 4): fewer, larger stages when shared memory allows
   // ---- dy-fused mode (gemm_dyfuse_kernel): large tap grids (7x7), weights streamed per (k-slab, dy)
   int n_dy, n_dx;              // taps = n_dy * n_dx, ordered dy-major
   int dy_row_off[8];           // first A row of the dy-th segment relative to the tile's first row (dy * wp + dx_min)
@@ -73,6 +103,12 @@ struct Config {
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /* barriers, tmem ptr, epilogue scratch */;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+// Tensor maps of the A planes (hi, lo) of a tap-fused / dy-fused launch; use == 0: the kernel issues plain bulk copies.
+struct TmaMaps {
+  sm100::TensorMap a[2];
+  int use;
 };
 
 struct Barriers {
@@ -442,7 +478,7 @@ gemm_ares_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
 // layers go from L2-operand-bound to MMA/epilogue-bound.
 template <int BLOCK_N, int SPLIT, class Epi>
 __global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
-gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
+gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi, const __grid_constant__ TmaMaps tm) {
   constexpr int PLANES = SPLIT == 3 ? 2 : 1;
   constexpr int KCH = 2;                                   // one UMMA k-step (16 bf16) per stage
   // SPLIT == 3 pairs the two products that share the A operand: a_hi * [w_hi | w_lo] is ONE MMA with N = 2 * BLOCK_N (the hi and
@@ -455,14 +491,21 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
   const uint32_t b_tap_bytes = (uint32_t)kcells * BLOCK_N * 16;               // one tap, one plane
   const uint32_t b_bytes = (uint32_t)PLANES * op.taps * b_tap_bytes;
   const uint32_t seg_bytes = (uint32_t)op.seg_len * 16;                       // one 16-byte k-cell column of a segment
-  const uint32_t a_plane_bytes = (uint32_t)op.n_seg * KCH * seg_bytes;
+  // a stage plane is [k-cell][segment][row][8] (the box order of the tensor map: ascending global stride), padded to the 128-byte
+  // alignment a TMA destination needs
+  // A stage carries S = op.kslabs k-slabs (2 * S cell columns): the ring hand-shake (commit -> empty -> refill -> full) costs the
+  // issuing threads a few hundred cycles per stage, as much as the 9 N = 64 MMAs of a single-plane slab take (432 cycles).
+  const int S = op.kslabs;
+  const uint32_t slab_bytes = (uint32_t)op.n_seg * KCH * seg_bytes;           // one k-slab of one plane
+  const uint32_t a_box_bytes = (uint32_t)S * slab_bytes;
+  const uint32_t a_plane_bytes = (a_box_bytes + 127u) & ~127u;
   const uint32_t stage_bytes = PLANES * a_plane_bytes;
   uint8_t* b_res = smem;
   uint8_t* stages = smem + ((b_bytes + 1023) & ~1023u);
   Barriers* bars = reinterpret_cast<Barriers*>(stages + (size_t)op.nstage * stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kiters = op.k / 16;
+  const int kiters = op.k / 16 / S;
   const int nstage = op.nstage;
 
   if (threadIdx.x == 0) {
@@ -481,38 +524,78 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
   if (warp == 0) {
     // ===================== producer =====================
     bool ok = true;
-    if (blockIdx.x < op.m_tiles) {
-      if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->b_full, b_bytes);
-      __syncwarp();
-      const int ncopies = PLANES * op.taps * kcells;
-      for (int c = lane; c < ncopies; c += 32) {
-        const int plane = c / (op.taps * kcells), r = c % (op.taps * kcells);      // r = tap * kcells + kc
-        const __nv_bfloat16* src = (plane ? op.b_lo : op.b_hi) + (long long)r * op.b_rows * 8;
-        sm100::bulk_g2s(b_res + ((size_t)r * PLANES + plane) * BLOCK_N * 16, src, BLOCK_N * 16, &bars->b_full);   // [tap][kc][plane][n]
+    // ONE elected thread runs the whole refill loop.  UBLKCP takes its addresses from uniform registers: issued from a converged
+    // single-thread region it is a plain instruction, while "one copy per lane" compiles to an ELECT / R2UR.BROADCAST / BRA.U.ANY
+    // loop that serialises the lanes at ~50 cycles each -- 12 copies per stage were ~730 cycles of the refill latency, and for
+    // the single-plane (split 1) layers more than the 432 tensor cycles the stage feeds (profiles/r02_tapfuse_roles.txt).
+    if (sm100::elect_one()) {
+      if (tm.use) {
+#pragma unroll
+        for (int plane = 0; plane < PLANES; ++plane) sm100::tma_prefetch_desc(&tm.a[plane]);
       }
-    }
-    uint32_t stage = 0, phase = 0;
-    // one copy slot per lane, source pointer advanced incrementally (the producer warp is on the critical path)
-    const int ncopies = PLANES * op.n_seg * KCH;
-    const bool active = lane < ncopies;
-    const int cplane = lane / (op.n_seg * KCH), cr = lane % (op.n_seg * KCH), cseg = cr / KCH, ckc = cr % KCH;
-    const uint32_t sm_off = (uint32_t)lane * seg_bytes;
-    const long long a_kstep = (long long)KCH * op.a_rows * 8;
-    const __nv_bfloat16* a_base = (cplane ? op.a_lo : op.a_hi) +
-                                  ((long long)ckc * op.a_rows + op.a_row0 + (active ? op.seg_row_off[cseg] : 0)) * 8;
-    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-      const __nv_bfloat16* src = a_base + m_tile * (BLOCK_M * 8);
-      for (int it = 0; it < kiters && ok; ++it) {
-        ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
-        if (!ok) break;
-        uint8_t* sa = stages + (size_t)stage * stage_bytes;
-        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
-        __syncwarp();
-        if (active) sm100::bulk_g2s(sa + sm_off, src, seg_bytes, &bars->full[stage]);
-        src += a_kstep;
-        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+      if (blockIdx.x < op.m_tiles) {
+        // the resident weights: one 1 KB .. 4 KB block per (tap, k-cell, plane) into the [tap][kc][plane][n] layout
+        sm100::mbar_arrive_expect_tx(&bars->b_full, b_bytes);
+        const int nblk = op.taps * kcells;
+        for (int r = 0; r < nblk; ++r) {                    // r = tap * kcells + kc
+#pragma unroll
+          for (int plane = 0; plane < PLANES; ++plane)
+            sm100::bulk_g2s(b_res + ((size_t)r * PLANES + plane) * BLOCK_N * 16, (plane ? op.b_lo : op.b_hi) + (long long)r * op.b_rows * 8,
+                            BLOCK_N * 16, &bars->b_full);
+        }
       }
+      uint32_t stage = 0, phase = 0;
+      const long long a_kstep = (long long)S * KCH * op.a_rows * 8;
+      GPEMSR_PROF_DECL
+      for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+        const long long row0 = op.a_row0 + m_tile * BLOCK_M;
+        for (int it = 0; it < kiters && ok; ++it) {
+          GPEMSR_PROF_T0
+          ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+          GPEMSR_PROF_WAIT(0)
+          if (!ok) break;
+          uint8_t* sa = stages + (size_t)stage * stage_bytes;
+#if GPEMSR_ABLATE & 2
+          if (m_tile != blockIdx.x) sm100::mbar_arrive(&bars->full[stage]); else     // profiling build: A loaded for the first tile only
+#endif
+          {
+            sm100::mbar_arrive_expect_tx(&bars->full[stage], PLANES * a_box_bytes);
+            if (tm.use) {
+              // one box per plane, 8-byte elements: {seg_len, 2 halves, n_seg segments, 2 * S cells} at (2 * first row of segment 0, 0, 0, k-cell)
+#pragma unroll
+              for (int plane = 0; plane < PLANES; ++plane)
+                sm100::tma_load_4d(sa + plane * a_plane_bytes, &tm.a[plane], (int)(2 * (row0 + op.seg_row_off[0])), 0, 0, it * S * KCH, &bars->full[stage]);
+#if GPEMSR_L2_PREFETCH
+              // the same k-slab of this CTA's NEXT tile, DRAM -> L2: the stage ring holds ~2 stages (50 KB) in flight, not enough to
+              // cover the DRAM latency at the rate the MMAs consume them; from L2 it is
+              if (m_tile + gridDim.x < op.m_tiles) {
+#pragma unroll
+                for (int plane = 0; plane < PLANES; ++plane)
+                  sm100::tma_prefetch_l2_4d(&tm.a[plane], (int)(2 * (row0 + (long long)gridDim.x * BLOCK_M + op.seg_row_off[0])), 0, 0, it * S * KCH);
+              }
+#endif
+            } else {
+#pragma unroll
+              for (int plane = 0; plane < PLANES; ++plane) {
+                const __nv_bfloat16* pb = (plane ? op.a_lo : op.a_hi) + (long long)it * a_kstep;
+                for (int kc = 0; kc < S * KCH; ++kc) {
+#pragma unroll
+                  for (int seg = 0; seg < 3; ++seg) {
+                    if (seg < op.n_seg)
+                      sm100::bulk_g2s(sa + plane * a_plane_bytes + (uint32_t)(kc * op.n_seg + seg) * seg_bytes,
+                                      pb + ((long long)kc * op.a_rows + row0 + op.seg_row_off[seg]) * 8, seg_bytes, &bars->full[stage]);
+                  }
+                }
+              }
+            }
+          }
+          if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+          GPEMSR_PROF_WORK
+        }
+      }
+      GPEMSR_PROF_PRINT("producer: wait empty", "-", "issue copies")
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = sm100::idesc_bf16_f32(BLOCK_M, BLOCK_N);
@@ -524,87 +607,117 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     // per-tap start-address offsets (16-byte units): [2t] = A (segment + dx shift), [2t+1] = B (tap block)
     uint32_t* tap_tab = bars->tap_tab;
     for (int t = lane; t < op.taps; t += 32) {
-      tap_tab[2 * t] = ((uint32_t)(op.tap_seg[t] * KCH) * seg_bytes + (uint32_t)op.tap_dx[t] * 16) >> 4;
+      tap_tab[2 * t] = ((uint32_t)op.tap_seg[t] * seg_bytes + (uint32_t)op.tap_dx[t] * 16) >> 4;
       tap_tab[2 * t + 1] = ((uint32_t)t * PLANES * b_tap_bytes) >> 4;
     }
     __syncwarp();
     constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1
-    const uint32_t a_desc_lo = ((seg_bytes >> 4) & 0x3FFFu) << 16;           // LBO = one k-cell column of a segment
+    const uint32_t a_desc_lo = ((((uint32_t)op.n_seg * seg_bytes) >> 4) & 0x3FFFu) << 16;    // LBO = the next k-cell: n_seg segments further
     const uint32_t b_desc_lo = (((uint32_t)PLANES * BLOCK_N * 16 >> 4) & 0x3FFFu) << 16;      // LBO: the next k-cell's [plane][n] block
     // a full 3x3 tap grid in dy-major order: segments of BLOCK_M + 2 rows, tap (dy, dx) at segment dy, row dx
     bool is3x3 = op.taps == 9 && op.n_seg == 3 && op.seg_len == BLOCK_M + 2;
     for (int t = 0; t < 9 && is3x3; ++t) is3x3 = op.tap_seg[t] == t / 3 && op.tap_dx[t] == t % 3;
+    // ONE elected thread runs the whole loop.  The tensor pipe queues only a few MMAs, so whatever the issuing thread does
+    // between the last MMA of a stage and the first of the next is a bubble: the barrier of the NEXT stage (and, on the last
+    // k-slab, the next accumulator buffer) is probed while this stage's MMAs are still being issued, and the blocking wait runs
+    // only when that probe failed.
+    if (sm100::elect_one()) {
+    GPEMSR_PROF_DECL
+    bool full_ready = false, acc_ready = false;
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-      ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+      GPEMSR_PROF_T0
+      if (!acc_ready) ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+      GPEMSR_PROF_WAIT(1)
       if (!ok) break;
       sm100::tc_fence_after();
+      acc_ready = false;
       const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N);
       for (int it = 0; it < kiters && ok; ++it) {
-        ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+        GPEMSR_PROF_T0
+        if (!full_ready) ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+        GPEMSR_PROF_WAIT(0)
         if (!ok) break;
         sm100::tc_fence_after();
-        if (sm100::elect_one()) {
-          // descriptors differ from a per-stage base only in the 14-bit start-address field (16-byte units): the issuing
-          // thread -- the serial bottleneck of this loop -- does two adds per MMA, offsets come from a smem table
-          const uint32_t a_lo0 = a_desc_lo + (sm100::smem_u32(stages + (size_t)stage * stage_bytes) >> 4);
-          const uint32_t b_lo0 = b_desc_lo + ((sb0 + (uint32_t)(it * KCH) * (PLANES * BLOCK_N * 16)) >> 4);
+        const uint32_t nstg = stage + 1 == (uint32_t)nstage ? 0 : stage + 1, nph = stage + 1 == (uint32_t)nstage ? phase ^ 1 : phase;
+        for (int sl = 0; sl < S; ++sl) {
+          // descriptors differ from a per-slab base only in the 14-bit start-address field (16-byte units): two adds per MMA
+          const uint32_t a_lo0 = a_desc_lo + ((sm100::smem_u32(stages + (size_t)stage * stage_bytes) + (uint32_t)sl * slab_bytes) >> 4);
+          const uint32_t b_lo0 = b_desc_lo + ((sb0 + (uint32_t)((it * S + sl) * KCH) * (PLANES * BLOCK_N * 16)) >> 4);
+          const bool last_slab = sl == S - 1;
+#if GPEMSR_ABLATE & 4
+          if (false) {                                     // profiling build: no MMAs, only the commits
+#else
           if (is3x3) {
+#endif
             // The 3x3 case (every 64-channel convolution of the model): the nine start-address offsets are compile-time
-            // constants (segment dy at 2 * 130 cell rows, dx = one row), so the fully unrolled loop is an add-immediate per
-            // descriptor.  The ISSUING THREAD bounds these kernels (ncu source view: it never waits and needs ~108 cycles per MMA
-            // through the table-driven loop while the tensor pipe is busy ~49), so every instruction here counts.
+            // constants (segment dy at 130 cell rows, dx = one row), so the fully unrolled loop is an add-immediate per
+            // descriptor.
             const uint32_t b_tap16 = ((uint32_t)PLANES * b_tap_bytes) >> 4, a_pl16 = a_plane_bytes >> 4;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              const uint32_t a_lo = a_lo0 + (uint32_t)((t / 3) * (KCH * (BLOCK_M + 2)) + t % 3), b_lo = b_lo0 + (uint32_t)t * b_tap16;
+              const uint32_t a_lo = a_lo0 + (uint32_t)((t / 3) * (BLOCK_M + 2) + t % 3), b_lo = b_lo0 + (uint32_t)t * b_tap16;
               const uint64_t a_hi_d = ((uint64_t)kDescHi << 32) | a_lo, b_hi_d = ((uint64_t)kDescHi << 32) | b_lo;
               if constexpr (SPLIT == 3) {
                 const uint64_t a_lo_d = ((uint64_t)kDescHi << 32) | (a_lo + a_pl16);
-                sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc_pair, (it | t) != 0);    // a_hi * [w_hi | w_lo]
-                sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);                  // a_lo * w_hi
+                sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc_pair, (it | sl | t) != 0);    // a_hi * [w_hi | w_lo]
+                sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);                       // a_lo * w_hi
               } else {
-                sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
+                sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | sl | t) != 0);
               }
+              if (t == 5 && last_slab) full_ready = sm100::mbar_try_wait(&bars->full[nstg], nph);
             }
           } else {
-          for (int t = 0; t < op.taps; ++t) {
+          for (int t = 0; t < (GPEMSR_ABLATE & 4 ? 0 : op.taps); ++t) {
             const uint32_t a_lo = a_lo0 + tap_tab[2 * t], b_lo = b_lo0 + tap_tab[2 * t + 1];
             const uint64_t a_hi_d = ((uint64_t)kDescHi << 32) | a_lo, b_hi_d = ((uint64_t)kDescHi << 32) | b_lo;
             if constexpr (SPLIT == 3) {
               const uint64_t a_lo_d = ((uint64_t)kDescHi << 32) | (a_lo + (a_plane_bytes >> 4));
-              sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc_pair, (it | t) != 0);      // a_hi * [w_hi | w_lo]
-              sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);                    // a_lo * w_hi
+              sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc_pair, (it | sl | t) != 0);      // a_hi * [w_hi | w_lo]
+              sm100::umma_bf16(tmem_acc, a_lo_d, b_hi_d, idesc, true);                         // a_lo * w_hi
             } else {
-              sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | t) != 0);
+              sm100::umma_bf16(tmem_acc, a_hi_d, b_hi_d, idesc, (it | sl | t) != 0);
             }
           }
+          if (last_slab) full_ready = sm100::mbar_try_wait(&bars->full[nstg], nph);
           }
+          if (!last_slab) continue;
           sm100::umma_commit(&bars->empty[stage]);
-          if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
+          if (it == kiters - 1) {
+            sm100::umma_commit(&bars->tmem_full[acc_buf]);
+            acc_ready = sm100::mbar_try_wait(&bars->tmem_empty[acc_buf ^ 1], acc_buf == 1 ? acc_phase : acc_phase ^ 1);
+          }
         }
-        __syncwarp();
-        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+        stage = nstg; phase = nph;
+        GPEMSR_PROF_WORK
       }
       if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
     }
+    GPEMSR_PROF_PRINT("mma: wait full", "wait tmem_empty", "issue + commit")
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t acc_buf = 0, acc_phase = 0;
     bool ok = true;
+    GPEMSR_PROF_DECL
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
       typename Epi::State st{};
+      GPEMSR_PROF_T0
       ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+      GPEMSR_PROF_WAIT(0)
       if (!ok) break;
       sm100::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-      epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);
+      if (!(GPEMSR_ABLATE & 1)) epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);     // profiling build: no epilogue work
       sm100::tc_fence_before();
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
       if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+      GPEMSR_PROF_WORK
     }
+    if (warp == 2 || warp == 2 + Epi::WARPS - 1) { GPEMSR_PROF_PRINT("epilogue: wait tmem_full", "-", "tile") }
   }
 
   sm100::tc_fence_before();
@@ -625,12 +738,12 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
 // of n_dy * n_dx times; a stage carries n_dx * SPLIT MMAs.
 template <int BLOCK_N, int SPLIT, class Epi>
 __global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
-gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi) {
+gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi, const __grid_constant__ TmaMaps tm) {
   constexpr int PLANES = SPLIT == 3 ? 2 : 1;
   constexpr int NMUL = SPLIT == 3 ? 2 : 1;                 // paired-N MMAs, see gemm_tapfuse_kernel
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t seg_bytes = (uint32_t)op.seg_len * 16;                       // one 16-byte k-cell column of the segment
-  const uint32_t a_plane_bytes = 2 * seg_bytes;
+  const uint32_t a_plane_bytes = (2 * seg_bytes + 127u) & ~127u;              // [cell][row][8], padded: a TMA destination is 128-byte aligned
   const uint32_t a_bytes = PLANES * a_plane_bytes;
   const uint32_t b_tap_bytes = PLANES * 2 * BLOCK_N * 16;                     // one tap, one k-slab: [cell][plane][n][8]
   const uint32_t b_bytes = (uint32_t)op.n_dx * b_tap_bytes;
@@ -655,32 +768,43 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================== producer: lanes 0 .. 2*PLANES-1 copy the A cell columns, the next lane the weight block ======
-    bool ok = true;
-    uint32_t stage = 0, phase = 0;
-    const bool is_a = lane < 2 * PLANES, is_b = lane == 2 * PLANES;
-    const int plane = lane >> 1, cell = lane & 1;
-    const long long a_slab = 2LL * op.a_rows * 8;                               // elements per k-slab advance of A
-    const __nv_bfloat16* a_base = is_a ? (plane ? op.a_lo : op.a_hi) + ((long long)cell * op.a_rows + op.a_row0) * 8 : nullptr;
-    for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-      const __nv_bfloat16* b_src = op.b_hi;
-      int slab = 0, dyi = 0;
-      for (int it = 0; it < kiters && ok; ++it) {
-        ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
-        if (!ok) break;
-        uint8_t* st = stages + (size_t)stage * stage_bytes;
-        if (lane == 0) sm100::mbar_arrive_expect_tx(&bars->full[stage], stage_bytes);
-        __syncwarp();
-        if (is_a)
-          sm100::bulk_g2s(st + (uint32_t)lane * seg_bytes, a_base + slab * a_slab + (m_tile * BLOCK_M + op.dy_row_off[dyi]) * 8,
-                          seg_bytes, &bars->full[stage]);
-        else if (is_b)
+    // ===================== producer (one elected thread, see gemm_tapfuse_kernel): 2 * PLANES A cell columns + the weight block
+    if (sm100::elect_one()) {
+      bool ok = true;
+      uint32_t stage = 0, phase = 0;
+      const long long a_slab = 2LL * op.a_rows * 8;                               // elements per k-slab advance of A
+      for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
+        const __nv_bfloat16* b_src = op.b_hi;
+        const long long row0 = op.a_row0 + m_tile * BLOCK_M;
+        int slab = 0, dyi = 0;
+        for (int it = 0; it < kiters && ok; ++it) {
+          ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+          if (!ok) break;
+          uint8_t* st = stages + (size_t)stage * stage_bytes;
+          sm100::mbar_arrive_expect_tx(&bars->full[stage], PLANES * 2 * seg_bytes + b_bytes);
+          if (tm.use) {
+            // one box per plane, 8-byte elements: {seg_len, 2 halves, 2 cells} at (2 * first row of this dy, 0, first cell of the slab)
+#pragma unroll
+            for (int plane = 0; plane < PLANES; ++plane)
+              sm100::tma_load_3d(st + plane * a_plane_bytes, &tm.a[plane], (int)(2 * (row0 + op.dy_row_off[dyi])), 0, slab * 2, &bars->full[stage]);
+          } else {
+            const long long a_off = slab * a_slab + (row0 + op.dy_row_off[dyi]) * 8;
+#pragma unroll
+            for (int plane = 0; plane < PLANES; ++plane) {
+#pragma unroll
+              for (int cell = 0; cell < 2; ++cell)
+                sm100::bulk_g2s(st + plane * a_plane_bytes + (uint32_t)cell * seg_bytes, (plane ? op.a_lo : op.a_hi) + a_off + (long long)cell * op.a_rows * 8,
+                                seg_bytes, &bars->full[stage]);
+            }
+          }
           sm100::bulk_g2s(st + a_bytes, b_src, b_bytes, &bars->full[stage]);
-        b_src += b_bytes / 2;
-        if (++dyi == op.n_dy) { dyi = 0; ++slab; }
-        if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+          b_src += b_bytes / 2;
+          if (++dyi == op.n_dy) { dyi = 0; ++slab; }
+          if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+        }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected thread) =====================
     if (sm100::elect_one()) {
@@ -696,15 +820,19 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
       const uint32_t a_lo_base = (((seg_bytes >> 4) & 0x3FFFu) << 16) | (sm100::smem_u32(stages) >> 4);
       const uint32_t b_lo_base = ((((uint32_t)PLANES * BLOCK_N * 16 >> 4) & 0x3FFFu) << 16) | ((sm100::smem_u32(stages) + a_bytes) >> 4);
       const uint32_t a_pl = a_plane_bytes >> 4, b_tap = b_tap_bytes >> 4;
+      // the next stage's barrier (and the next accumulator's) is probed while this stage's MMAs are in flight, see gemm_tapfuse_kernel
+      bool full_ready = false, acc_ready = false;
       for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-        ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+        if (!acc_ready) ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
         if (!ok) break;
         sm100::tc_fence_after();
+        acc_ready = false;
         const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N);
         for (int it = 0; it < kiters && ok; ++it) {
-          ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
+          if (!full_ready) ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
           if (!ok) break;
           sm100::tc_fence_after();
+          const uint32_t nstg = stage + 1 == (uint32_t)nstage ? 0 : stage + 1, nph = stage + 1 == (uint32_t)nstage ? phase ^ 1 : phase;
           uint32_t a = a_lo_base + stage * (stage_bytes >> 4);
           uint32_t b = b_lo_base + stage * (stage_bytes >> 4);
           // one tap = one 16-byte row of A and one weight block of B.  The issuing thread bounds the narrow kernels, so the two tap
@@ -721,16 +849,20 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
           };
           if (op.n_dx == 3) {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) issue(dx);
+            for (int dx = 0; dx < 3; ++dx) { issue(dx); if (dx == 1) full_ready = sm100::mbar_try_wait(&bars->full[nstg], nph); }
           } else if (op.n_dx == 7) {
 #pragma unroll
-            for (int dx = 0; dx < 7; ++dx) issue(dx);
+            for (int dx = 0; dx < 7; ++dx) { issue(dx); if (dx == 4) full_ready = sm100::mbar_try_wait(&bars->full[nstg], nph); }
           } else {
             for (int dx = 0; dx < op.n_dx; ++dx) issue(dx);
+            full_ready = sm100::mbar_try_wait(&bars->full[nstg], nph);
           }
           sm100::umma_commit(&bars->empty[stage]);
-          if (it == kiters - 1) sm100::umma_commit(&bars->tmem_full[acc_buf]);
-          if (++stage == (uint32_t)nstage) { stage = 0; phase ^= 1; }
+          if (it == kiters - 1) {
+            sm100::umma_commit(&bars->tmem_full[acc_buf]);
+            acc_ready = sm100::mbar_try_wait(&bars->tmem_empty[acc_buf ^ 1], acc_buf == 1 ? acc_phase : acc_phase ^ 1);
+          }
+          stage = nstg; phase = nph;
         }
         if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
       }

@@ -65,6 +65,9 @@ GPEMSR_API int         gpemsr_version(void);                  /* 0xMMmmpp */
 GPEMSR_API const char* gpemsr_last_error_string(void);
 GPEMSR_API int         gpemsr_device_check(int device);       /* OK iff `device` is sm_100-class */
 GPEMSR_API int64_t     gpemsr_kernel_launches(void);          /* kernels launched by this library so far (process-wide) */
+/* Tensor maps (TMA descriptors of the activation tiles of the tap-fused / dy-fused GEMMs) encoded so far, and shapes the driver
+ * refused (those launches ran the bulk-copy producer instead).  GPEMSR_TMA=0 in the environment disables them (A/B timing). */
+GPEMSR_API void        gpemsr_tensor_map_stats(int64_t* built, int64_t* rejected);
 
 /* ---- a-5: flow_warp -------------------------------------------------------------------
  * Replaces basicsr.archs.arch_util.flow_warp (third-party; reached from model/GPEMSR.py:99-100

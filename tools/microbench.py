@@ -65,25 +65,31 @@ def conv_bench(which=None):
     cases = [('rb512_80', 5, 512, 512, 80, 3, {}), ('rb256_160', 5, 256, 256, 160, 3, {}), ('rb128_320', 5, 128, 128, 320, 3, {}),
              ('rb64_640', 5, 64, 64, 640, 3, {}), ('hr64_1280', 1, 64, 64, 1280, 3, dict(act=G.ACT_LRELU, slope=0.1)),
              ('up256_640', 1, 64, 256, 640, 3, dict(ps=True)), ('out1_1280', 5, 64, 1, 1280, 3, dict(nchw=True)),
-             ('q512_80', 5, 512, 512, 80, 1, {})]
+             ('q512_80', 5, 512, 512, 80, 1, {}),
+             ('vgg64_1280', 2, 64, 64, 1280, 3, dict(split=1, act=G.ACT_RELU, planes_only=True)),      # VGG conv1_2, one bf16 pass
+             ('hr64_1280p', 1, 64, 64, 1280, 3, dict(act=G.ACT_LRELU, slope=0.1, planes_only=True)),     # (hi, lo) planes out, no fp32 copy
+             ('spy7x7_320', 5, 32, 64, 320, 7, dict(split=1, act=G.ACT_RELU, planes_only=True))]         # a SpyNet 7x7 layer (dy-fused kernel)
     out = []
     err = torch.zeros(1, dtype=torch.int32, device='cuda')
     for name, n, ci, co, s, ks, opt in cases:
         if which and name not in which:
             continue
-        g = G.Geom(n, s, s, True)
+        g = G.Geom(n, s, s, ks // 2 if ks > 1 else True)
         x = G.Act(g, ci, 'cuda', f32=False)
         x.hi.normal_(); x.lo.normal_(std=0.004)
         w = torch.randn(co, ci, ks, ks, device='cuda') * 0.05
         b = torch.randn(co, device='cuda')
         wt = G.Weights(w, 'conv')
-        kw = dict(split=3, bias=b, act=opt.get('act', G.ACT_NONE), slope=opt.get('slope', 0.0))
+        kw = dict(split=opt.get('split', 3), bias=b, act=opt.get('act', G.ACT_NONE), slope=opt.get('slope', 0.0))
         if opt.get('ps'):
             y = G.Act(G.Geom(n, 2 * s, 2 * s, True), co // 4, 'cuda', f32=False)
             fn = lambda: G.igemm(x, wt, err, out=y, up=2, pixel_shuffle=True, out_f32=False, **kw)
         elif opt.get('nchw'):
             img = torch.empty(n, co, s, s, device='cuda')
             fn = lambda: G.igemm(x, wt, err, out_nchw=img, nchw_c=co, **kw)
+        elif opt.get('planes_only'):
+            y = G.Act(g, co, 'cuda', f32=False)
+            fn = lambda: G.igemm(x, wt, err, out=y, out_f32=False, **kw)
         else:
             y = G.Act(g, co, 'cuda', f32=True)
             fn = lambda: G.igemm(x, wt, err, out=y, **kw)
@@ -93,6 +99,12 @@ def conv_bench(which=None):
                         frac_of_split3_ceiling=fl / med / 1e9 / (1388.4 / 3)))
         del x, wt
     assert int(err.item()) == 0
+    import ctypes
+    from gpemsr_b200 import _lib
+    built, rej = ctypes.c_int64(0), ctypes.c_int64(0)
+    if hasattr(_lib.lib(), 'gpemsr_tensor_map_stats'):
+        _lib.lib().gpemsr_tensor_map_stats(ctypes.byref(built), ctypes.byref(rej))
+        print(json.dumps(dict(tensor_maps_built=built.value, tensor_maps_rejected=rej.value)), file=sys.stderr)
     return out
 
 
