@@ -49,6 +49,12 @@ bool use_clusters() {
   return v != 0;
 }
 
+bool use_pair_mma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPEMSR_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 bool use_tensor_maps() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPEMSR_TMA"); v = (e && e[0] == '0') ? 0 : 1; }

@@ -15,6 +15,7 @@ extern std::atomic<long long> g_launches;   // kernels launched by this library
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();
 bool use_clusters();                      // GPEMSR_CLUSTER=0 disables the cluster-multicast kernels (A/B testing)
+bool use_pair_mma();                      // GPEMSR_PAIR=0: the wide streaming GEMMs stay on cta_group::1 + multicast (A/B testing)
 bool use_tensor_maps();                   // GPEMSR_TMA=0: activation tiles by plain bulk copies instead of tensor-map TMA (A/B testing)
 
 using TensorMap = sm100::TensorMap;      // a CUtensorMap as an opaque kernel parameter

@@ -53,6 +53,11 @@ struct EpiConv {
   // split-3 / single-pass 64-channel convs.  (Measured and dropped: 16 warps on the N >= 128 tiles -- the 112-register cap spills and the
   // wide kernels get 2-4 % slower.)
   static constexpr int WARPS = BLOCK_N == 64 ? 16 : BLOCK_N >= 128 ? 8 : BLOCK_N == 32 ? 8 : 4;
+  // In the tap-fused / dy-fused kernels (one column tile per row tile) the epilogue warps form GROUPS groups that own one TMEM
+  // accumulator buffer each and take alternate tiles: TWO tile epilogues are in flight.  An epilogue alone needs ~3 400 cycles per
+  // tile whatever the warp count (a latency chain: barrier wake-up, bias loads, TMEM loads, stores, fence, arrive), more than the
+  // MMAs of a single-plane tile; tools/ablate.py: the VGG layer ran 0.417 ms with and 0.277 ms without its epilogue.
+  static constexpr int GROUPS = (BLOCK_N == 64 || BLOCK_N == 32) ? 2 : 1;
   struct State {
     bool init = false, valid = false;
     int img = 0, y = 0, x = 0;
@@ -267,6 +272,14 @@ struct EpiConv {
   }
 
   __device__ __forceinline__ void tile(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int part) const {
+    tile_span<BLOCK_N / (WARPS / 4)>(st, tmem_acc, m_tile, n_tile, n_tiles, row, part);
+  }
+  // the same with the columns split over the warps of ONE group (WARPS / GROUPS warps per tile)
+  __device__ __forceinline__ void tile_group(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int part) const {
+    tile_span<BLOCK_N / (WARPS / GROUPS / 4)>(st, tmem_acc, m_tile, n_tile, n_tiles, row, part);
+  }
+  template <int SPAN>                                    // SPAN = columns this warp covers
+  __device__ __forceinline__ void tile_span(State& st, uint32_t tmem_acc, long long m_tile, int n_tile, int n_tiles, int row, int part) const {
     const long long rel = m_tile * gemm::BLOCK_M + row;
     if (!st.init) {
       st.init = true;
@@ -281,8 +294,7 @@ struct EpiConv {
         if (row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
       }
     }
-    constexpr int SPAN = BLOCK_N / (WARPS / 4);          // columns this warp covers
-    constexpr int CHUNK = SPAN >= 32 ? 32 : 16;
+    constexpr int CHUNK = (SPAN >= 32 && BLOCK_N >= 128) ? 32 : 16;     // the narrow kernels run 18 warps: 16 columns at a time fit their registers
     const bool row_stats = (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
 #pragma unroll 1
     for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
@@ -383,6 +395,37 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
         const double cost = (double)waves * ((double)per + overhead);
         if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && (y < gy || (y == gy && x > gx)))) { best = cost; gx = x; gy = y; }
       }
+  }
+  if constexpr (BLOCK_N == 256) {
+    // CTA-pair MMAs (cta_group::2): packed weights, no per-tile weight batches, operands by tensor map
+    if (clustered && d.b_packed == 1 && op.batch_tiles == 0 && gpemsr::use_pair_mma() && gpemsr::use_tensor_maps()) {
+      constexpr int PLANES = SPLIT == 3 ? 2 : 1, KCH = BLOCK_K / 8;
+      constexpr int NST = (227 * 1024 - 1024) / (PLANES * (gemm::BLOCK_M + BLOCK_N / 2) * BLOCK_K * 2) >= 6 ? 6 : 4;
+      constexpr int SMEM = NST * PLANES * (gemm::BLOCK_M + BLOCK_N / 2) * BLOCK_K * 2 + 1024;
+      int off_min = 0, off_max = 0;
+      for (int t = 0; t < op.taps; ++t) { off_min = std::min(off_min, op.a_row_off[t]); off_max = std::max(off_max, op.a_row_off[t]); }
+      gemm::PairMaps tm;
+      bool maps_ok = op.a_row0 + off_min >= 0 && 2 * (op.a_row0 + op.m_tiles * gemm::BLOCK_M + off_max) < (1LL << 31);
+      if (maps_ok) {
+        const unsigned long long adims[2] = {2ull * (unsigned long long)op.a_rows, (unsigned long long)(op.k / 8)};
+        const unsigned long long astr[2] = {0, (unsigned long long)op.a_rows * 16};
+        const unsigned abox[2] = {2 * gemm::BLOCK_M, (unsigned)KCH};
+        const void* abase[2] = {op.a_hi, op.a_lo};
+        for (int p = 0; p < PLANES && maps_ok; ++p) maps_ok = gpemsr::encode_u64_map(&tm.a[p], abase[p], 2, adims, astr, abox);
+        const unsigned long long blocks = (unsigned long long)op.n_tiles * op.taps * (op.k / BLOCK_K);
+        const unsigned long long bdims[3] = {2ull * BLOCK_N, (unsigned long long)(PLANES * KCH), blocks};
+        const unsigned long long bstr[3] = {0, (unsigned long long)BLOCK_N * 16, (unsigned long long)PLANES * KCH * BLOCK_N * 16};
+        const unsigned bbox[3] = {(unsigned)BLOCK_N, (unsigned)(PLANES * KCH), 1};
+        if (maps_ok) maps_ok = gpemsr::encode_u64_map(&tm.b, op.b_hi, 3, bdims, bstr, bbox);
+      }
+      if (maps_ok) {
+        auto kern = gemm::gemm_pair_kernel<BLOCK_N, BLOCK_K, SPLIT, NST, Epi>;
+        GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        GPEMSR_CUDA_OK(gpemsr::launch_cluster(kern, dim3((unsigned)gx, (unsigned)gy), dim3(gemm::num_threads<Epi>()), SMEM, s, 2, op, e, tm));
+        gpemsr::count_launch();
+        return GPEMSR_OK;
+      }
+    }
   }
   if (clustered) {
     // wide tiles are bound by operand traffic out of L2: pairs of CTAs share every B stage by multicast
@@ -756,12 +799,19 @@ __global__ void patch_cosine_kernel(const float* __restrict__ s, long long n, fl
 // channel block (p*2 + q) holds input pixel (2y + p, 2x + q); whole 16-byte cells move, pixels past an odd edge are zero.
 __global__ void space_to_depth_kernel(const uint4* __restrict__ in_hi, const uint4* __restrict__ in_lo, Geom gi, int cells,
                                       uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, Geom go) {
-  const long long hw = (long long)go.h * go.w;
+  const long long hw = (long long)go.h * go.w, total = (long long)go.n * 4 * cells * hw;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (img, phase, cell, pixel): pixel fastest
-  if (t >= (long long)go.n * 4 * cells * hw) return;
-  const long long px = t % hw;
-  const int cc = (int)((t / hw) % cells), ph = (int)((t / (hw * cells)) % 4), img = (int)(t / (hw * cells * 4));
-  const int y = (int)(px / go.w), x = (int)(px % go.w);
+  if (t >= total) return;
+  int cc, ph, img, y, x;
+  if (total < (1LL << 32)) {                 // 32-bit index arithmetic whenever the shape allows (always, in the model)
+    const unsigned tt = (unsigned)t, uhw = (unsigned)hw, q = tt / uhw, px = tt - q * uhw, q2 = q / (unsigned)cells;
+    cc = (int)(q - q2 * (unsigned)cells); ph = (int)(q2 & 3u); img = (int)(q2 >> 2);
+    y = (int)(px / (unsigned)go.w); x = (int)(px - (unsigned)y * (unsigned)go.w);
+  } else {
+    const long long px = t % hw;
+    cc = (int)((t / hw) % cells); ph = (int)((t / (hw * cells)) % 4); img = (int)(t / (hw * cells * 4));
+    y = (int)(px / go.w); x = (int)(px % go.w);
+  }
   const int sy = 2 * y + (ph >> 1), sx = 2 * x + (ph & 1);
   const bool in = sy < gi.h && sx < gi.w;
   const size_t src = (size_t)cc * gi.rows_alloc + (in ? place_row(gi, img, sy, sx) : 0);
@@ -871,13 +921,14 @@ __global__ void gn_scale_shift_kernel(const double* __restrict__ sums, int per_g
 __global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, const float* __restrict__ ss, int act, float slope,
                                   const float* __restrict__ residual, Geom og, float* __restrict__ out_f32,
                                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_nchw) {
-  const long long hw = (long long)g.h * g.w;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (img, cell, pixel)
+  // grid: x = pixels of one image, y = (img, cell) -- the kernel is HBM bound only if the index arithmetic stays out of the way:
+  // the flat (img, cell, pixel) index of round 1 cost three 64-bit divisions per 64 bytes moved
+  const unsigned hw = (unsigned)g.h * (unsigned)g.w;
+  const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hw) return;
   const int cells = (c + 7) / 8;
-  if (t >= (long long)g.n * cells * hw) return;
-  const long long p = t % hw;
-  const int cc = (int)((t / hw) % cells), img = (int)(t / (hw * cells));
-  const int y = (int)(p / g.w), xx = (int)(p % g.w);
+  const int cc = (int)(blockIdx.y % (unsigned)cells), img = (int)(blockIdx.y / (unsigned)cells);
+  const int y = (int)(p / (unsigned)g.w), xx = (int)(p - (unsigned)y * (unsigned)g.w);
   const size_t cell = ((size_t)cc * g.rows_alloc + place_row(g, img, y, xx)) * 8;
   const float4 a = *reinterpret_cast<const float4*>(x + cell), b = *reinterpret_cast<const float4*>(x + cell + 4);
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -1350,8 +1401,9 @@ int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const f
   if (!x_f32 || !g || !og || c <= 0) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: bad arguments");
   if ((rc = check_geom(*g, "affine_act(in)")) != GPEMSR_OK || (rc = check_geom(*og, "affine_act(out)")) != GPEMSR_OK) return rc;
   if (g->n != og->n || g->h != og->h || g->w != og->w) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: geometries differ in shape");
-  const long long total = (long long)g->n * ((c + 7) / 8) * g->h * g->w;
-  affine_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  const long long hw = (long long)g->h * g->w, planes = (long long)g->n * ((c + 7) / 8);
+  if (hw >= (1LL << 31) || planes > 65535) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: %lld pixels x %lld (image, cell) planes exceed the grid", hw, planes);
+  affine_act_kernel<<<dim3((unsigned)((hw + 255) / 256), (unsigned)planes), 256, 0, (cudaStream_t)stream>>>(
       x_f32, c, to_geom(*g), scale_shift, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
       out_nchw);
   GPEMSR_LAUNCH_OK("affine_act_kernel");

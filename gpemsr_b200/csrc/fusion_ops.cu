@@ -45,8 +45,14 @@ __device__ __forceinline__ Lerp lerp_src(int dst, float rscale, int in_size) {
 
 // decode the flat thread index (img, cell, pixel) with the pixel fastest
 __device__ __forceinline__ bool decode_t(long long t, const Geom& g, int cells, int& img, int& cc, int& y, int& x) {
-  const long long hw = (long long)g.h * g.w;
-  if (t >= (long long)g.n * cells * hw) return false;
+  const long long hw = (long long)g.h * g.w, total = (long long)g.n * cells * hw;
+  if (t >= total) return false;
+  if (total < (1LL << 32)) {        // every shape of the model: 32-bit divisions (a 64-bit one is ~4x the instructions, and these
+    const unsigned tt = (unsigned)t, uhw = (unsigned)hw, q = tt / uhw, p = tt - q * uhw;      // kernels move 64 bytes per thread)
+    img = (int)(q / (unsigned)cells); cc = (int)(q - (unsigned)img * (unsigned)cells);
+    y = (int)(p / (unsigned)g.w); x = (int)(p - (unsigned)y * (unsigned)g.w);
+    return true;
+  }
   const long long p = t % hw;
   cc = (int)((t / hw) % cells); img = (int)(t / (hw * cells));
   y = (int)(p / g.w); x = (int)(p % g.w);

@@ -295,6 +295,177 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the streaming kernel (`tcgen05.mma.cta_group::2`, M = 256): the two CTAs of a cluster work on neighbouring
+// row tiles and ONE instruction of the leader drives both tensor cores.  Each CTA keeps its own A tile and only HALF of the B
+// rows (N / 2) in shared memory, so per stage a CTA receives 32 KB instead of 48 KB and the tensor core reads 8 KB instead of
+// 12 KB of operands per MMA: shared memory is what the single-CTA kernel saturates (per stage 6 MMAs x 12 KB read + 48 KB
+// written = 960 cycles at 128 B/clk against 768 cycles of math; profiles/r02_mma_probe.txt).  Six 32 KB stages instead of four 48 KB.
+// Operands arrive by tensor-map TMA (8-byte elements, see encode_u64_map): per stage one box per A plane {128 rows x 4 cells}
+// and one box for this CTA's half of the packed weight block {128 rows x (plane, cell)}: three instructions per stage.
+// Protocol (leader = cluster rank 0):
+//   full[s]       on the leader only: its producer expects the bytes of BOTH CTAs' stage; the peer's TMA loads count down the
+//                 leader's barrier through its cluster address (cp.async.bulk.tensor ... .cta_group::2)
+//   empty[s]      per CTA, released by the leader's tcgen05.commit multicast once the pair's MMAs on the stage have retired
+//   tmem_full[b]  per CTA, same commit multicast after the last k-step
+//   tmem_empty[b] on the leader: all epilogue warps of BOTH CTAs arrive there (the peer's through the cluster address)
+struct PairMaps {
+  sm100::TensorMap a[2];       // A planes: {2 * rows, k-cells}, box {256, BLOCK_K / 8}
+  sm100::TensorMap b;          // packed weights: {2 * BLOCK_N, planes * cells, stage blocks}, box {BLOCK_N, planes * cells, 1}
+};
+
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, class Epi>
+__global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
+gemm_pair_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi, const __grid_constant__ PairMaps tm) {
+  constexpr int PLANES = SPLIT == 3 ? 2 : 1;
+  constexpr int KCH = BLOCK_K / 8;
+  constexpr int A_PLANE_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int BH_PLANE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;           // this CTA's half of the weight rows
+  constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + BH_PLANE_BYTES);
+  constexpr int TMEM_COLS = 2 * BLOCK_N <= 256 ? 256 : 512;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "pair MMA: N multiple of 16 per CTA half");
+  static_assert(NSTAGE * STAGE_BYTES + 1024 <= 227 * 1024, "shared memory budget");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stages = smem;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + NSTAGE * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kiters_per_tap = op.k / BLOCK_K;
+  const int kiters = op.taps * kiters_per_tap;
+  const uint32_t crank = sm100::cluster_ctarank();
+  const bool leader = crank == 0;
+  const long long n_iter = (op.m_tiles + gridDim.x - 1) / gridDim.x;    // identical in both CTAs of a pair (surplus tiles are discarded)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], 2 * Epi::WARPS); }
+    sm100::fence_mbar_init();
+  }
+  if (warp == 1) sm100::tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base);
+  sm100::tc_fence_before();
+  sm100::cluster_sync_all();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer (one elected thread): 2 A boxes + 1 weight box per stage =====================
+    if (sm100::elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+#pragma unroll
+      for (int plane = 0; plane < PLANES; ++plane) sm100::tma_prefetch_desc(&tm.a[plane]);
+      sm100::tma_prefetch_desc(&tm.b);
+      GPEMSR_PROF_DECL
+      for (long long i = 0; i < n_iter && ok; ++i) {
+        const long long m_tile = min(blockIdx.x + i * gridDim.x, op.m_tiles - 1);
+        const long long row0 = op.a_row0 + m_tile * BLOCK_M;
+        for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+          int blk = n_tile * op.taps * kiters_per_tap;                 // packed weight block of (n_tile, tap 0, k-chunk 0)
+          for (int tap = 0; tap < op.taps && ok; ++tap) {
+            const int a_c0 = (int)(2 * (row0 + op.a_row_off[tap]));
+            for (int kci = 0; kci < kiters_per_tap; ++kci, ++blk) {
+              GPEMSR_PROF_T0
+              ok = sm100::mbar_wait(&bars->empty[stage], phase ^ 1, op.err_flag, 1);
+              GPEMSR_PROF_WAIT(0)
+              if (!ok) break;
+              uint8_t* st = stages + stage * STAGE_BYTES;
+              const uint32_t full_leader = sm100::cluster_map(&bars->full[stage], 0);
+              if (leader) sm100::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
+#pragma unroll
+              for (int plane = 0; plane < PLANES; ++plane)
+                sm100::tma_load_2d_pair(st + plane * A_PLANE_BYTES, &tm.a[plane], a_c0, kci * KCH, full_leader);
+              sm100::tma_load_3d_pair(st + PLANES * A_PLANE_BYTES, &tm.b, (int)crank * BLOCK_N, 0, blk, full_leader);
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+              GPEMSR_PROF_WORK
+            }
+          }
+        }
+      }
+      GPEMSR_PROF_PRINT("pair producer: wait empty", "-", "issue loads")
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (sm100::elect_one()) {
+      uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
+      bool ok = true;
+      GPEMSR_PROF_DECL
+      if (leader) {
+        // ===================== MMA issuer of the pair =====================
+        constexpr uint32_t idesc = sm100::idesc_bf16_f32(2 * BLOCK_M, BLOCK_N);
+        const uint64_t a_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages), BLOCK_M * 16, 128);
+        const uint64_t b_desc0 = sm100::smem_desc_kmajor_noswz(sm100::smem_u32(stages) + PLANES * A_PLANE_BYTES, (BLOCK_N / 2) * 16, 128);
+        for (long long i = 0; i < n_iter && ok; ++i) {
+          for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+            GPEMSR_PROF_T0
+            ok = sm100::mbar_wait_cluster(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+            GPEMSR_PROF_WAIT(1)
+            if (!ok) break;
+            sm100::tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
+            for (int it = 0; it < kiters && ok; ++it) {
+              GPEMSR_PROF_T0
+              ok = sm100::mbar_wait_cluster(&bars->full[stage], phase, op.err_flag, 3);
+              GPEMSR_PROF_WAIT(0)
+              if (!ok) break;
+              sm100::tc_fence_after();
+              const uint64_t sa = a_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+              const uint64_t sb = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+#pragma unroll
+              for (int k16 = 0; k16 < BLOCK_K / 16; ++k16) {
+                const uint64_t a_hi = sa + k16 * ((2 * BLOCK_M * 16) >> 4);
+                const uint64_t b_hi = sb + k16 * ((2 * (BLOCK_N / 2) * 16) >> 4);
+                sm100::umma_bf16_pair(tmem_acc, a_hi, b_hi, idesc, (it | k16) != 0);
+                if constexpr (SPLIT == 3) {
+                  const uint64_t a_lo = a_hi + (A_PLANE_BYTES >> 4);
+                  const uint64_t b_lo = b_hi + (BH_PLANE_BYTES >> 4);
+                  sm100::umma_bf16_pair(tmem_acc, a_lo, b_hi, idesc, true);
+                  sm100::umma_bf16_pair(tmem_acc, a_hi, b_lo, idesc, true);
+                }
+              }
+              sm100::umma_commit_pair(&bars->empty[stage], 3);                               // stage reusable in both CTAs
+              if (it == kiters - 1) sm100::umma_commit_pair(&bars->tmem_full[acc_buf], 3);   // both accumulators complete
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+              GPEMSR_PROF_WORK
+            }
+            if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+          }
+        }
+        GPEMSR_PROF_PRINT("pair mma: wait full", "wait tmem_empty", "issue + commit")
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (each CTA drains its own 128 rows) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t acc_buf = 0, acc_phase = 0;
+    bool ok = true;
+    for (long long i = 0; i < n_iter && ok; ++i) {
+      const long long m_tile = blockIdx.x + i * gridDim.x;
+      const bool live = m_tile < op.m_tiles;
+      typename Epi::State st{};
+      for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
+        ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+        if (live) epi.tile(st, tmem_acc, m_tile, n_tile, op.n_tiles, row, (warp - 2) >> 2);
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive_cluster(&bars->tmem_empty[acc_buf], 0);
+        if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  sm100::tc_fence_before();
+  sm100::cluster_sync_all();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // A-resident variant (single bf16 pass, one tap, tiled B): the whole [128 x K] A tile of a row tile lives in shared memory
 // and is fetched ONCE, while the B tiles of all column tiles stream through the stage ring.  The streaming kernel re-reads A
 // for every column tile; for the VQ lookup (4 code tiles) that is 4 x 147 KB of the 1.2 MB a row tile pulls out of L2, and
@@ -484,7 +655,8 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
   // SPLIT == 3 pairs the two products that share the A operand: a_hi * [w_hi | w_lo] is ONE MMA with N = 2 * BLOCK_N (the hi and
   // lo weight rows of a (tap, k-cell) sit next to each other in shared memory), a_lo * w_hi the second (N = BLOCK_N, into the
   // first half).  The accumulator is 2 * BLOCK_N columns and the epilogue adds column c + BLOCK_N to column c (same TMEM lane).
-  // A narrow MMA costs ~60 cycles whatever N is (the A fetch from shared memory), so 2 MMAs instead of 3 is ~1.4x.
+  // Isolated cost of one M = 128, K = 16 MMA (tools/mma_probe.cu, profiles/r02_mma_probe.txt): max(math, operand fetch at 128 B/clk)
+  // = 39 / 42 / 49 / 64 / 128 cycles for N = 16 / 32 / 64 / 128 / 256, so the pair N = 128 + N = 64 is 112 cycles against 3 x 49.
   constexpr int NMUL = SPLIT == 3 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int kcells = op.k / 8;
@@ -510,7 +682,7 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstage; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS / Epi::GROUPS); }
     sm100::mbar_init(&bars->b_full, 1);
     sm100::fence_mbar_init();
   }
@@ -697,25 +869,29 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;
+    // Epi::GROUPS == 2: group g owns accumulator buffer g and takes every other tile (two tile epilogues in flight)
+    constexpr int WPG = Epi::WARPS / Epi::GROUPS;
+    const int q = warp & 3, grp = (warp - 2) / WPG, part = ((warp - 2) % WPG) >> 2;
     const int row = q * 32 + lane;
     uint32_t acc_buf = 0, acc_phase = 0;
     bool ok = true;
     GPEMSR_PROF_DECL
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-      typename Epi::State st{};
-      GPEMSR_PROF_T0
-      ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
-      GPEMSR_PROF_WAIT(0)
-      if (!ok) break;
-      sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-      if (!(GPEMSR_ABLATE & 1)) epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);     // profiling build: no epilogue work
-      sm100::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+      if (Epi::GROUPS == 1 || (int)acc_buf == grp) {
+        typename Epi::State st{};
+        GPEMSR_PROF_T0
+        ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+        GPEMSR_PROF_WAIT(0)
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+        if (!(GPEMSR_ABLATE & 1)) epi.tile_group(st, tmem_acc, m_tile, 0, 1, row, part);     // profiling build: no epilogue work
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+        GPEMSR_PROF_WORK
+      }
       if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
-      GPEMSR_PROF_WORK
     }
     if (warp == 2 || warp == 2 + Epi::WARPS - 1) { GPEMSR_PROF_PRINT("epilogue: wait tmem_full", "-", "tile") }
   }
@@ -757,7 +933,7 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstage; ++s) { sm100::mbar_init(&bars->full[s], 1); sm100::mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS); }
+    for (int b = 0; b < 2; ++b) { sm100::mbar_init(&bars->tmem_full[b], 1); sm100::mbar_init(&bars->tmem_empty[b], Epi::WARPS / Epi::GROUPS); }
     sm100::fence_mbar_init();
   }
   constexpr int TMEM_COLS = (2 * NMUL * BLOCK_N <= 32) ? 32 : (2 * NMUL * BLOCK_N <= 64) ? 64 : (2 * NMUL * BLOCK_N <= 128) ? 128 : 256;
@@ -813,9 +989,9 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
       uint32_t stage = 0, phase = 0, acc_buf = 0, acc_phase = 0;
       bool ok = true;
       // descriptors differ only in their low word (LBO << 16 | start address >> 4); the high word (SBO = 128 B, version 1) is
-      // a constant, so the issuing thread does 32-bit adds only.  Measured: every M = 128, K = 16 MMA costs >= ~60 cycles
-      // whatever N <= 64 is (the 4 KB A operand fetch from shared memory), so these narrow layers run at ~N/128 of the tensor
-      // rate; keeping the (small) weight sets resident instead of streaming them was measured and changes nothing.
+      // a constant, so the issuing thread does 32-bit adds only.  An M = 128, K = 16 MMA costs max(math, (4 KB + N * 32 B) /
+      // 128 B/clk) -- 39 .. 49 cycles for N = 16 .. 64 (profiles/r02_mma_probe.txt) -- so these narrow layers run far below the
+      // tensor rate; keeping the (small) weight sets resident instead of streaming them was measured and changes nothing.
       constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_base = (((seg_bytes >> 4) & 0x3FFFu) << 16) | (sm100::smem_u32(stages) >> 4);
       const uint32_t b_lo_base = ((((uint32_t)PLANES * BLOCK_N * 16 >> 4) & 0x3FFFu) << 16) | ((sm100::smem_u32(stages) + a_bytes) >> 4);
@@ -870,20 +1046,24 @@ gemm_dyfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ 
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;
+    // Epi::GROUPS == 2: group g owns accumulator buffer g and takes every other tile, see gemm_tapfuse_kernel
+    constexpr int WPG = Epi::WARPS / Epi::GROUPS;
+    const int q = warp & 3, grp = (warp - 2) / WPG, part = ((warp - 2) % WPG) >> 2;
     const int row = q * 32 + lane;
     uint32_t acc_buf = 0, acc_phase = 0;
     bool ok = true;
     for (long long m_tile = blockIdx.x; m_tile < op.m_tiles && ok; m_tile += gridDim.x) {
-      typename Epi::State st{};
-      ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
-      if (!ok) break;
-      sm100::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-      epi.tile(st, tmem_acc, m_tile, 0, 1, row, (warp - 2) >> 2);
-      sm100::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+      if (Epi::GROUPS == 1 || (int)acc_buf == grp) {
+        typename Epi::State st{};
+        ok = sm100::mbar_wait(&bars->tmem_full[acc_buf], acc_phase, op.err_flag, 4);
+        if (!ok) break;
+        sm100::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc_buf * (NMUL * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+        epi.tile_group(st, tmem_acc, m_tile, 0, 1, row, part);
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&bars->tmem_empty[acc_buf]);
+      }
       if (++acc_buf == 2) { acc_buf = 0; acc_phase ^= 1; }
     }
   }

@@ -58,6 +58,39 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
   return false;
 }
 
+// Cluster-scope variants for barriers that receive arrivals from the peer CTA of a pair: arrive on the barrier at the same
+// shared-memory offset in CTA `cta` of this cluster, and a bounded wait with cluster-scope acquire.
+// shared::cluster address of `p` (a shared-memory address of this CTA) at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(const void* p, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(cta));
+  return remote;
+}
+// (default .release.cta semantics: the .release.cluster form blocks the arriving thread for ~1 300 cycles -- measured, it was the
+// bottleneck of a relay thread -- and nothing this thread wrote needs publishing: the data travels through the async proxy)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_map(bar, cta)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+  for (uint32_t it = 0; it < (1u << 20); ++it) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    if ((it & 1023) == 1023 && err_flag && *reinterpret_cast<volatile int*>(err_flag) != 0) return false;
+  }
+  if (err_flag) atomicCAS(err_flag, 0, code);
+  return false;
+}
+
 // ---------------------------------------------------------------- async proxy / bulk copy
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -76,6 +109,29 @@ struct alignas(64) TensorMap { unsigned long long opaque[16]; };
 // Tensor-map (TMA) tile loads: ONE instruction moves a whole multi-dimensional box (here: [k-cell][segment][row][8 bf16]) where
 // the bulk-copy path needs one instruction per contiguous run -- and every UBLKCP costs the issuing thread ~65 cycles.
 // `tmap` is the address of a CUtensorMap kernel parameter (__grid_constant__), coordinates are element indices, innermost first.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+// cta_group::2 forms: the completion (complete_tx) is signalled on `bar_cluster`, a shared::cluster mbarrier address that may
+// belong to the PEER CTA of the pair (cluster_map(bar, 0) = the leader's): both CTAs' loads of a stage count down one barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst_smem, const void* tmap, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst_smem, const void* tmap, int c0, int c1, int c2, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -171,6 +227,34 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // arrive on `bar` once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- cta_group::2: one instruction drives the tensor cores of BOTH CTAs of a pair (M = 256: 128 rows from each CTA's shared
+// memory, each CTA supplies N / 2 rows of B, each accumulates its own 128 rows in its own TMEM at the same address).  Only the
+// leader (cluster rank 0) issues; allocation / deallocation are executed by one warp of EACH CTA.
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {   // whole warp, in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at this offset in the CTAs of `cta_mask` once every pair MMA issued so far has completed in both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // same, arriving on the barrier at this offset in every CTA of `cta_mask`
