@@ -70,6 +70,9 @@ struct EpiConv {
 
   // one cell = 8 consecutive output channels of one output pixel; (dy, dx) only differ from 0 under PixelShuffle
   __device__ __forceinline__ void store_cell(const State& st, float (&v)[8], int ch0, int dy, int dx) const {
+#if GPEMSR_ABLATE & 16
+    if (v[0] != 12345.678f) return;          // profiling build: the epilogue computes but does not store
+#endif
     if (out_f32 || out_hi || residual) {
       const long long orow = st.orow + (long long)dy * (og.w + 2 * og.padded) + dx;
       const size_t cell = ((size_t)(ch0 >> 3) * og.rows_alloc + orow) * 8;
@@ -376,7 +379,10 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   e.patch_other = (const float*)d.patch_other; e.patch_other_bf16 = d.patch_other_bf16; e.patch_sums = d.patch_sums; e.patch_size = d.patch_size;
   e.row_max_out = d.row_max_out; e.row_max = d.row_max; e.row_sum = d.row_sum; e.row_div = d.row_div;
   const int sms = gpemsr::num_sms();
-  const bool clustered = BLOCK_N >= 128 && op.m_tiles >= 2 && gpemsr::use_clusters();
+  // CTA pairs: the cta_group::2 kernel for every tile width >= 64 whose operands can be described by tensor maps; else (N >= 128)
+  // the cta_group::1 kernel with the B stages multicast
+  const bool pair_ok = BLOCK_N >= 64 && d.b_packed <= 1 && op.batch_tiles == 0 && gpemsr::use_pair_mma() && gpemsr::use_tensor_maps();
+  const bool clustered = (BLOCK_N >= 128 || pair_ok) && op.m_tiles >= 2 && gpemsr::use_clusters();
   // grid: gx persistent row-tile walkers x gy column-tile splitters.  Model: one CTA per SM, CTAs run in waves, a CTA's
   // time = its (row tile, column tile) count.  Take the cheapest shape (e.g. 50 row tiles x 25 column tiles: 50 x 5 CTAs
   // = 2 waves x 5 units, not 50 x 3 = 150 CTAs whose 2 stragglers double the time); ties go to fewer column splits
@@ -396,15 +402,17 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
         if (best < 0 || cost < best - 1e-9 || (cost < best + 1e-9 && (y < gy || (y == gy && x > gx)))) { best = cost; gx = x; gy = y; }
       }
   }
-  if constexpr (BLOCK_N == 256) {
-    // CTA-pair MMAs (cta_group::2): packed weights, no per-tile weight batches, operands by tensor map
-    if (clustered && d.b_packed == 1 && op.batch_tiles == 0 && gpemsr::use_pair_mma() && gpemsr::use_tensor_maps()) {
+  if constexpr (BLOCK_N >= 64) {
+    // CTA-pair MMAs (cta_group::2), operands by tensor map: packed weights or a plain K8-blocked B (attention), no weight batches
+    if (clustered && pair_ok) {
       constexpr int PLANES = SPLIT == 3 ? 2 : 1, KCH = BLOCK_K / 8;
-      constexpr int NST = (227 * 1024 - 1024) / (PLANES * (gemm::BLOCK_M + BLOCK_N / 2) * BLOCK_K * 2) >= 6 ? 6 : 4;
-      constexpr int SMEM = NST * PLANES * (gemm::BLOCK_M + BLOCK_N / 2) * BLOCK_K * 2 + 1024;
+      constexpr int STAGE = PLANES * (gemm::BLOCK_M + BLOCK_N / 2) * BLOCK_K * 2;
+      constexpr int NST = (227 * 1024 - 1024) / STAGE >= 8 ? 8 : (227 * 1024 - 1024) / STAGE;
+      constexpr int SMEM = NST * STAGE + 1024;
       int off_min = 0, off_max = 0;
       for (int t = 0; t < op.taps; ++t) { off_min = std::min(off_min, op.a_row_off[t]); off_max = std::max(off_max, op.a_row_off[t]); }
       gemm::PairMaps tm;
+      tm.b_packed = d.b_packed;
       bool maps_ok = op.a_row0 + off_min >= 0 && 2 * (op.a_row0 + op.m_tiles * gemm::BLOCK_M + off_max) < (1LL << 31);
       if (maps_ok) {
         const unsigned long long adims[2] = {2ull * (unsigned long long)op.a_rows, (unsigned long long)(op.k / 8)};
@@ -412,11 +420,19 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
         const unsigned abox[2] = {2 * gemm::BLOCK_M, (unsigned)KCH};
         const void* abase[2] = {op.a_hi, op.a_lo};
         for (int p = 0; p < PLANES && maps_ok; ++p) maps_ok = gpemsr::encode_u64_map(&tm.a[p], abase[p], 2, adims, astr, abox);
+      }
+      if (maps_ok && d.b_packed) {
         const unsigned long long blocks = (unsigned long long)op.n_tiles * op.taps * (op.k / BLOCK_K);
         const unsigned long long bdims[3] = {2ull * BLOCK_N, (unsigned long long)(PLANES * KCH), blocks};
         const unsigned long long bstr[3] = {0, (unsigned long long)BLOCK_N * 16, (unsigned long long)PLANES * KCH * BLOCK_N * 16};
         const unsigned bbox[3] = {(unsigned)BLOCK_N, (unsigned)(PLANES * KCH), 1};
-        if (maps_ok) maps_ok = gpemsr::encode_u64_map(&tm.b, op.b_hi, 3, bdims, bstr, bbox);
+        maps_ok = gpemsr::encode_u64_map(&tm.b[0], op.b_hi, 3, bdims, bstr, bbox);
+      } else if (maps_ok) {
+        const unsigned long long bdims[2] = {2ull * (unsigned long long)op.b_rows, (unsigned long long)op.taps * (op.k / 8)};
+        const unsigned long long bstr[2] = {0, (unsigned long long)op.b_rows * 16};
+        const unsigned bbox[2] = {(unsigned)BLOCK_N, (unsigned)KCH};
+        const void* bbase[2] = {op.b_hi, op.b_lo};
+        for (int p = 0; p < PLANES && maps_ok; ++p) maps_ok = gpemsr::encode_u64_map(&tm.b[p], bbase[p], 2, bdims, bstr, bbox);
       }
       if (maps_ok) {
         auto kern = gemm::gemm_pair_kernel<BLOCK_N, BLOCK_K, SPLIT, NST, Epi>;
@@ -427,7 +443,7 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
       }
     }
   }
-  if (clustered) {
+  if (clustered && BLOCK_N >= 128) {
     // wide tiles are bound by operand traffic out of L2: pairs of CTAs share every B stage by multicast
     auto kern = gemm::gemm_kernel<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, Epi, 2>;
     GPEMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));

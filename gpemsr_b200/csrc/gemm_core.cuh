@@ -310,7 +310,9 @@ gemm_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi
 //   tmem_empty[b] on the leader: all epilogue warps of BOTH CTAs arrive there (the peer's through the cluster address)
 struct PairMaps {
   sm100::TensorMap a[2];       // A planes: {2 * rows, k-cells}, box {256, BLOCK_K / 8}
-  sm100::TensorMap b;          // packed weights: {2 * BLOCK_N, planes * cells, stage blocks}, box {BLOCK_N, planes * cells, 1}
+  sm100::TensorMap b[2];       // b_packed: b[0] = packed weights {2 * BLOCK_N, planes * cells, stage blocks}, box {BLOCK_N, planes * cells, 1};
+                               // else one map per plane of the K8-blocked operand {2 * b_rows, taps * K / 8}, box {BLOCK_N, BLOCK_K / 8}
+  int b_packed;
 };
 
 template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, class Epi>
@@ -323,6 +325,7 @@ gemm_pair_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
   constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + BH_PLANE_BYTES);
   constexpr int TMEM_COLS = 2 * BLOCK_N <= 256 ? 256 : 512;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "pair MMA: N multiple of 16 per CTA half");
+  static_assert(NSTAGE <= 8, "Barriers holds 8 stages");
   static_assert(NSTAGE * STAGE_BYTES + 1024 <= 227 * 1024, "shared memory budget");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stages = smem;
@@ -353,8 +356,10 @@ gemm_pair_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
       bool ok = true;
 #pragma unroll
       for (int plane = 0; plane < PLANES; ++plane) sm100::tma_prefetch_desc(&tm.a[plane]);
-      sm100::tma_prefetch_desc(&tm.b);
+#pragma unroll
+      for (int plane = 0; plane < PLANES; ++plane) sm100::tma_prefetch_desc(&tm.b[plane]);
       GPEMSR_PROF_DECL
+      const int kcells = op.k / 8;
       for (long long i = 0; i < n_iter && ok; ++i) {
         const long long m_tile = min(blockIdx.x + i * gridDim.x, op.m_tiles - 1);
         const long long row0 = op.a_row0 + m_tile * BLOCK_M;
@@ -373,7 +378,15 @@ gemm_pair_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
 #pragma unroll
               for (int plane = 0; plane < PLANES; ++plane)
                 sm100::tma_load_2d_pair(st + plane * A_PLANE_BYTES, &tm.a[plane], a_c0, kci * KCH, full_leader);
-              sm100::tma_load_3d_pair(st + PLANES * A_PLANE_BYTES, &tm.b, (int)crank * BLOCK_N, 0, blk, full_leader);
+              if (tm.b_packed) {
+                sm100::tma_load_3d_pair(st + PLANES * A_PLANE_BYTES, &tm.b[0], (int)crank * BLOCK_N, 0, blk, full_leader);
+              } else {
+                // this CTA's BLOCK_N / 2 rows of column tile n_tile, KCH cells of (tap, k-chunk)
+#pragma unroll
+                for (int plane = 0; plane < PLANES; ++plane)
+                  sm100::tma_load_2d_pair(st + PLANES * A_PLANE_BYTES + plane * BH_PLANE_BYTES, &tm.b[plane],
+                                          (2 * n_tile + (int)crank) * BLOCK_N, tap * kcells + kci * KCH, full_leader);
+              }
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
               GPEMSR_PROF_WORK
             }
@@ -396,14 +409,14 @@ gemm_pair_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
         for (long long i = 0; i < n_iter && ok; ++i) {
           for (int n_tile = blockIdx.y; n_tile < op.n_tiles && ok; n_tile += gridDim.y) {
             GPEMSR_PROF_T0
-            ok = sm100::mbar_wait_cluster(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
+            ok = sm100::mbar_wait(&bars->tmem_empty[acc_buf], acc_phase ^ 1, op.err_flag, 2);
             GPEMSR_PROF_WAIT(1)
             if (!ok) break;
             sm100::tc_fence_after();
             const uint32_t tmem_acc = tmem_base + acc_buf * BLOCK_N;
             for (int it = 0; it < kiters && ok; ++it) {
               GPEMSR_PROF_T0
-              ok = sm100::mbar_wait_cluster(&bars->full[stage], phase, op.err_flag, 3);
+              ok = sm100::mbar_wait(&bars->full[stage], phase, op.err_flag, 3);
               GPEMSR_PROF_WAIT(0)
               if (!ok) break;
               sm100::tc_fence_after();
