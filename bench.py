@@ -249,7 +249,12 @@ def instrumented_step(hp, dev_in):
         else:
             n, k, taps = kw['n_cols'], kw['k_pad'], 1
         bn = 16 if (n <= 16 and not kw.get('pixel_shuffle')) else 64 if n <= 64 else 128 if n <= 128 else 256
-        name = getattr(w, 'kernel', None) or f'gemm_kernel<{bn}>'             # the kernel template gpemsr_igemm() launches
+        # the kernel template gpemsr_igemm() launches: tap-/dy-fused (recorded on the weights), else the streaming kernel -- its
+        # CTA-pair form (cta_group::2) for every tile width >= 64 unless GPEMSR_PAIR=0 / GPEMSR_TMA=0 / GPEMSR_CLUSTER=0
+        name = getattr(w, 'kernel', None) or f'gemm_kernel<{bn}>'
+        if name.startswith('gemm_kernel<') and int(name[12:-1]) >= 64 and \
+                all(os.environ.get(v, '1') != '0' for v in ('GPEMSR_PAIR', 'GPEMSR_TMA', 'GPEMSR_CLUSTER')):
+            name = 'gemm_pair_kernel<' + name[12:]
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         orig(a, w, err, **kw)

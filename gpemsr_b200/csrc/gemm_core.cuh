@@ -718,17 +718,8 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
 #pragma unroll
         for (int plane = 0; plane < PLANES; ++plane) sm100::tma_prefetch_desc(&tm.a[plane]);
       }
-      if (blockIdx.x < op.m_tiles) {
-        // the resident weights: one 1 KB .. 4 KB block per (tap, k-cell, plane) into the [tap][kc][plane][n] layout
-        sm100::mbar_arrive_expect_tx(&bars->b_full, b_bytes);
-        const int nblk = op.taps * kcells;
-        for (int r = 0; r < nblk; ++r) {                    // r = tap * kcells + kc
-#pragma unroll
-          for (int plane = 0; plane < PLANES; ++plane)
-            sm100::bulk_g2s(b_res + ((size_t)r * PLANES + plane) * BLOCK_N * 16, (plane ? op.b_lo : op.b_hi) + (long long)r * op.b_rows * 8,
-                            BLOCK_N * 16, &bars->b_full);
-        }
-      }
+      // the resident weights are fetched by the epilogue warps (below); this thread only registers the byte count
+      if (blockIdx.x < op.m_tiles) sm100::mbar_arrive_expect_tx(&bars->b_full, b_bytes);
       uint32_t stage = 0, phase = 0;
       const long long a_kstep = (long long)S * KCH * op.a_rows * 8;
       GPEMSR_PROF_DECL
@@ -882,6 +873,20 @@ gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
+    // The resident weights first: one 1 KB .. 4 KB block per (tap, k-cell, plane) into the [tap][kc][plane][n] layout.  A bulk copy
+    // costs its issuing thread ~65 cycles, and 144 of them from the producer alone were ~5 us before the first MMA of EVERY
+    // launch (most launches of the model are small: ~50 us); the epilogue warps are idle until the first tile is done, so their
+    // elected lanes issue a slice each.  (complete_tx may precede the producer's expect_tx: the phase cannot complete before it.)
+    if (blockIdx.x < op.m_tiles && sm100::elect_one()) {
+      const int nblk = op.taps * kcells;
+      for (int r = warp - 2; r < nblk; r += Epi::WARPS) {                    // r = tap * kcells + kc
+#pragma unroll
+        for (int plane = 0; plane < PLANES; ++plane)
+          sm100::bulk_g2s(b_res + ((size_t)r * PLANES + plane) * BLOCK_N * 16, (plane ? op.b_lo : op.b_hi) + (long long)r * op.b_rows * 8,
+                          BLOCK_N * 16, &bars->b_full);
+      }
+    }
+    __syncwarp();
     // Epi::GROUPS == 2: group g owns accumulator buffer g and takes every other tile (two tile epilogues in flight)
     constexpr int WPG = Epi::WARPS / Epi::GROUPS;
     const int q = warp & 3, grp = (warp - 2) / WPG, part = ((warp - 2) % WPG) >> 2;

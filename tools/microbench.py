@@ -63,7 +63,7 @@ def conv_bench(which=None):
     """Single conv layers of the bench step, fp32-faithful split-3 path: ms and algorithmic TFLOP/s."""
     from gpemsr_b200 import igemm as G
     cases = [('rb512_80', 5, 512, 512, 80, 3, {}), ('rb256_160', 5, 256, 256, 160, 3, {}), ('rb128_320', 5, 128, 128, 320, 3, {}),
-             ('rb64_640', 5, 64, 64, 640, 3, {}), ('hr64_1280', 1, 64, 64, 1280, 3, dict(act=G.ACT_LRELU, slope=0.1)),
+             ('rb64_640', 5, 64, 64, 640, 3, {}), ('rb64_80', 5, 64, 64, 80, 3, {}), ('rb64_160', 5, 64, 64, 160, 3, {}), ('hr64_1280', 1, 64, 64, 1280, 3, dict(act=G.ACT_LRELU, slope=0.1)),
              ('up256_640', 1, 64, 256, 640, 3, dict(ps=True)), ('out1_1280', 5, 64, 1, 1280, 3, dict(nchw=True)),
              ('q512_80', 5, 512, 512, 80, 1, {}),
              ('vgg64_1280', 2, 64, 64, 1280, 3, dict(split=1, act=G.ACT_RELU, planes_only=True)),      # VGG conv1_2, one bf16 pass
@@ -105,6 +105,31 @@ def conv_bench(which=None):
     if hasattr(_lib.lib(), 'gpemsr_tensor_map_stats'):
         _lib.lib().gpemsr_tensor_map_stats(ctypes.byref(built), ctypes.byref(rej))
         print(json.dumps(dict(tensor_maps_built=built.value, tensor_maps_rejected=rej.value)), file=sys.stderr)
+    return out
+
+
+def small_conv_bench(reps=20):
+    """Fixed cost of a tap-fused launch: the 64 -> 64 3x3 conv on SMALL images (2 .. 9 tiles per SM), `reps` launches captured in
+    one CUDA graph so that the host's launch path is out of the measurement; us per launch."""
+    from gpemsr_b200 import igemm as G
+    out = []
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    for name, n, s, split in (('rb64_80', 5, 80, 3), ('rb64_160', 5, 160, 3), ('rb64_320', 5, 320, 3), ('vgg64_160', 5, 160, 1)):
+        g = G.Geom(n, s, s, True)
+        x = G.Act(g, 64, 'cuda', f32=False)
+        x.hi.normal_(); x.lo.normal_(std=0.004)
+        wt = G.Weights(torch.randn(64, 64, 3, 3, device='cuda') * 0.05, 'conv')
+        b = torch.randn(64, device='cuda')
+        y = G.Act(g, 64, 'cuda', f32=False)
+        fn = lambda: G.igemm(x, wt, err, out=y, out_f32=False, split=split, bias=b)
+        fn(); torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(reps):
+                fn()
+        med, best = timeit(graph.replay, iters=7, warm=2)
+        out.append(dict(op='small_conv', name=name, n=n, hw=s, split=split, tiles_per_sm=round(n * g.r_img / 128 / 148, 2), us_per_launch=med * 1e3 / reps))
+    assert int(err.item()) == 0
     return out
 
 
@@ -173,6 +198,8 @@ if __name__ == '__main__':
         res += flow1_bench()
     if 'flow' in sys.argv[1:] or len(sys.argv) == 1:
         res += flow_warp_bench()
+    if 'small' in sys.argv[1:]:
+        res += small_conv_bench()
     if 'conv' in sys.argv[1:]:
         res += conv_bench([a for a in sys.argv[2:]] or None)
     if 'vq1' in sys.argv[1:]:
