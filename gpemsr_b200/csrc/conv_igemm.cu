@@ -17,7 +17,11 @@ namespace {
 // PAIR: the accumulator is split over the column ranges (c, c + BLOCK_N) -- the paired-N MMAs of the tap-fused / dy-fused kernels in
 // the fp32-faithful split keep a_hi * w_lo apart from a_hi * w_hi + a_lo * w_hi; the epilogue sums them.  A compile-time property
 // of the launch: the kernels that never pair (the streaming kernel, every single-pass launch) carry no second TMEM load.
-template <int BLOCK_N, bool PAIR = false>
+// LEAN: a compile-time promise (made by the host dispatch, lean_epilogue()) that none of the special epilogues is active -- no
+// GroupNorm sums, patch correlation, softmax row statistics, exp, PixelShuffle, phase scatter, NCHW / row-major stores, per-row
+// bias, partial column tiles -- so that the narrow kernels, whose epilogue warps are ISSUE bound (~600 instructions per thread and
+// tile through the generic path), run the plain scale / bias / activation / residual / store path only.
+template <int BLOCK_N, bool PAIR = false, bool LEAN = false>
 struct EpiConv {
   Geom ag, og;
   int n_cols;
@@ -91,7 +95,7 @@ struct EpiConv {
         if (out_lo) *reinterpret_cast<uint4*>(out_lo + cell) = lo;
       }
     }
-    if (out_nchw) {
+    if (!LEAN && out_nchw) {
       const long long Wo = (long long)up * ag.w, plane = (long long)up * ag.h * Wo;
       float* p = out_nchw + st.nchw0 + (long long)ch0 * plane + (long long)dy * Wo + dx;
 #pragma unroll
@@ -136,7 +140,7 @@ struct EpiConv {
   // warps stall on exactly these loads: ncu source view)
   template <int CHUNK>
   __device__ __forceinline__ void load_bias(const State& st, float (&bv)[CHUNK], int col0) const {
-    if (bias_per_row) {
+    if (!LEAN && bias_per_row) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) bv[j] = st.row_bias;
     } else if (bias && col0 + CHUNK <= n_cols) {
@@ -155,18 +159,18 @@ struct EpiConv {
   __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], const float (&bv)[CHUNK], const uint4 (&po)[CHUNK / 8],
                                         int col0, long long rel) const {
     float f[CHUNK];
-    const bool full = col0 + CHUNK <= n_cols;
+    const bool full = LEAN || col0 + CHUNK <= n_cols;
     // v = scale * acc + bias
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), bv[j]);
-    if (row_max_out) {                   // softmax pre-pass: nothing is stored
+    if (!LEAN && row_max_out) {          // softmax pre-pass: nothing is stored
       float m = st.r_max;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (full || col0 + j < n_cols) m = fmaxf(m, f[j]);
       st.r_max = m;
       return;
     }
-    if (row_div) {
+    if (!LEAN && row_div) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] *= st.r_inv;
     }
@@ -176,7 +180,7 @@ struct EpiConv {
     } else if (act == GPEMSR_ACT_LRELU) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
-    } else if (act == GPEMSR_ACT_EXP) {
+    } else if (!LEAN && act == GPEMSR_ACT_EXP) {
       // exp(v - max) = 2^(v * log2(e) - max * log2(e)): one FFMA + MUFU.EX2 per element (relative error ~2^-22; the arguments are
       // <= ~0, so no overflow; expf() costs ~4x the instructions and this epilogue is what bounds the scores GEMM)
       const float sub2 = st.r_sub * 1.4426950408889634f;
@@ -187,13 +191,13 @@ struct EpiConv {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (col0 + j >= n_cols) f[j] = 0.f;
     }
-    if (row_sum) {
+    if (!LEAN && row_sum) {
       float a = 0.f;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) a += f[j];
       st.r_sum += a;
     }
-    if (gn_sums) {                       // all 32 lanes take part; rows outside the image contribute zeros
+    if (!LEAN && gn_sums) {              // all 32 lanes take part; rows outside the image contribute zeros
       if (!st.valid) {
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) f[j] = 0.f;
@@ -201,7 +205,7 @@ struct EpiConv {
       group_stats<CHUNK>(st, f, col0);
     }
     if (!st.valid) return;
-    if (patch_sums) {
+    if (!LEAN && patch_sums) {
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
         if (col0 + 8 * g >= n_cols) break;
@@ -224,13 +228,13 @@ struct EpiConv {
         }
       }
     }
-    if (out_rowmajor) {
+    if (!LEAN && out_rowmajor) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 4)
         *reinterpret_cast<float4*>(out_rowmajor + rel * ld + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     }
-    if (!(out_f32 || out_hi || out_nchw)) return;
-    if (pixel_shuffle) {
+    if (!(out_f32 || out_hi || (!LEAN && out_nchw))) return;
+    if (!LEAN && pixel_shuffle) {
       if constexpr (CHUNK == 32) {     // 32 columns = 8 channels x (dy, dx)
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
@@ -240,7 +244,7 @@ struct EpiConv {
           store_cell(st, v, c_off + (col0 >> 2), sub >> 1, sub & 1);
         }
       }
-    } else if (phase_cols && (phase_cols & 31)) {
+    } else if (!LEAN && phase_cols && (phase_cols & 31)) {
       // few channels per phase (the composed up-block + output conv: phase_cols = image channels): scalar NCHW scatter
       if (out_nchw) {
         const long long Wo = (long long)up * ag.w, plane = (long long)up * ag.h * Wo;
@@ -253,7 +257,7 @@ struct EpiConv {
           }
         }
       }
-    } else if (phase_cols) {             // the four parity phases of a ConvTranspose2d side by side along the columns
+    } else if (!LEAN && phase_cols) {    // the four parity phases of a ConvTranspose2d side by side along the columns
       const int ph = col0 / phase_cols, ch = col0 - ph * phase_cols;
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
@@ -265,7 +269,7 @@ struct EpiConv {
     } else {
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
-        if (col0 + 8 * g >= n_cols) break;
+        if (!LEAN && col0 + 8 * g >= n_cols) break;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = f[8 * g + j];
@@ -288,26 +292,26 @@ struct EpiConv {
       st.init = true;
       st.valid = decode_row(ag, rel, st.img, st.y, st.x);
       if (st.valid) {
-        if (bias_per_row) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
+        if (!LEAN && bias_per_row) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
         const int Y = up * st.y + py, X = up * st.x + px;
         st.orow = place_row(og, st.img, Y, X);
         const long long Wo = (long long)up * ag.w, Ho = (long long)up * ag.h;
         st.nchw0 = ((long long)st.img * nchw_c * Ho + Y) * Wo + X;
-        if (row_max) st.r_sub = __ldg(row_max + rel);
-        if (row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
+        if (!LEAN && row_max) st.r_sub = __ldg(row_max + rel);
+        if (!LEAN && row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
       }
     }
     constexpr int CHUNK = (SPAN >= 32 && BLOCK_N >= 128) ? 32 : 16;     // the narrow kernels run 18 warps: 16 columns at a time fit their registers
-    const bool row_stats = (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
+    const bool row_stats = !LEAN && (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
 #pragma unroll 1
     for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
       const int col0 = n_tile * BLOCK_N + c0;
-      const bool work = (st.valid || gn_sums) && col0 < n_cols;
+      const bool work = (st.valid || (!LEAN && gn_sums)) && (LEAN || col0 < n_cols);
       float bv[CHUNK];
       uint4 po[CHUNK / 8];
       if (work) {
         load_bias<CHUNK>(st, bv, col0);
-        if (patch_sums && patch_other_bf16 && st.valid) {
+        if (!LEAN && patch_sums && patch_other_bf16 && st.valid) {
 #pragma unroll
           for (int g = 0; g < CHUNK / 8; ++g) {
             const size_t cell = ((size_t)((c_off + col0 + 8 * g) >> 3) * og.rows_alloc + st.orow) * 8;
@@ -330,7 +334,7 @@ struct EpiConv {
       sm100::tmem_ld_wait();
       if (work) chunk<CHUNK>(st, r, bv, po, col0, rel);
     }
-    if (patch_sums) flush_patch(st);
+    if (!LEAN && patch_sums) flush_patch(st);
     // fused softmax statistics: one atomic per row once this CTA has swept its last column tile of the row tile
     if (row_stats && st.valid) {
       if (row_max_out) {                 // float max through the ordered-integer trick (the buffer starts at -1.7e38)
@@ -365,10 +369,15 @@ struct EpiConv {
   }
 };
 
-template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE>
+bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n);
+
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, bool LEAN = false>
 int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t s) {
+  if constexpr (!LEAN && BLOCK_N >= 64 && BLOCK_N <= 128) {
+    if (lean_epilogue(d, BLOCK_N)) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, true>(op, d, s);
+  }
   using Cfg = gemm::Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
-  using Epi = EpiConv<BLOCK_N>;
+  using Epi = EpiConv<BLOCK_N, false, LEAN>;
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
@@ -499,9 +508,18 @@ void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
   tm.use = 1;
 }
 
-template <int BLOCK_N, int SPLIT>
+// the plain epilogue (EpiConv<..., LEAN>): scale, per-column bias, ReLU / LeakyReLU, residual, fp32 / plane stores of whole column tiles
+bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n) {
+  return !d.gn_sums && !d.patch_sums && !d.row_max_out && !d.row_max && !d.row_sum && !d.row_div && !d.pixel_shuffle && !d.phase_cols &&
+         !d.out_nchw && !d.out_rowmajor && !d.bias_per_row && d.act != GPEMSR_ACT_EXP && d.n_cols % block_n == 0 && (d.out_f32 || d.out_hi);
+}
+
+template <int BLOCK_N, int SPLIT, bool LEAN = false>
 int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
-  using Epi = EpiConv<BLOCK_N, SPLIT == 3>;
+  if constexpr (!LEAN) {
+    if (lean_epilogue(d, BLOCK_N)) return launch_fused<BLOCK_N, SPLIT, true>(op, d, smem_bytes, s);
+  }
+  using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
@@ -543,9 +561,12 @@ size_t plan_dyfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n
   return (size_t)op.nstage * stage_bytes + 1024;
 }
 
-template <int BLOCK_N, int SPLIT>
+template <int BLOCK_N, int SPLIT, bool LEAN = false>
 int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
-  using Epi = EpiConv<BLOCK_N, SPLIT == 3>;
+  if constexpr (!LEAN) {
+    if (lean_epilogue(d, BLOCK_N)) return launch_dyfuse<BLOCK_N, SPLIT, true>(op, d, smem_bytes, s);
+  }
+  using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
   e.ag = to_geom(d.a_geom); e.og = to_geom(d.o_geom);
   e.n_cols = d.n_cols; e.scale = d.scale; e.bias = d.bias; e.bias_per_row = d.bias_per_row; e.act = d.act; e.slope = d.slope;
