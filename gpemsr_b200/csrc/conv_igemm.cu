@@ -21,8 +21,9 @@ namespace {
 // GroupNorm sums, patch correlation, softmax row statistics, exp, PixelShuffle, phase scatter, NCHW / row-major stores, per-row
 // bias, partial column tiles -- so that the narrow kernels, whose epilogue warps are ISSUE bound (~600 instructions per thread and
 // tile through the generic path), run the plain scale / bias / activation / residual / store path only.
-template <int BLOCK_N, bool PAIR = false, bool LEAN = false>
+template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic, 1 = plain, 2 = plain + patch correlation (VGG mask)
 struct EpiConv {
+  static constexpr bool GEN = LEAN == 0, PATCH = LEAN != 1;
   Geom ag, og;
   int n_cols;
   float scale;
@@ -95,7 +96,7 @@ struct EpiConv {
         if (out_lo) *reinterpret_cast<uint4*>(out_lo + cell) = lo;
       }
     }
-    if (!LEAN && out_nchw) {
+    if (GEN && out_nchw) {
       const long long Wo = (long long)up * ag.w, plane = (long long)up * ag.h * Wo;
       float* p = out_nchw + st.nchw0 + (long long)ch0 * plane + (long long)dy * Wo + dx;
 #pragma unroll
@@ -140,7 +141,7 @@ struct EpiConv {
   // warps stall on exactly these loads: ncu source view)
   template <int CHUNK>
   __device__ __forceinline__ void load_bias(const State& st, float (&bv)[CHUNK], int col0) const {
-    if (!LEAN && bias_per_row) {
+    if (GEN && bias_per_row) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) bv[j] = st.row_bias;
     } else if (bias && col0 + CHUNK <= n_cols) {
@@ -159,18 +160,18 @@ struct EpiConv {
   __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], const float (&bv)[CHUNK], const uint4 (&po)[CHUNK / 8],
                                         int col0, long long rel) const {
     float f[CHUNK];
-    const bool full = LEAN || col0 + CHUNK <= n_cols;
+    const bool full = !GEN || col0 + CHUNK <= n_cols;
     // v = scale * acc + bias
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), bv[j]);
-    if (!LEAN && row_max_out) {          // softmax pre-pass: nothing is stored
+    if (GEN && row_max_out) {          // softmax pre-pass: nothing is stored
       float m = st.r_max;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (full || col0 + j < n_cols) m = fmaxf(m, f[j]);
       st.r_max = m;
       return;
     }
-    if (!LEAN && row_div) {
+    if (GEN && row_div) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] *= st.r_inv;
     }
@@ -180,7 +181,7 @@ struct EpiConv {
     } else if (act == GPEMSR_ACT_LRELU) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
-    } else if (!LEAN && act == GPEMSR_ACT_EXP) {
+    } else if (GEN && act == GPEMSR_ACT_EXP) {
       // exp(v - max) = 2^(v * log2(e) - max * log2(e)): one FFMA + MUFU.EX2 per element (relative error ~2^-22; the arguments are
       // <= ~0, so no overflow; expf() costs ~4x the instructions and this epilogue is what bounds the scores GEMM)
       const float sub2 = st.r_sub * 1.4426950408889634f;
@@ -191,13 +192,13 @@ struct EpiConv {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (col0 + j >= n_cols) f[j] = 0.f;
     }
-    if (!LEAN && row_sum) {
+    if (GEN && row_sum) {
       float a = 0.f;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) a += f[j];
       st.r_sum += a;
     }
-    if (!LEAN && gn_sums) {              // all 32 lanes take part; rows outside the image contribute zeros
+    if (GEN && gn_sums) {              // all 32 lanes take part; rows outside the image contribute zeros
       if (!st.valid) {
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) f[j] = 0.f;
@@ -205,7 +206,7 @@ struct EpiConv {
       group_stats<CHUNK>(st, f, col0);
     }
     if (!st.valid) return;
-    if (!LEAN && patch_sums) {
+    if (PATCH && patch_sums) {
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
         if (col0 + 8 * g >= n_cols) break;
@@ -228,13 +229,13 @@ struct EpiConv {
         }
       }
     }
-    if (!LEAN && out_rowmajor) {
+    if (GEN && out_rowmajor) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 4)
         *reinterpret_cast<float4*>(out_rowmajor + rel * ld + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     }
-    if (!(out_f32 || out_hi || (!LEAN && out_nchw))) return;
-    if (!LEAN && pixel_shuffle) {
+    if (!(out_f32 || out_hi || (GEN && out_nchw))) return;
+    if (GEN && pixel_shuffle) {
       if constexpr (CHUNK == 32) {     // 32 columns = 8 channels x (dy, dx)
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
@@ -244,7 +245,7 @@ struct EpiConv {
           store_cell(st, v, c_off + (col0 >> 2), sub >> 1, sub & 1);
         }
       }
-    } else if (!LEAN && phase_cols && (phase_cols & 31)) {
+    } else if (GEN && phase_cols && (phase_cols & 31)) {
       // few channels per phase (the composed up-block + output conv: phase_cols = image channels): scalar NCHW scatter
       if (out_nchw) {
         const long long Wo = (long long)up * ag.w, plane = (long long)up * ag.h * Wo;
@@ -257,7 +258,7 @@ struct EpiConv {
           }
         }
       }
-    } else if (!LEAN && phase_cols) {    // the four parity phases of a ConvTranspose2d side by side along the columns
+    } else if (GEN && phase_cols) {    // the four parity phases of a ConvTranspose2d side by side along the columns
       const int ph = col0 / phase_cols, ch = col0 - ph * phase_cols;
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
@@ -269,7 +270,7 @@ struct EpiConv {
     } else {
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
-        if (!LEAN && col0 + 8 * g >= n_cols) break;
+        if (GEN && col0 + 8 * g >= n_cols) break;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = f[8 * g + j];
@@ -292,26 +293,26 @@ struct EpiConv {
       st.init = true;
       st.valid = decode_row(ag, rel, st.img, st.y, st.x);
       if (st.valid) {
-        if (!LEAN && bias_per_row) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
+        if (GEN && bias_per_row) st.row_bias = __ldg(bias + (long long)st.y * ag.w + st.x);
         const int Y = up * st.y + py, X = up * st.x + px;
         st.orow = place_row(og, st.img, Y, X);
         const long long Wo = (long long)up * ag.w, Ho = (long long)up * ag.h;
         st.nchw0 = ((long long)st.img * nchw_c * Ho + Y) * Wo + X;
-        if (!LEAN && row_max) st.r_sub = __ldg(row_max + rel);
-        if (!LEAN && row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
+        if (GEN && row_max) st.r_sub = __ldg(row_max + rel);
+        if (GEN && row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
       }
     }
     constexpr int CHUNK = (SPAN >= 32 && BLOCK_N >= 128) ? 32 : 16;     // the narrow kernels run 18 warps: 16 columns at a time fit their registers
-    const bool row_stats = !LEAN && (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
+    const bool row_stats = GEN && (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
 #pragma unroll 1
     for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
       const int col0 = n_tile * BLOCK_N + c0;
-      const bool work = (st.valid || (!LEAN && gn_sums)) && (LEAN || col0 < n_cols);
+      const bool work = (st.valid || (GEN && gn_sums)) && (!GEN || col0 < n_cols);
       float bv[CHUNK];
       uint4 po[CHUNK / 8];
       if (work) {
         load_bias<CHUNK>(st, bv, col0);
-        if (!LEAN && patch_sums && patch_other_bf16 && st.valid) {
+        if (PATCH && patch_sums && patch_other_bf16 && st.valid) {
 #pragma unroll
           for (int g = 0; g < CHUNK / 8; ++g) {
             const size_t cell = ((size_t)((c_off + col0 + 8 * g) >> 3) * og.rows_alloc + st.orow) * 8;
@@ -334,7 +335,7 @@ struct EpiConv {
       sm100::tmem_ld_wait();
       if (work) chunk<CHUNK>(st, r, bv, po, col0, rel);
     }
-    if (!LEAN && patch_sums) flush_patch(st);
+    if (PATCH && patch_sums) flush_patch(st);
     // fused softmax statistics: one atomic per row once this CTA has swept its last column tile of the row tile
     if (row_stats && st.valid) {
       if (row_max_out) {                 // float max through the ordered-integer trick (the buffer starts at -1.7e38)
@@ -371,10 +372,10 @@ struct EpiConv {
 
 bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n);
 
-template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, bool LEAN = false>
+template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, int LEAN = 0>
 int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t s) {
-  if constexpr (!LEAN && BLOCK_N >= 64 && BLOCK_N <= 128) {
-    if (lean_epilogue(d, BLOCK_N)) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, true>(op, d, s);
+  if constexpr (LEAN == 0 && BLOCK_N >= 64 && BLOCK_N <= 128) {
+    if (lean_epilogue(d, BLOCK_N)) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 1>(op, d, s);
   }
   using Cfg = gemm::Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
   using Epi = EpiConv<BLOCK_N, false, LEAN>;
@@ -508,16 +509,24 @@ void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
   tm.use = 1;
 }
 
-// the plain epilogue (EpiConv<..., LEAN>): scale, per-column bias, ReLU / LeakyReLU, residual, fp32 / plane stores of whole column tiles
-bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n) {
-  return !d.gn_sums && !d.patch_sums && !d.row_max_out && !d.row_max && !d.row_sum && !d.row_div && !d.pixel_shuffle && !d.phase_cols &&
-         !d.out_nchw && !d.out_rowmajor && !d.bias_per_row && d.act != GPEMSR_ACT_EXP && d.n_cols % block_n == 0 && (d.out_f32 || d.out_hi);
+// the plain epilogue (EpiConv<..., LEAN>): scale, per-column bias, ReLU / LeakyReLU, residual, fp32 / plane stores of whole column
+// tiles (mode 1); the same plus the patch correlation of the VGG mask branch (mode 2); 0 = the generic path
+int lean_mode(const gpemsr_igemm_desc_t& d, int block_n) {
+  if (d.gn_sums || d.row_max_out || d.row_max || d.row_sum || d.row_div || d.pixel_shuffle || d.phase_cols || d.out_nchw || d.out_rowmajor ||
+      d.bias_per_row || d.act == GPEMSR_ACT_EXP || d.n_cols % block_n != 0) return 0;
+  if (d.patch_sums) return 2;
+  return (d.out_f32 || d.out_hi) ? 1 : 0;
 }
+bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n) { return lean_mode(d, block_n) == 1; }
 
-template <int BLOCK_N, int SPLIT, bool LEAN = false>
+template <int BLOCK_N, int SPLIT, int LEAN = 0>
 int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
-  if constexpr (!LEAN) {
-    if (lean_epilogue(d, BLOCK_N)) return launch_fused<BLOCK_N, SPLIT, true>(op, d, smem_bytes, s);
+  if constexpr (LEAN == 0) {
+    const int mode = lean_mode(d, BLOCK_N);
+    if (mode == 1) return launch_fused<BLOCK_N, SPLIT, 1>(op, d, smem_bytes, s);
+    if constexpr (BLOCK_N == 64 && SPLIT == 1) {
+      if (mode == 2) return launch_fused<BLOCK_N, SPLIT, 2>(op, d, smem_bytes, s);       // VGG conv1_2 of the second image
+    }
   }
   using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
@@ -561,10 +570,10 @@ size_t plan_dyfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n
   return (size_t)op.nstage * stage_bytes + 1024;
 }
 
-template <int BLOCK_N, int SPLIT, bool LEAN = false>
+template <int BLOCK_N, int SPLIT, int LEAN = 0>
 int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
-  if constexpr (!LEAN) {
-    if (lean_epilogue(d, BLOCK_N)) return launch_dyfuse<BLOCK_N, SPLIT, true>(op, d, smem_bytes, s);
+  if constexpr (LEAN == 0) {
+    if (lean_epilogue(d, BLOCK_N)) return launch_dyfuse<BLOCK_N, SPLIT, 1>(op, d, smem_bytes, s);
   }
   using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
