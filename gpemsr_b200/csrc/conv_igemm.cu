@@ -21,9 +21,10 @@ namespace {
 // GroupNorm sums, patch correlation, softmax row statistics, exp, PixelShuffle, phase scatter, NCHW / row-major stores, per-row
 // bias, partial column tiles -- so that the narrow kernels, whose epilogue warps are ISSUE bound (~600 instructions per thread and
 // tile through the generic path), run the plain scale / bias / activation / residual / store path only.
-template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic, 1 = plain, 2 = plain + patch correlation (VGG mask)
+template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic, 1 = plain, 2 = plain + patch correlation (VGG mask),
+                                                             //       3 = plain, partial column tiles and row-major stores allowed (the tap GEMMs)
 struct EpiConv {
-  static constexpr bool GEN = LEAN == 0, PATCH = LEAN != 1;
+  static constexpr bool GEN = LEAN == 0, PATCH = LEAN == 0 || LEAN == 2, ROWM = LEAN == 0 || LEAN == 3, FULLCOLS = LEAN == 1 || LEAN == 2;
   Geom ag, og;
   int n_cols;
   float scale;
@@ -160,7 +161,7 @@ struct EpiConv {
   __device__ __forceinline__ void chunk(State& st, const uint32_t (&r)[CHUNK], const float (&bv)[CHUNK], const uint4 (&po)[CHUNK / 8],
                                         int col0, long long rel) const {
     float f[CHUNK];
-    const bool full = !GEN || col0 + CHUNK <= n_cols;
+    const bool full = FULLCOLS || col0 + CHUNK <= n_cols;
     // v = scale * acc + bias
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), bv[j]);
@@ -229,7 +230,7 @@ struct EpiConv {
         }
       }
     }
-    if (GEN && out_rowmajor) {
+    if (ROWM && out_rowmajor) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 4)
         *reinterpret_cast<float4*>(out_rowmajor + rel * ld + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -270,7 +271,7 @@ struct EpiConv {
     } else {
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
-        if (GEN && col0 + 8 * g >= n_cols) break;
+        if (!FULLCOLS && col0 + 8 * g >= n_cols) break;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = f[8 * g + j];
@@ -307,7 +308,7 @@ struct EpiConv {
 #pragma unroll 1
     for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
       const int col0 = n_tile * BLOCK_N + c0;
-      const bool work = (st.valid || (GEN && gn_sums)) && (!GEN || col0 < n_cols);
+      const bool work = (st.valid || (GEN && gn_sums)) && (FULLCOLS || col0 < n_cols);
       float bv[CHUNK];
       uint4 po[CHUNK / 8];
       if (work) {
@@ -510,10 +511,13 @@ void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
 }
 
 // the plain epilogue (EpiConv<..., LEAN>): scale, per-column bias, ReLU / LeakyReLU, residual, fp32 / plane stores of whole column
-// tiles (mode 1); the same plus the patch correlation of the VGG mask branch (mode 2); 0 = the generic path
+// tiles (mode 1); the same plus the patch correlation of the VGG mask branch (mode 2); plain stores with any column
+// count / row-major (mode 3); 0 = the generic path
 int lean_mode(const gpemsr_igemm_desc_t& d, int block_n) {
-  if (d.gn_sums || d.row_max_out || d.row_max || d.row_sum || d.row_div || d.pixel_shuffle || d.phase_cols || d.out_nchw || d.out_rowmajor ||
-      d.bias_per_row || d.act == GPEMSR_ACT_EXP || d.n_cols % block_n != 0) return 0;
+  if (d.gn_sums || d.row_max_out || d.row_max || d.row_sum || d.row_div || d.pixel_shuffle || d.phase_cols || d.out_nchw ||
+      d.bias_per_row || d.act == GPEMSR_ACT_EXP) return 0;
+  if (d.out_rowmajor || d.n_cols % block_n != 0)      // partial column tiles / row-major stores: the tap GEMMs of the few-output convs
+    return (!d.patch_sums && (d.out_f32 || d.out_hi || d.out_rowmajor)) ? 3 : 0;
   if (d.patch_sums) return 2;
   return (d.out_f32 || d.out_hi) ? 1 : 0;
 }
@@ -527,6 +531,7 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
     if constexpr (BLOCK_N == 64 && SPLIT == 1) {
       if (mode == 2) return launch_fused<BLOCK_N, SPLIT, 2>(op, d, smem_bytes, s);       // VGG conv1_2 of the second image
     }
+    if (mode == 3) return launch_fused<BLOCK_N, SPLIT, 3>(op, d, smem_bytes, s);
   }
   using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
@@ -573,7 +578,9 @@ size_t plan_dyfuse(gemm::Operands& op, const gpemsr_igemm_desc_t& d, int block_n
 template <int BLOCK_N, int SPLIT, int LEAN = 0>
 int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t smem_bytes, cudaStream_t s) {
   if constexpr (LEAN == 0) {
-    if (lean_epilogue(d, BLOCK_N)) return launch_dyfuse<BLOCK_N, SPLIT, 1>(op, d, smem_bytes, s);
+    const int mode = lean_mode(d, BLOCK_N);
+    if (mode == 1) return launch_dyfuse<BLOCK_N, SPLIT, 1>(op, d, smem_bytes, s);
+    if (mode == 3) return launch_dyfuse<BLOCK_N, SPLIT, 3>(op, d, smem_bytes, s);
   }
   using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
