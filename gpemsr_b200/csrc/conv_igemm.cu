@@ -22,9 +22,11 @@ namespace {
 // bias, partial column tiles -- so that the narrow kernels, whose epilogue warps are ISSUE bound (~600 instructions per thread and
 // tile through the generic path), run the plain scale / bias / activation / residual / store path only.
 template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic, 1 = plain, 2 = plain + patch correlation (VGG mask),
-                                                             //       3 = plain, partial column tiles and row-major stores allowed (the tap GEMMs)
+                                                             //       3 = plain, partial column tiles and row-major stores allowed (the tap GEMMs),
+                                                             //       4 = plain + the parity-phase scatter of the merged ConvTranspose2d GEMMs
 struct EpiConv {
-  static constexpr bool GEN = LEAN == 0, PATCH = LEAN == 0 || LEAN == 2, ROWM = LEAN == 0 || LEAN == 3, FULLCOLS = LEAN == 1 || LEAN == 2;
+  static constexpr bool GEN = LEAN == 0, PATCH = LEAN == 0 || LEAN == 2, ROWM = LEAN == 0 || LEAN == 3, FULLCOLS = LEAN == 1 || LEAN == 2 || LEAN == 4,
+                        PHASE = LEAN == 0 || LEAN == 4;
   Geom ag, og;
   int n_cols;
   float scale;
@@ -259,7 +261,7 @@ struct EpiConv {
           }
         }
       }
-    } else if (GEN && phase_cols) {    // the four parity phases of a ConvTranspose2d side by side along the columns
+    } else if (PHASE && phase_cols) {  // the four parity phases of a ConvTranspose2d side by side along the columns
       const int ph = col0 / phase_cols, ch = col0 - ph * phase_cols;
 #pragma unroll
       for (int g = 0; g < CHUNK / 8; ++g) {
@@ -371,12 +373,14 @@ struct EpiConv {
   }
 };
 
-bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n);
+int lean_mode(const gpemsr_igemm_desc_t& d, int block_n);
 
 template <int BLOCK_N, int BLOCK_K, int SPLIT, int NSTAGE, int LEAN = 0>
 int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t s) {
-  if constexpr (LEAN == 0 && BLOCK_N >= 64 && BLOCK_N <= 128) {
-    if (lean_epilogue(d, BLOCK_N)) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 1>(op, d, s);
+  if constexpr (LEAN == 0 && BLOCK_N >= 64) {
+    const int mode = lean_mode(d, BLOCK_N);
+    if (mode == 1) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 1>(op, d, s);
+    if (mode == 4) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 4>(op, d, s);
   }
   using Cfg = gemm::Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
   using Epi = EpiConv<BLOCK_N, false, LEAN>;
@@ -514,8 +518,10 @@ void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
 // tiles (mode 1); the same plus the patch correlation of the VGG mask branch (mode 2); plain stores with any column
 // count / row-major (mode 3); 0 = the generic path
 int lean_mode(const gpemsr_igemm_desc_t& d, int block_n) {
-  if (d.gn_sums || d.row_max_out || d.row_max || d.row_sum || d.row_div || d.pixel_shuffle || d.phase_cols || d.out_nchw ||
+  if (d.gn_sums || d.row_max_out || d.row_max || d.row_sum || d.row_div || d.pixel_shuffle || d.out_nchw ||
       d.bias_per_row || d.act == GPEMSR_ACT_EXP) return 0;
+  if (d.phase_cols)                                   // merged ConvTranspose2d phases, whole 8-channel cells per phase
+    return (d.phase_cols % 32 == 0 && d.n_cols % block_n == 0 && !d.patch_sums && !d.out_rowmajor && (d.out_f32 || d.out_hi)) ? 4 : 0;
   if (d.out_rowmajor || d.n_cols % block_n != 0)      // partial column tiles / row-major stores: the tap GEMMs of the few-output convs
     return (!d.patch_sums && (d.out_f32 || d.out_hi || d.out_rowmajor)) ? 3 : 0;
   if (d.patch_sums) return 2;
