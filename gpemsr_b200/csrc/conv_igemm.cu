@@ -21,12 +21,13 @@ namespace {
 // GroupNorm sums, patch correlation, softmax row statistics, exp, PixelShuffle, phase scatter, NCHW / row-major stores, per-row
 // bias, partial column tiles -- so that the narrow kernels, whose epilogue warps are ISSUE bound (~600 instructions per thread and
 // tile through the generic path), run the plain scale / bias / activation / residual / store path only.
-template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic, 1 = plain, 2 = plain + patch correlation (VGG mask),
-                                                             //       3 = plain, partial column tiles and row-major stores allowed (the tap GEMMs),
-                                                             //       4 = plain + the parity-phase scatter of the merged ConvTranspose2d GEMMs
-struct EpiConv {
-  static constexpr bool GEN = LEAN == 0, PATCH = LEAN == 0 || LEAN == 2, ROWM = LEAN == 0 || LEAN == 3, FULLCOLS = LEAN == 1 || LEAN == 2 || LEAN == 4,
-                        PHASE = LEAN == 0 || LEAN == 4;
+template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic; else bit 0 set + the features that stay enabled:
+struct EpiConv {                                             //   2 patch correlation (VGG mask), 4 partial column tiles / row-major
+  static constexpr bool GEN = LEAN == 0;                     //   stores (tap GEMMs), 8 parity-phase scatter (merged ConvTranspose2d),
+  static constexpr bool PATCH = GEN || (LEAN & 2);           //   16 fused softmax (row max / exp / row sum / row division)
+  static constexpr bool ROWM = GEN || (LEAN & 4), FULLCOLS = !GEN && !(LEAN & 4);
+  static constexpr bool PHASE = GEN || (LEAN & 8);
+  static constexpr bool SOFTMAX = GEN || (LEAN & 16);
   Geom ag, og;
   int n_cols;
   float scale;
@@ -167,14 +168,14 @@ struct EpiConv {
     // v = scale * acc + bias
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) f[j] = fmaf(scale, __uint_as_float(r[j]), bv[j]);
-    if (GEN && row_max_out) {          // softmax pre-pass: nothing is stored
+    if (SOFTMAX && row_max_out) {      // softmax pre-pass: nothing is stored
       float m = st.r_max;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (full || col0 + j < n_cols) m = fmaxf(m, f[j]);
       st.r_max = m;
       return;
     }
-    if (GEN && row_div) {
+    if (SOFTMAX && row_div) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] *= st.r_inv;
     }
@@ -184,7 +185,7 @@ struct EpiConv {
     } else if (act == GPEMSR_ACT_LRELU) {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * slope;
-    } else if (GEN && act == GPEMSR_ACT_EXP) {
+    } else if (SOFTMAX && act == GPEMSR_ACT_EXP) {
       // exp(v - max) = 2^(v * log2(e) - max * log2(e)): one FFMA + MUFU.EX2 per element (relative error ~2^-22; the arguments are
       // <= ~0, so no overflow; expf() costs ~4x the instructions and this epilogue is what bounds the scores GEMM)
       const float sub2 = st.r_sub * 1.4426950408889634f;
@@ -195,7 +196,7 @@ struct EpiConv {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) if (col0 + j >= n_cols) f[j] = 0.f;
     }
-    if (GEN && row_sum) {
+    if (SOFTMAX && row_sum) {
       float a = 0.f;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) a += f[j];
@@ -301,12 +302,12 @@ struct EpiConv {
         st.orow = place_row(og, st.img, Y, X);
         const long long Wo = (long long)up * ag.w, Ho = (long long)up * ag.h;
         st.nchw0 = ((long long)st.img * nchw_c * Ho + Y) * Wo + X;
-        if (GEN && row_max) st.r_sub = __ldg(row_max + rel);
-        if (GEN && row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
+        if (SOFTMAX && row_max) st.r_sub = __ldg(row_max + rel);
+        if (SOFTMAX && row_div) st.r_inv = 1.0f / __ldg(row_div + rel);
       }
     }
     constexpr int CHUNK = (SPAN >= 32 && BLOCK_N >= 128) ? 32 : 16;     // the narrow kernels run 18 warps: 16 columns at a time fit their registers
-    const bool row_stats = GEN && (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
+    const bool row_stats = SOFTMAX && (row_max_out || row_sum) && n_tile + (int)gridDim.y >= n_tiles;      // (evaluated before the loads below)
 #pragma unroll 1
     for (int c0 = part * SPAN; c0 < (part + 1) * SPAN; c0 += CHUNK) {
       const int col0 = n_tile * BLOCK_N + c0;
@@ -380,7 +381,10 @@ int launch(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, cudaStream_t 
   if constexpr (LEAN == 0 && BLOCK_N >= 64) {
     const int mode = lean_mode(d, BLOCK_N);
     if (mode == 1) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 1>(op, d, s);
-    if (mode == 4) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 4>(op, d, s);
+    if (mode == 9) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 9>(op, d, s);
+    if constexpr (BLOCK_N >= 128) {
+      if (mode == 17) return launch<BLOCK_N, BLOCK_K, SPLIT, NSTAGE, 17>(op, d, s);
+    }
   }
   using Cfg = gemm::Config<BLOCK_N, BLOCK_K, SPLIT, NSTAGE>;
   using Epi = EpiConv<BLOCK_N, false, LEAN>;
@@ -514,17 +518,19 @@ void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
   tm.use = 1;
 }
 
-// the plain epilogue (EpiConv<..., LEAN>): scale, per-column bias, ReLU / LeakyReLU, residual, fp32 / plane stores of whole column
-// tiles (mode 1); the same plus the patch correlation of the VGG mask branch (mode 2); plain stores with any column
-// count / row-major (mode 3); 0 = the generic path
+// the specialised epilogues (EpiConv<..., LEAN>, a feature mask): 1 = scale, per-column bias, ReLU / LeakyReLU, residual, fp32 /
+// plane stores of whole column tiles; 3 = + patch correlation (VGG mask); 5 = + partial column tiles / row-major stores; 9 = +
+// parity-phase scatter; 17 = + fused softmax; 0 = the generic path
 int lean_mode(const gpemsr_igemm_desc_t& d, int block_n) {
-  if (d.gn_sums || d.row_max_out || d.row_max || d.row_sum || d.row_div || d.pixel_shuffle || d.out_nchw ||
-      d.bias_per_row || d.act == GPEMSR_ACT_EXP) return 0;
-  if (d.phase_cols)                                   // merged ConvTranspose2d phases, whole 8-channel cells per phase
-    return (d.phase_cols % 32 == 0 && d.n_cols % block_n == 0 && !d.patch_sums && !d.out_rowmajor && (d.out_f32 || d.out_hi)) ? 4 : 0;
-  if (d.out_rowmajor || d.n_cols % block_n != 0)      // partial column tiles / row-major stores: the tap GEMMs of the few-output convs
-    return (!d.patch_sums && (d.out_f32 || d.out_hi || d.out_rowmajor)) ? 3 : 0;
-  if (d.patch_sums) return 2;
+  if (d.gn_sums || d.pixel_shuffle || d.out_nchw || d.bias_per_row) return 0;
+  const bool softmax = d.row_max_out || d.row_max || d.row_sum || d.row_div || d.act == GPEMSR_ACT_EXP;
+  const bool partial = d.out_rowmajor || d.n_cols % block_n != 0;
+  const int special = (softmax ? 1 : 0) + (partial ? 1 : 0) + (d.phase_cols ? 1 : 0) + (d.patch_sums ? 1 : 0);
+  if (special > 1) return 0;                          // one special feature at a time has a specialised epilogue
+  if (softmax) return 17;                             // attention GEMMs: row-max pre-pass, scores + exp + row sums, P v^T / row sum
+  if (d.phase_cols) return (d.phase_cols % 32 == 0 && (d.out_f32 || d.out_hi)) ? 9 : 0;      // merged ConvTranspose2d phases, whole cells per phase
+  if (partial) return (d.out_f32 || d.out_hi || d.out_rowmajor) ? 5 : 0;                      // the tap GEMMs of the few-output convs
+  if (d.patch_sums) return 3;
   return (d.out_f32 || d.out_hi) ? 1 : 0;
 }
 bool lean_epilogue(const gpemsr_igemm_desc_t& d, int block_n) { return lean_mode(d, block_n) == 1; }
@@ -535,9 +541,9 @@ int launch_fused(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t 
     const int mode = lean_mode(d, BLOCK_N);
     if (mode == 1) return launch_fused<BLOCK_N, SPLIT, 1>(op, d, smem_bytes, s);
     if constexpr (BLOCK_N == 64 && SPLIT == 1) {
-      if (mode == 2) return launch_fused<BLOCK_N, SPLIT, 2>(op, d, smem_bytes, s);       // VGG conv1_2 of the second image
+      if (mode == 3) return launch_fused<BLOCK_N, SPLIT, 3>(op, d, smem_bytes, s);       // VGG conv1_2 of the second image
     }
-    if (mode == 3) return launch_fused<BLOCK_N, SPLIT, 3>(op, d, smem_bytes, s);
+    if (mode == 5) return launch_fused<BLOCK_N, SPLIT, 5>(op, d, smem_bytes, s);
   }
   using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
@@ -586,7 +592,7 @@ int launch_dyfuse(const gemm::Operands& op, const gpemsr_igemm_desc_t& d, size_t
   if constexpr (LEAN == 0) {
     const int mode = lean_mode(d, BLOCK_N);
     if (mode == 1) return launch_dyfuse<BLOCK_N, SPLIT, 1>(op, d, smem_bytes, s);
-    if (mode == 3) return launch_dyfuse<BLOCK_N, SPLIT, 3>(op, d, smem_bytes, s);
+    if (mode == 5) return launch_dyfuse<BLOCK_N, SPLIT, 5>(op, d, smem_bytes, s);
   }
   using Epi = EpiConv<BLOCK_N, SPLIT == 3, LEAN>;
   Epi e;
