@@ -56,7 +56,6 @@ SIGNATURES = {
     'gpemsr_gn_stats': (_i, [_p, _i, _p, _p, _p]),
     'gpemsr_gn_scale_shift': (_i, [_p, _i, _p, _p, _i, _i, _i, C.c_double, _f, _p, _p]),
     'gpemsr_affine_act': (_i, [_p, _i, _p, _p, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
-    'gpemsr_gn_affine_act': (_i, [_p, _i, _p, _p, _i, _p, _p, _i, C.c_double, _f, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     'gpemsr_softmax_cells_blocked': (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     'gpemsr_border_phase_conv': (_i, [_p, _i, _p, _p, _p, _i, _p, _p]),
     'gpemsr_add_bilinear_base': (_i, [_p, _i, _i, _i, _i, _p, _p]),

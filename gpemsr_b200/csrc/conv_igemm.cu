@@ -961,59 +961,38 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int c, Geom g, doub
   }
 }
 
-// GroupNorm statistics -> scale / shift of one channel: the arithmetic of gn_scale_shift_kernel, shared with the fused kernel
-struct GnArgs {
-  const double* sums;          // nullptr: scale / shift come from `ss`
-  int per_group, groups;
-  const float *gamma, *beta;
-  double count;
-  float eps;
-};
-__device__ __forceinline__ float2 gn_scale_shift_of(const GnArgs& gn, int img, int ch, int c) {
-  const int cpg = c / gn.groups, g0 = (ch / cpg) * cpg;
-  double s = 0, q = 0;
-  if (gn.per_group) {
-    s = gn.sums[((size_t)img * gn.groups + ch / cpg) * 2]; q = gn.sums[((size_t)img * gn.groups + ch / cpg) * 2 + 1];
-  } else {
-    for (int j = 0; j < cpg; ++j) { s += gn.sums[((size_t)img * c + g0 + j) * 2]; q += gn.sums[((size_t)img * c + g0 + j) * 2 + 1]; }
-  }
-  const double cnt = gn.count * cpg, mean = s / cnt;
-  double var = q / cnt - mean * mean;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)gn.eps));
-  const float sc = gn.gamma[ch] * rstd;
-  return make_float2(sc, gn.beta[ch] - (float)mean * sc);
-}
-
 __global__ void gn_scale_shift_kernel(const double* __restrict__ sums, int per_group, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, int n, int c, int groups, double count, float eps,
                                       float* __restrict__ ss) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * c) return;
-  GnArgs gn{sums, per_group, groups, gamma, beta, count, eps};
-  const float2 r = gn_scale_shift_of(gn, t / c, t % c, c);
-  ss[(size_t)t * 2] = r.x;
-  ss[(size_t)t * 2 + 1] = r.y;
+  const int img = t / c, ch = t % c, cpg = c / groups, g0 = (ch / cpg) * cpg;
+  double s = 0, q = 0;
+  if (per_group) {
+    s = sums[((size_t)img * groups + ch / cpg) * 2]; q = sums[((size_t)img * groups + ch / cpg) * 2 + 1];
+  } else {
+    for (int j = 0; j < cpg; ++j) { s += sums[((size_t)img * c + g0 + j) * 2]; q += sums[((size_t)img * c + g0 + j) * 2 + 1]; }
+  }
+  const double cnt = count * cpg, mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[ch] * rstd;
+  ss[(size_t)t * 2] = sc;
+  ss[(size_t)t * 2 + 1] = beta[ch] - (float)mean * sc;
 }
 
-// y = act(x * scale + shift) (+ residual); re-rowed into `og` when it differs from `g`.  With gn.sums the per-(image, channel) scale
-// and shift are derived from the GroupNorm sums by the first 8 threads of the block (a block = one 8-channel cell of one image):
-// the separate gn_scale_shift launch (38 per forward) is gone.
-__global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, const float* __restrict__ ss, GnArgs gn, int act, float slope,
+// y = act(x * scale + shift) (+ residual); re-rowed into `og` when it differs from `g`
+__global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, const float* __restrict__ ss, int act, float slope,
                                   const float* __restrict__ residual, Geom og, float* __restrict__ out_f32,
                                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_nchw) {
   // grid: x = pixels of one image, y = (img, cell) -- the kernel is HBM bound only if the index arithmetic stays out of the way:
   // the flat (img, cell, pixel) index of round 1 cost three 64-bit divisions per 64 bytes moved
   const unsigned hw = (unsigned)g.h * (unsigned)g.w;
   const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hw) return;
   const int cells = (c + 7) / 8;
   const int cc = (int)(blockIdx.y % (unsigned)cells), img = (int)(blockIdx.y / (unsigned)cells);
-  __shared__ float2 s_ss[8];
-  if (gn.sums) {
-    if (threadIdx.x < 8 && cc * 8 + (int)threadIdx.x < c) s_ss[threadIdx.x] = gn_scale_shift_of(gn, img, cc * 8 + threadIdx.x, c);
-    __syncthreads();
-  }
-  if (p >= hw) return;
   const int y = (int)(p / (unsigned)g.w), xx = (int)(p - (unsigned)y * (unsigned)g.w);
   const size_t cell = ((size_t)cc * g.rows_alloc + place_row(g, img, y, xx)) * 8;
   const float4 a = *reinterpret_cast<const float4*>(x + cell), b = *reinterpret_cast<const float4*>(x + cell + 4);
@@ -1021,8 +1000,8 @@ __global__ void affine_act_kernel(const float* __restrict__ x, int c, Geom g, co
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = cc * 8 + j;
-    if ((ss || gn.sums) && ch < c) {
-      const float2 s2 = gn.sums ? s_ss[j] : __ldg(reinterpret_cast<const float2*>(ss) + (size_t)img * c + ch);
+    if (ss && ch < c) {
+      const float2 s2 = __ldg(reinterpret_cast<const float2*>(ss) + (size_t)img * c + ch);
       v[j] = fmaf(v[j], s2.x, s2.y);
     }
     v[j] = ch < c ? apply_act(v[j], act, slope) : 0.f;
@@ -1490,28 +1469,8 @@ int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const f
   const long long hw = (long long)g->h * g->w, planes = (long long)g->n * ((c + 7) / 8);
   if (hw >= (1LL << 31) || planes > 65535) return set_error(GPEMSR_ERR_BAD_SHAPE, "affine_act: %lld pixels x %lld (image, cell) planes exceed the grid", hw, planes);
   affine_act_kernel<<<dim3((unsigned)((hw + 255) / 256), (unsigned)planes), 256, 0, (cudaStream_t)stream>>>(
-      x_f32, c, to_geom(*g), scale_shift, GnArgs{}, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+      x_f32, c, to_geom(*g), scale_shift, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
       out_nchw);
-  GPEMSR_LAUNCH_OK("affine_act_kernel");
-  return GPEMSR_OK;
-}
-
-int gpemsr_gn_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const double* sums, int sums_per_group, const float* gamma,
-                         const float* beta, int groups, double count_per_channel, float eps, int act, float slope,
-                         const float* residual, const gpemsr_geom_t* og, float* out_f32, void* out_hi, void* out_lo,
-                         float* out_nchw, gpemsr_stream_t stream) {
-  using namespace gpemsr;
-  int rc = check_device_current();
-  if (rc != GPEMSR_OK) return rc;
-  if (!x_f32 || !g || !og || c <= 0 || !sums || !gamma || !beta || groups <= 0 || c % groups)
-    return set_error(GPEMSR_ERR_BAD_SHAPE, "gn_affine_act: bad arguments (c=%d groups=%d)", c, groups);
-  if ((rc = check_geom(*g, "gn_affine_act(in)")) != GPEMSR_OK || (rc = check_geom(*og, "gn_affine_act(out)")) != GPEMSR_OK) return rc;
-  if (g->n != og->n || g->h != og->h || g->w != og->w) return set_error(GPEMSR_ERR_BAD_SHAPE, "gn_affine_act: geometries differ in shape");
-  const long long hw = (long long)g->h * g->w, planes = (long long)g->n * ((c + 7) / 8);
-  if (hw >= (1LL << 31) || planes > 65535) return set_error(GPEMSR_ERR_BAD_SHAPE, "gn_affine_act: %lld pixels x %lld (image, cell) planes exceed the grid", hw, planes);
-  GnArgs gn{sums, sums_per_group, groups, gamma, beta, count_per_channel, eps};
-  affine_act_kernel<<<dim3((unsigned)((hw + 255) / 256), (unsigned)planes), 256, 0, (cudaStream_t)stream>>>(
-      x_f32, c, to_geom(*g), nullptr, gn, act, slope, residual, to_geom(*og), out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_nchw);
   GPEMSR_LAUNCH_OK("affine_act_kernel");
   return GPEMSR_OK;
 }

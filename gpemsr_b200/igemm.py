@@ -479,12 +479,12 @@ def group_norm_act(x, gamma, beta, scratch, out, act=ACT_NONE, slope=0.0, residu
     st = _lib.stream_ptr()
     if not fused_stats:
         _lib.check(L.gpemsr_gn_stats(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.sums), st))
-    # scale / shift are derived inside the apply kernel (one launch instead of gn_scale_shift + affine_act)
-    _lib.check(L.gpemsr_gn_affine_act(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.sums), int(fused_stats), _lib.ptr(gamma),
-                                      _lib.ptr(beta), groups, float(x.geom.h * x.geom.w), eps, act, slope, _lib.ptr(residual),
-                                      C.byref(og), _lib.ptr(out.f32) if out_f32 else None,
-                                      _lib.ptr(out.hi) if out_planes else None, _lib.ptr(out.lo) if out_planes else None,
-                                      _lib.ptr(out_nchw), st))
+    _lib.check(L.gpemsr_gn_scale_shift(_lib.ptr(scratch.sums), int(fused_stats), _lib.ptr(gamma), _lib.ptr(beta), x.geom.n, x.c,
+                                       groups, float(x.geom.h * x.geom.w), eps, _lib.ptr(scratch.ss), st))
+    _lib.check(L.gpemsr_affine_act(_lib.ptr(x.f32), x.c, C.byref(g), _lib.ptr(scratch.ss), act, slope, _lib.ptr(residual),
+                                   C.byref(og), _lib.ptr(out.f32) if out_f32 else None,
+                                   _lib.ptr(out.hi) if out_planes else None, _lib.ptr(out.lo) if out_planes else None,
+                                   _lib.ptr(out_nchw), st))
 
 
 def softmax_cells_blocked(s_cells, t, rows_alloc, t_pad, scratch, p_hi, p_lo):

@@ -254,12 +254,6 @@ GPEMSR_API int gpemsr_affine_act(const float* x_f32, int c, const gpemsr_geom_t*
                       float* out_f32, void* out_hi, void* out_lo, float* out_nchw /* [n,c,h,w] or NULL */,
                       gpemsr_stream_t stream);
 
-/* gn_scale_shift + affine_act in ONE launch: every block (one 8-channel cell of one image) derives its scale / shift from the sums. */
-GPEMSR_API int gpemsr_gn_affine_act(const float* x_f32, int c, const gpemsr_geom_t* g, const double* sums, int sums_per_group,
-                         const float* gamma, const float* beta, int groups, double count_per_channel, float eps,
-                         int act, float slope, const float* residual, const gpemsr_geom_t* og,
-                         float* out_f32, void* out_hi, void* out_lo, float* out_nchw, gpemsr_stream_t stream);
-
 /* softmax over the keys of attention scores (model/blocks.py:76) stored as K8-blocked fp32 cells [t_pad/8][rows_alloc][8] (the
  * igemm out_f32 format with keys as "channels"): coalesced without a transpose; probabilities come out as K8-blocked bf16 A
  * operand planes [t_pad/8][t_pad][8] (hi, lo).  scratch: 2*t*(1+16) floats. */
