@@ -17,10 +17,11 @@ namespace {
 // PAIR: the accumulator is split over the column ranges (c, c + BLOCK_N) -- the paired-N MMAs of the tap-fused / dy-fused kernels in
 // the fp32-faithful split keep a_hi * w_lo apart from a_hi * w_hi + a_lo * w_hi; the epilogue sums them.  A compile-time property
 // of the launch: the kernels that never pair (the streaming kernel, every single-pass launch) carry no second TMEM load.
-// LEAN: a compile-time promise (made by the host dispatch, lean_epilogue()) that none of the special epilogues is active -- no
-// GroupNorm sums, patch correlation, softmax row statistics, exp, PixelShuffle, phase scatter, NCHW / row-major stores, per-row
-// bias, partial column tiles -- so that the narrow kernels, whose epilogue warps are ISSUE bound (~600 instructions per thread and
-// tile through the generic path), run the plain scale / bias / activation / residual / store path only.
+// LEAN: a compile-time promise made by the host dispatch (lean_mode()) about which special epilogues can be active.  The generic
+// epilogue keeps GroupNorm sums, patch correlation, softmax row statistics, exp, PixelShuffle, phase scatter, NCHW / row-major
+// stores, per-row bias and partial column tiles behind run-time branches: ~600 issued instructions per thread and tile, and the
+// epilogue warps of the narrow kernels are ISSUE bound (profiles/r02_tapfuse_roles.txt).  A specialised instantiation contains the
+// plain scale / bias / activation / residual / store path plus only the features its mask names.
 template <int BLOCK_N, bool PAIR = false, int LEAN = 0>      // LEAN: 0 = generic; else bit 0 set + the features that stay enabled:
 struct EpiConv {                                             //   2 patch correlation (VGG mask), 4 partial column tiles / row-major
   static constexpr bool GEN = LEAN == 0;                     //   stores (tap GEMMs), 8 parity-phase scatter (merged ConvTranspose2d),

@@ -659,7 +659,7 @@ gemm_ares_kernel(const __grid_constant__ Operands op, const __grid_constant__ Ep
 //     tap dy (rows [r0 + dy*wp + dx_min, +128 + dx_max - dx_min)); every tap then reads its operand from the same
 //     stage at a 16-byte row offset (the canonical layout has uniform 16-byte rows, so a shift is a start address).
 // A 3x3 convolution thus reads each activation row 3x instead of 9x and never re-reads weights: the wide-image 64-channel
-// layers go from L2-operand-bound to MMA/epilogue-bound.
+// layers go from L2-operand-bound to shared-memory-operand / epilogue bound.
 template <int BLOCK_N, int SPLIT, class Epi>
 __global__ void __launch_bounds__(64 + 32 * Epi::WARPS, 1)
 gemm_tapfuse_kernel(const __grid_constant__ Operands op, const __grid_constant__ Epi epi, const __grid_constant__ TmaMaps tm) {
