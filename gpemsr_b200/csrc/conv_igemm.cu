@@ -11,6 +11,7 @@
 #include "gemm_core.cuh"
 #include "act_layout.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -523,7 +524,8 @@ void maps_dyfuse(gemm::TmaMaps& tm, const gemm::Operands& op, int planes) {
 // plane stores of whole column tiles; 3 = + patch correlation (VGG mask); 5 = + partial column tiles / row-major stores; 9 = +
 // parity-phase scatter; 17 = + fused softmax; 0 = the generic path
 int lean_mode(const gpemsr_igemm_desc_t& d, int block_n) {
-  if (d.gn_sums || d.pixel_shuffle || d.out_nchw || d.bias_per_row) return 0;
+  static const int enabled = [] { const char* e = getenv("GPEMSR_LEAN"); return (e && e[0] == '0') ? 0 : 1; }();      // GPEMSR_LEAN=0: A/B, tests
+  if (!enabled || d.gn_sums || d.pixel_shuffle || d.out_nchw || d.bias_per_row) return 0;
   const bool softmax = d.row_max_out || d.row_max || d.row_sum || d.row_div || d.act == GPEMSR_ACT_EXP;
   const bool partial = d.out_rowmajor || d.n_cols % block_n != 0;
   const int special = (softmax ? 1 : 0) + (partial ? 1 : 0) + (d.phase_cols ? 1 : 0) + (d.patch_sums ? 1 : 0);

@@ -3,7 +3,8 @@
 The CTA-pair streaming GEMM (tcgen05.mma.cta_group::2, tensor-map operands) accumulates the same products in the same order as the
 cta_group::1 + multicast kernel, and the tensor-map / multi-slab / plain-epilogue forms of the tap-fused and dy-fused kernels only
 change how operands travel and which epilogue branches exist -- so every result must be BIT-identical to a run of the same
-library with GPEMSR_PAIR=0 GPEMSR_TMA=0 (the switches are read once per process: the reference run is a child process).
+library with GPEMSR_PAIR=0 GPEMSR_TMA=0 GPEMSR_LEAN=0 (the switches are read once per process: the reference run is a child
+process; GPEMSR_LEAN=0 sends every launch through the generic epilogue instead of its specialised instantiation).
 Also checks that the tensor-map path really ran here (maps built, none refused)."""
 import ctypes as C
 import os
@@ -29,6 +30,8 @@ CASES = [
     ('dyfuse_7x7', 2, 32, 64, 40, 7, dict(split=1, act=1)),           # SpyNet layer
     ('dyfuse_k128', 1, 128, 64, 40, 3, {}),                           # K > 64, N = 64: (k-slab, tap row) stages
     ('odd_tiles', 1, 128, 256, 19, 3, {}),                            # odd number of row tiles: the pair's surplus tile is discarded
+    ('convT_merged_phases', 2, 128, 64, 24, 3, dict(convT=True)),     # ConvTranspose2d as ONE 4-phase GEMM: phase-scatter epilogue
+    ('tap_gemm_36_columns', 1, 64, 4, 40, 3, dict(taps_gemm=True)),   # few-output conv: 1x1 GEMM with 9 * 4 columns (partial tile)
 ]
 
 
@@ -46,6 +49,19 @@ def run_cases():
         b = torch.randn(co, device='cuda', generator=gen)
         wt = G.Weights(w, 'conv', split=opt.get('split', 3), pixel_shuffle=bool(opt.get('ps')))
         kw = dict(split=opt.get('split', 3), bias=b, act=opt.get('act', G.ACT_NONE), slope=opt.get('slope', 0.0))
+        if opt.get('convT'):
+            wT = torch.randn(ci, co, 3, 3, device='cuda', generator=gen) * 0.05
+            wt = G.Weights(G.convT_merged_weight(wT), 'conv', taps='offsets01')
+            y = G.Act(G.Geom(n, 2 * s, 2 * s, True), co, 'cuda', f32=True)
+            G.igemm(x, wt, err, bias=b.repeat(4).contiguous(), out=y, up=2, phase_cols=co, out_f32=True)
+            out[name] = (y.hi.clone().cpu(), y.lo.clone().cpu(), y.f32.clone().cpu())
+            continue
+        if opt.get('taps_gemm'):
+            wt = G.Weights(G.taps_as_columns(w), 'conv')
+            cells = G.TapCells(g, co, 'cuda')
+            G.igemm(x, wt, err, out=cells, out_planes=False)
+            out[name] = (None, None, cells.f32.clone().cpu())
+            continue
         if opt.get('ps'):
             y = G.Act(G.Geom(n, 2 * s, 2 * s, True), co // 4, 'cuda', f32=False)
             G.igemm(x, wt, err, out=y, up=2, pixel_shuffle=True, out_f32=False, **kw)
@@ -71,7 +87,7 @@ def test_pair_and_tensor_map_kernels_match_the_plain_kernels_bit_for_bit(cuda_de
     _lib.lib().gpemsr_tensor_map_stats(C.byref(built), C.byref(rej))
     assert built.value > 0 and rej.value == 0, (built.value, rej.value)          # the tensor-map path ran, the driver took every shape
     ref_file = str(tmp_path / 'ref.pt')
-    env = dict(os.environ, GPEMSR_PAIR='0', GPEMSR_TMA='0', PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, 'tests'))
+    env = dict(os.environ, GPEMSR_PAIR='0', GPEMSR_TMA='0', GPEMSR_LEAN='0', PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, 'tests'))
     code = ("import sys, torch; sys.path[:0] = [%r, %r]; import test_kernel_variants_gpu as T; "
             "torch.save(T.run_cases(), %r)" % (ROOT, os.path.join(ROOT, 'tests'), ref_file))
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
